@@ -1,0 +1,366 @@
+'''
+Flat scene description shared by the CUDA engine (through the C ABI in include/odw.h), the
+CPU oracle and the tests.  numpy structured dtypes below mirror the C structs byte for byte.
+
+What the reference does per segment — walk every optical group, every placement of it, every
+shell, every face, and ask OCC (reference freecad_elements/ray.py:328-432) — is replaced by a
+one-shot export: every face instance is written once, in WORLD coordinates, as a closed-form
+surface (plane / cylinder / cone / sphere / torus) plus its trimming region in (u, v) space.
+'''
+
+import numpy as np
+
+SURF_PLANE, SURF_CYLINDER, SURF_CONE, SURF_SPHERE, SURF_TORUS = 1, 2, 3, 4, 5
+TRIM_NONE, TRIM_UVBOX, TRIM_LOOPS = 0, 1, 2
+SEG_LINE, SEG_ARC = 1, 2
+OPT_MIRROR, OPT_LENS, OPT_GRATING, OPT_ABSORBER, OPT_VACUUM = 0, 1, 2, 3, 4
+OPTICAL_TYPES = ('Mirror', 'Lens', 'Grating', 'Absorber', 'Vacuum')
+GRATING_TYPES = ('Reflection', 'Transmission')
+SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED = 0, 1
+
+_KIND_ID = dict(plane=SURF_PLANE, cylinder=SURF_CYLINDER, cone=SURF_CONE, sphere=SURF_SPHERE,
+                torus=SURF_TORUS)
+
+FACE_DTYPE = np.dtype([
+  ('origin', '<f8', 3), ('xdir', '<f8', 3), ('ydir', '<f8', 3), ('zdir', '<f8', 3),
+  ('p0', '<f8'), ('p1', '<f8'),
+  ('uv_min', '<f8', 2), ('uv_max', '<f8', 2),
+  ('aabb_min', '<f8', 3), ('aabb_max', '<f8', 3),
+  ('kind', '<i4'), ('trim_kind', '<i4'), ('nsign', '<i4'), ('group', '<i4'),
+  ('shell', '<i4'), ('seg_first', '<i4'), ('seg_count', '<i4'), ('face_id', '<i4'),
+], align=True)
+SEG_DTYPE = np.dtype([('a', '<f8', 5), ('kind', '<i4'), ('pad', '<i4')], align=True)
+SHELL_DTYPE = np.dtype([
+  ('aabb_min', '<f8', 3), ('aabb_max', '<f8', 3),
+  ('face_first', '<i4'), ('face_count', '<i4'), ('group', '<i4'), ('pad', '<i4'),
+], align=True)
+GROUP_DTYPE = np.dtype([
+  ('refractive_index', '<f8'), ('reflectivity', '<f8'), ('absorption_length', '<f8'),
+  ('grating_lines_per_mm', '<f8'), ('grating_order', '<f8'), ('grating_orientation', '<f8', 3),
+  ('optical_type', '<i4'), ('record_hits', '<i4'), ('grating_type', '<i4'), ('pad', '<i4'),
+], align=True)
+
+assert FACE_DTYPE.itemsize == 224 and SEG_DTYPE.itemsize == 48
+assert SHELL_DTYPE.itemsize == 64 and GROUP_DTYPE.itemsize == 80
+
+TWO_PI = 2*np.pi
+
+
+class UnsupportedGeometry(ValueError):
+  'face cannot be expressed in closed form (needs the tessellation path)'
+
+
+# ------------------------------------------------------------------------------------------
+# pcurves -> trim segments
+
+def _curve_to_segs(curve, first, last, deflection=1e-7, out=None):
+  out = [] if out is None else out
+  kind = curve.kind
+  if kind == 'trimmed':
+    return _curve_to_segs(curve.basis, first, last, deflection, out)
+  if kind == 'line':
+    p0 = curve.p + first*curve.d
+    p1 = curve.p + last*curve.d
+    out.append((SEG_LINE, [p0[0], p0[1], p1[0], p1[1], 0.0]))
+    return out
+  if kind == 'circle':
+    alpha = np.arctan2(curve.dx[1], curve.dx[0])
+    sense = np.sign(curve.dx[0]*curve.dy[1]-curve.dx[1]*curve.dy[0])
+    span = last-first
+    a0 = alpha+first if sense > 0 else alpha-last
+    a0 = a0 % TWO_PI
+    span = min(span, TWO_PI)
+    out.append((SEG_ARC, [curve.p[0], curve.p[1], curve.r, a0, span]))
+    return out
+  # everything else: polyline fine enough that the chord error is below `deflection`
+  n = 32
+  while True:
+    t = np.linspace(first, last, n+1)
+    pts = curve.eval(t)
+    tm = (t[1:]+t[:-1])/2
+    mid = curve.eval(tm)
+    err = np.linalg.norm(mid-(pts[1:]+pts[:-1])/2, axis=-1).max()
+    if err < deflection or n >= 4096:
+      break
+    n *= 2
+  for a, b in zip(pts[:-1], pts[1:]):
+    out.append((SEG_LINE, [a[0], a[1], b[0], b[1], 0.0]))
+  return out
+
+
+def _segs_bbox(segs):
+  lo = np.array([np.inf, np.inf])
+  hi = -lo
+  for kind, a in segs:
+    if kind == SEG_LINE:
+      pts = np.array([[a[0], a[1]], [a[2], a[3]]])
+    else:
+      cu, cv, r, a0, span = a
+      angs = [a0, a0+span]
+      for k in range(-1, 6):
+        ang = k*np.pi/2
+        if a0 <= ang <= a0+span:
+          angs.append(ang)
+      angs = np.array(angs)
+      pts = np.stack([cu+r*np.cos(angs), cv+r*np.sin(angs)], axis=-1)
+    lo = np.minimum(lo, pts.min(axis=0))
+    hi = np.maximum(hi, pts.max(axis=0))
+  return lo, hi
+
+
+def _is_uvbox(segs, lo, hi, eps=1e-9):
+  'all segments are axis-aligned lines on the bounding rectangle and together cover its perimeter once'
+  total = 0.0
+  for kind, a in segs:
+    if kind != SEG_LINE:
+      return False
+    u0, v0, u1, v1 = a[:4]
+    if abs(u0-u1) < eps:
+      if not (abs(u0-lo[0]) < eps or abs(u0-hi[0]) < eps):
+        return False
+      total += abs(v1-v0)
+    elif abs(v0-v1) < eps:
+      if not (abs(v0-lo[1]) < eps or abs(v0-hi[1]) < eps):
+        return False
+      total += abs(u1-u0)
+    else:
+      return False
+  return abs(total-2*((hi[0]-lo[0])+(hi[1]-lo[1]))) < 1e-6*max(1.0, total)
+
+
+def point_in_segs(segs, u, v):
+  '''
+  Even-odd test of (u, v) against trim segments given as (kind, a) tuples or SEG_DTYPE rows:
+  count crossings of the half-line {(u', v): u' > u}.  numpy restatement used by tests/export;
+  the oracle (oracle/odw_oracle.c) and the CUDA kernel implement the same rule.
+  '''
+  crossings = 0
+  for s in segs:
+    kind, a = (s['kind'], s['a']) if isinstance(s, np.void) else s
+    if kind == SEG_LINE:
+      u0, v0, u1, v1 = a[:4]
+      if (v0 > v) != (v1 > v):
+        ux = u0 + (v-v0)*(u1-u0)/(v1-v0)
+        if ux > u:
+          crossings += 1
+    else:
+      cu, cv, r, a0, span = a[:5]
+      dv = v-cv
+      if abs(dv) < r:
+        h = np.sqrt(r*r-dv*dv)
+        for ux in (cu-h, cu+h):
+          if ux > u:
+            ang = np.arctan2(dv, ux-cu)
+            rel = (ang-a0) % TWO_PI
+            if rel <= span:
+              crossings += 1
+  return (crossings & 1) == 1
+
+
+# ------------------------------------------------------------------------------------------
+# face instance -> FACE_DTYPE row
+
+def _rigid(transform):
+  R = transform[:3, :3]
+  s = np.cbrt(abs(np.linalg.det(R)))
+  if abs(s-1) > 1e-9:
+    raise UnsupportedGeometry(f'non-rigid placement (scale {s}) is not supported')
+  return R, transform[:3, 3]
+
+
+def face_record(fi, transform, group, shell, face_id, segs_out):
+  '''
+  Convert a brep.FaceInstance (+ an extra world transform applied on the left) into a FACE_DTYPE
+  row; trim segments are appended to segs_out (list of (kind, a)).
+  '''
+  surf = fi.surface
+  if surf.kind not in _KIND_ID:
+    raise UnsupportedGeometry(f'surface kind {surf.kind!r} has no closed form')
+  R, T = _rigid(transform @ fi.transform)
+  f = np.zeros((), dtype=FACE_DTYPE)
+  f['origin'] = R @ surf.p + T
+  X, Y, Z = R @ surf.dx, R @ surf.dy, R @ surf.n
+  f['xdir'], f['ydir'], f['zdir'] = X, Y, Z
+  handed = 1 if np.dot(np.cross(X, Y), Z) > 0 else -1
+  f['nsign'] = (-1 if fi.reversed else 1)*handed
+  f['kind'] = _KIND_ID[surf.kind]
+  if surf.kind in ('cylinder', 'sphere'):
+    f['p0'] = surf.r
+  elif surf.kind == 'cone':
+    f['p0'], f['p1'] = surf.r, surf.angle
+  elif surf.kind == 'torus':
+    f['p0'], f['p1'] = surf.r, surf.r2
+  f['group'], f['shell'], f['face_id'] = group, shell, face_id
+
+  segs = []
+  for loop in fi.loops:
+    for curve, first, last in loop:
+      _curve_to_segs(curve, first, last, out=segs)
+  if not segs:
+    if surf.kind in ('sphere', 'torus'):
+      lo, hi = np.array([0.0, -np.pi/2 if surf.kind == 'sphere' else 0.0]), \
+               np.array([TWO_PI, np.pi/2 if surf.kind == 'sphere' else TWO_PI])
+      trim = TRIM_NONE
+    else:
+      raise UnsupportedGeometry('face without boundary on an unbounded surface')
+  else:
+    lo, hi = _segs_bbox(segs)
+    trim = TRIM_UVBOX if _is_uvbox(segs, lo, hi) else TRIM_LOOPS
+    if trim == TRIM_UVBOX:
+      full_u = abs((hi[0]-lo[0])-TWO_PI) < 1e-9
+      if surf.kind == 'sphere' and full_u and lo[1] < -np.pi/2+1e-9 and hi[1] > np.pi/2-1e-9:
+        trim = TRIM_NONE
+      if surf.kind == 'torus' and full_u and abs((hi[1]-lo[1])-TWO_PI) < 1e-9:
+        trim = TRIM_NONE
+  f['trim_kind'] = trim
+  f['uv_min'], f['uv_max'] = lo, hi
+  if trim == TRIM_LOOPS:
+    f['seg_first'], f['seg_count'] = len(segs_out), len(segs)
+    segs_out.extend(segs)
+  f['aabb_min'], f['aabb_max'] = _face_aabb(f)
+  return f
+
+
+def eval_face(f, u, v):
+  'world point(s) of FACE_DTYPE row f at parameters u, v'
+  u = np.asarray(u, dtype=float)[..., None]
+  v = np.asarray(v, dtype=float)[..., None]
+  O, X, Y, Z = f['origin'], f['xdir'], f['ydir'], f['zdir']
+  k = int(f['kind'])
+  if k == SURF_PLANE:
+    return O + u*X + v*Y
+  er = np.cos(u)*X + np.sin(u)*Y
+  if k == SURF_CYLINDER:
+    return O + f['p0']*er + v*Z
+  if k == SURF_CONE:
+    return O + (f['p0']+v*np.sin(f['p1']))*er + v*np.cos(f['p1'])*Z
+  if k == SURF_SPHERE:
+    return O + f['p0']*np.cos(v)*er + f['p0']*np.sin(v)*Z
+  if k == SURF_TORUS:
+    return O + (f['p0']+f['p1']*np.cos(v))*er + f['p1']*np.sin(v)*Z
+  raise ValueError(k)
+
+
+def _face_aabb(f, n=65):
+  lo, hi = f['uv_min'], f['uv_max']
+  k = int(f['kind'])
+  if k == SURF_PLANE:
+    uu, vv = np.meshgrid([lo[0], hi[0]], [lo[1], hi[1]])
+    pts = eval_face(f, uu, vv).reshape(-1, 3)
+    return pts.min(axis=0), pts.max(axis=0)
+  uu, vv = np.meshgrid(np.linspace(lo[0], hi[0], n), np.linspace(lo[1], hi[1], n))
+  pts = eval_face(f, uu, vv).reshape(-1, 3)
+  # sagitta of the sampling: a point between samples can stick out by R(1-cos(h/2))
+  hu = (hi[0]-lo[0])/(n-1)
+  rmax = {SURF_CYLINDER: f['p0'], SURF_SPHERE: f['p0'], SURF_TORUS: f['p0']+f['p1'],
+          SURF_CONE: abs(f['p0'])+max(abs(lo[1]), abs(hi[1]))*abs(np.sin(f['p1']))}[k]
+  pad = rmax*(1-np.cos(hu/2))
+  if k in (SURF_SPHERE, SURF_TORUS):
+    hv = (hi[1]-lo[1])/(n-1)
+    rv = f['p0'] if k == SURF_SPHERE else f['p1']
+    pad += rv*(1-np.cos(hv/2))
+  return pts.min(axis=0)-pad, pts.max(axis=0)+pad
+
+
+# ------------------------------------------------------------------------------------------
+
+class Scene:
+  '''
+  Immutable scene: numpy arrays laid out exactly like the C structs of include/odw.h plus the
+  names needed by the hit writer.
+  '''
+  def __init__(self, faces, segs, shells, groups, group_names, group_labels,
+               seq_offsets=None, seq_groups=None):
+    self.faces = np.ascontiguousarray(faces, dtype=FACE_DTYPE)
+    self.segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    self.shells = np.ascontiguousarray(shells, dtype=SHELL_DTYPE)
+    self.groups = np.ascontiguousarray(groups, dtype=GROUP_DTYPE)
+    self.group_names = list(group_names)
+    self.group_labels = list(group_labels)
+    self.seq_offsets = np.ascontiguousarray(seq_offsets if seq_offsets is not None else [0], dtype=np.int32)
+    self.seq_groups = np.ascontiguousarray(seq_groups if seq_groups is not None else [], dtype=np.int32)
+
+  @property
+  def n_seq_steps(self):
+    return len(self.seq_offsets)-1
+
+  def summary(self):
+    kinds = {v: k for k, v in _KIND_ID.items()}
+    from collections import Counter
+    c = Counter((kinds[int(f['kind'])], ('none', 'uvbox', 'loops')[int(f['trim_kind'])]) for f in self.faces)
+    return dict(faces=len(self.faces), segs=len(self.segs), shells=len(self.shells),
+                groups=len(self.groups), census={f'{k}/{t}': n for (k, t), n in sorted(c.items())})
+
+
+class SceneBuilder:
+  'collects face instances group by group, shell by shell'
+
+  def __init__(self):
+    self.faces, self.segs, self.shells, self.groups = [], [], [], []
+    self.group_names, self.group_labels = [], []
+    self.skipped = []          # (group, reason) for faces that need the tessellation path
+
+  def add_group(self, name, label, optical_type, refractive_index=1.0, reflectivity=1.0,
+                absorption_length=np.inf, record_hits=False, grating_type=0,
+                grating_lines_per_mm=1000.0, grating_order=1.0, grating_orientation=(0, 0, 1)):
+    g = np.zeros((), dtype=GROUP_DTYPE)
+    g['optical_type'] = (OPTICAL_TYPES.index(optical_type) if isinstance(optical_type, str)
+                         else optical_type)
+    g['refractive_index'], g['reflectivity'] = refractive_index, reflectivity
+    g['absorption_length'] = absorption_length
+    g['record_hits'] = int(bool(record_hits))
+    g['grating_type'] = (GRATING_TYPES.index(grating_type) if isinstance(grating_type, str)
+                         else grating_type)
+    g['grating_lines_per_mm'], g['grating_order'] = grating_lines_per_mm, grating_order
+    g['grating_orientation'] = grating_orientation
+    self.groups.append(g)
+    self.group_names.append(name)
+    self.group_labels.append(label)
+    return len(self.groups)-1
+
+  def add_shape(self, group, face_instances, transform):
+    '''
+    face_instances: brep.FaceInstance list of ONE shape; transform: 4x4 world matrix applied on top.
+    Faces are grouped into shells by FaceInstance.shell_key; like the reference
+    (`cachedShells(shape) or [shape]`, ray.py:345) faces outside any shell only count when the shape has
+    no shell at all.
+    '''
+    keys = []
+    for fi in face_instances:
+      if fi.shell_key not in keys:
+        keys.append(fi.shell_key)
+    if any(k is not None for k in keys):
+      keys = [k for k in keys if k is not None]
+    for key in keys:
+      shell_index = len(self.shells)
+      first = len(self.faces)
+      for fi in face_instances:
+        if fi.shell_key != key:
+          continue
+        try:
+          self.faces.append(face_record(fi, transform, group, shell_index, len(self.faces), self.segs))
+        except UnsupportedGeometry as e:
+          self.skipped.append((group, str(e)))
+      count = len(self.faces)-first
+      if count == 0:
+        continue
+      sh = np.zeros((), dtype=SHELL_DTYPE)
+      fa = self.faces[first:]
+      sh['aabb_min'] = np.min([f['aabb_min'] for f in fa], axis=0)
+      sh['aabb_max'] = np.max([f['aabb_max'] for f in fa], axis=0)
+      sh['face_first'], sh['face_count'], sh['group'] = first, count, group
+      self.shells.append(sh)
+
+  def build(self, sequence=None):
+    segs = np.zeros(len(self.segs), dtype=SEG_DTYPE)
+    for i, (kind, a) in enumerate(self.segs):
+      segs[i]['kind'] = kind
+      segs[i]['a'] = a
+    faces = np.array(self.faces, dtype=FACE_DTYPE) if self.faces else np.zeros(0, dtype=FACE_DTYPE)
+    shells = np.array(self.shells, dtype=SHELL_DTYPE) if self.shells else np.zeros(0, dtype=SHELL_DTYPE)
+    groups = np.array(self.groups, dtype=GROUP_DTYPE) if self.groups else np.zeros(0, dtype=GROUP_DTYPE)
+    seq_offsets, seq_groups = [0], []
+    for step in (sequence or []):
+      seq_groups.extend(step)
+      seq_offsets.append(len(seq_groups))
+    return Scene(faces, segs, shells, groups, self.group_names, self.group_labels, seq_offsets, seq_groups)
