@@ -1,0 +1,200 @@
+'''
+Host-side construction of the tabulated inverse-CDF sampler and the deterministic fan grid.
+
+Restates the NUMERIC mode of the reference sampler
+(reference distributions/random_number_generator.py:337-464 `_generateNumericScalarLambda` /
+`_lambdasFromSampled`) and the fan-grid quantile placement
+(reference distributions/points_by_density.py:25-38, random_number_generator.py:685-725).  The
+tables go to the device once per simulation (odw_source_create); the per-ray draw itself happens
+in the CUDA kernel.
+
+Differences to the reference, both deliberate:
+  * the analytic (sympy integrate + solve) mode is never used: the tabulated mode is the
+    reference's own fallback, gives the same distribution and is the only one that maps to a GPU;
+    all benchmark sources report 'numeric' anyway.
+  * a density without phi is detected symbolically and stored as ONE conditional row
+    (n_rows = 1) instead of 100 identical 100001-entry rows.
+'''
+
+import numpy as np
+import sympy as sy
+
+
+def parse_domain(text, default=(0.0, 1.0)):
+  'domain string "a, b" with sympy expressions (reference freecad_elements/common.py:293-361, happy path)'
+  try:
+    vals = [float(sy.sympify(d).evalf()) for d in str(text).split(',')]
+    if len(vals) != 2:
+      return tuple(default)
+    l1, l2 = vals
+    return (l2, l1) if l1 > l2 else (l1, l2)
+  except Exception:
+    return tuple(default)
+
+
+def odd_resolution(res):
+  'reference random_number_generator.py:330-334'
+  res = int(round(float(res)))
+  return res+1 if res % 2 == 0 else res
+
+
+def point_source_density(density, focal_length, scalar=False):
+  '''
+  Power density string of a point source -> (sympy expression, first variable name), restating
+  PointSourceProxy._rvArgs (reference freecad_elements/point_source.py:277-366): the area element
+  |sin(theta)| (finite focal length) or |r| (collimated) is multiplied in for the 2-D variable, and
+  r, x, y are substituted by their theta/phi (or r/phi) expressions.
+  '''
+  f = float(focal_length)
+  if np.isfinite(f):
+    if np.isclose(f, 0):
+      stripped = str(density)
+      for w in ('exp', 'arcsin', 'arccos', 'arctan2', 'arctan', 'arccot', 'arsinh', 'arcosh', 'artanh',
+                'arcoth', 'DiracDelta', 'Piecewise', 'Heaviside', 'True', 'False'):
+        stripped = stripped.replace(w, '')
+      for c in 'rxy':
+        if c in stripped:
+          raise ValueError(f'Variable {c} in power density expression {density} is forbidden if focal length is zero.')
+    if not scalar:
+      density = '('+str(density)+')*abs(sin(theta))'
+    fs = f'{abs(f):.8e}'
+    expr = (sy.sympify(density)
+            .subs('r', sy.sympify(f'(tan(theta)*{fs})'))
+            .subs('x', sy.sympify(f'(tan(theta)*cos(phi)*{fs})'))
+            .subs('y', sy.sympify(f'(tan(theta)*sin(phi)*{fs})')))
+    return expr, 'theta'
+  if not scalar:
+    density = '('+str(density)+')*abs(r)'
+  if 'theta' in str(density):
+    raise ValueError(f'Variable theta in power density expression {density} is forbidden if focal length is infinite.')
+  expr = (sy.sympify(density)
+          .subs('x', sy.sympify('(r*cos(phi))'))
+          .subs('y', sy.sympify('(r*sin(phi))')))
+  return expr, 'r'
+
+
+class SamplerTables:
+  '''
+  phi_cdf   [n_phi]            normalised marginal CDF of phi on edges linspace(phi_domain, n_phi)
+  first_cdf [n_rows, n_first]  normalised conditional CDF of theta|r per phi mid-point row
+                               (n_rows = n_phi-1, or 1 when the density does not depend on phi)
+  '''
+  def __init__(self, phi_cdf, first_cdf, first_domain, phi_domain, first_var):
+    self.phi_cdf = np.ascontiguousarray(phi_cdf, dtype=np.float64)
+    self.first_cdf = np.ascontiguousarray(np.atleast_2d(first_cdf), dtype=np.float64)
+    self.first_domain = (float(first_domain[0]), float(first_domain[1]))
+    self.phi_domain = (float(phi_domain[0]), float(phi_domain[1]))
+    self.first_var = first_var
+
+  @property
+  def n_rows(self):
+    return self.first_cdf.shape[0]
+
+  # numpy restatement of the draw (random_number_generator.py:413-456,492-500); used by tests
+  def draw_from_uniforms(self, u_phi, u_first):
+    e_phi = np.linspace(*self.phi_domain, len(self.phi_cdf))
+    e_first = np.linspace(*self.first_domain, self.first_cdf.shape[1])
+    phi = np.interp(u_phi, self.phi_cdf, e_phi)
+    if self.n_rows == 1:
+      return np.interp(u_first, self.first_cdf[0], e_first), phi
+    c_phi = (e_phi[1:]+e_phi[:-1])/2
+    first = np.empty_like(phi)
+    for i, (p, u) in enumerate(zip(phi, u_first)):
+      row = int(np.argmin(np.abs(c_phi-p)))
+      first[i] = np.interp(u, self.first_cdf[row], e_first)
+    return first, phi
+
+
+def build_tables(expr, first_var, first_domain, phi_domain, first_resolution, phi_resolution):
+  '''
+  expr: sympy expression in (first_var, phi).  Follows _generateNumericScalarLambda: edges
+  linspace(l1, l2, odd res), density evaluated at the cell mid-points on meshgrid(C_first, C_phi)
+  (shape [n_phi-1, n_first-1]), conditional table = [0, cumsum along first], marginal =
+  [0, cumsum of the row sums]; every CDF divided by its last entry.
+  '''
+  expr = sy.sympify(expr)
+  n_first = odd_resolution(first_resolution)
+  n_phi = odd_resolution(phi_resolution)
+  e_first = np.linspace(first_domain[0], first_domain[1], n_first)
+  e_phi = np.linspace(phi_domain[0], phi_domain[1], n_phi)
+  c_first = (e_first[1:]+e_first[:-1])/2
+  c_phi = (e_phi[1:]+e_phi[:-1])/2
+  names = {str(s) for s in expr.free_symbols}
+  extra = names-{first_var, 'phi'}
+  if extra:
+    raise ValueError(f'probability density expression {expr} has free symbols {sorted(extra)} besides {first_var}, phi')
+  v1, v2 = sy.Symbol(first_var), sy.Symbol('phi')
+  expr = expr.subs({s: (v1 if str(s) == first_var else v2) for s in expr.free_symbols})
+  lam = sy.lambdify([v1, v2], expr, modules=['numpy', 'scipy'])
+  phi_dependent = 'phi' in names
+  if phi_dependent:
+    g1, g2 = np.meshgrid(c_first, c_phi)
+    probs = np.asarray(lam(g1, g2), dtype=np.float64)
+    if probs.shape != g1.shape:
+      probs = g1*0+probs
+  else:
+    probs = np.asarray(lam(c_first, c_phi[0]), dtype=np.float64)
+    if probs.shape != c_first.shape:
+      probs = c_first*0+probs
+    probs = probs[None, :]
+  if not np.all(np.isfinite(probs)):
+    raise ValueError(f'probability density {expr} is not finite on its domain')
+  if (probs < 0).any():
+    raise ValueError(f'found negative probability density, expression: {expr}')
+  cond = np.cumsum(np.insert(probs, 0, 0.0, axis=-1), axis=-1)
+  rowsum = probs.sum(axis=-1)
+  if not phi_dependent:
+    rowsum = np.full(n_phi-1, rowsum[0])
+  marg = np.cumsum(np.insert(rowsum, 0, 0.0))
+  cond = cond/cond[:, -1:]
+  marg = marg/marg[-1]
+  return SamplerTables(marg, cond, first_domain, phi_domain, first_var)
+
+
+def point_source_tables(rec):
+  'source record (scene_export.fcstd.source_records) -> SamplerTables'
+  f = float(rec.get('FocalLength', '0'))
+  expr, var = point_source_density(rec['PowerDensity'], f)
+  if var == 'theta':
+    dom = parse_domain(rec.get('ThetaDomain', '0, pi/4'), (0, np.pi/4))
+    res = rec.get('ThetaResolutionNumericMode', '1e5')
+  else:
+    dom = parse_domain(rec.get('RadiusDomain', '0, 10'), (0, 10))
+    res = rec.get('RadiusResolutionNumericMode', '1e5')
+  phi_dom = parse_domain(rec.get('PhiDomain', '0, 2*pi'), (0, 2*np.pi))
+  return build_tables(expr, var, dom, phi_dom, float(res), float(rec.get('PhiResolutionNumericMode', '1e2')))
+
+
+# ------------------------------------------------------------------------------------------
+# deterministic fan grid
+
+def points_with_given_density_1d(X, Y, N):
+  'reference distributions/points_by_density.py:25-38'
+  X = np.asarray(X, dtype=float)
+  Y = np.asarray(Y, dtype=float)
+  Xi = np.concatenate([[X[0]-(X[1]-X[0])/2], (X[:-1]+X[1:])/2, [X[-1]+(X[-1]-X[-2])/2]])
+  Yi = np.concatenate([[0], np.cumsum(Y)])
+  Yi = (Yi-Yi.min())/(Yi.max()-Yi.min())
+  Ypick = np.linspace(0, 1, int(round(N)))[1:-1]
+  return np.concatenate([[X[0]], np.interp(Ypick, Yi, Xi), [X[-1]]])
+
+
+def find_grid(expr, var, domain, resolution, N, constants=None):
+  '''
+  ScalarRandomVariable.findGrid (reference random_number_generator.py:685-725): evaluate the density on
+  linspace(domain, odd res) and place N points by quantiles; result clipped to the domain.
+  '''
+  expr = sy.sympify(expr)
+  for k, v in (constants or {}).items():
+    if k in [str(s) for s in expr.free_symbols]:
+      expr = expr.subs(k, v)
+  free = [s for s in expr.free_symbols]
+  if len(free) > 1:
+    raise ValueError(f'expression "{expr}" seems to have more than one free variable after substituting constants')
+  sym = free[0] if free else sy.Symbol(var)
+  rng = np.linspace(domain[0], domain[1], odd_resolution(resolution))
+  density = sy.lambdify(sym, expr, modules=['numpy', 'scipy'])(rng)
+  if not hasattr(density, 'shape') or np.shape(density) != rng.shape:
+    density = density*np.ones(rng.shape)
+  result = points_with_given_density_1d(rng, density, N)
+  return result[np.logical_and(rng.min() <= result, result <= rng.max())]
