@@ -1,0 +1,609 @@
+// odw_api.cu — host side of the C ABI declared in include/odw.h: device memory, scene/source upload,
+// BVH build, kernel launches, result copy-out.  No CPU fallback: without a CUDA device every entry point
+// that needs one fails with ODW_ENODEVICE / ODW_ECUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "odw_device.cuh"
+
+extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int blocks, size_t smem, cudaStream_t st);
+extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
+                                         unsigned long long n, double* first_out, double* phi_out, double* origins,
+                                         double* dirs, int blocks, cudaStream_t st);
+extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem);
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  return fail(e_ == cudaErrorMemoryAllocation ? ODW_ENOMEM : ODW_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+static const int SMEM_FACE_LIMIT = 64;      // scenes up to this many faces are staged in shared memory and brute-forced
+
+struct odw_engine {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string name;
+  // size-keyed pool so that per-call result buffers are not re-allocated every step
+  std::multimap<size_t, void*> pool;
+  size_t pooled_bytes = 0;
+
+  int alloc(void** out, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    auto it = pool.lower_bound(bytes);
+    if (it != pool.end() && it->first <= bytes + bytes/4) {
+      *out = it->second; pooled_bytes -= it->first; alloc_size[*out] = it->first; pool.erase(it);
+      return ODW_OK;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {                 // release the pool and retry once
+      cudaGetLastError();
+      for (auto& kv : pool) cudaFree(kv.second);
+      pool.clear(); pooled_bytes = 0;
+      e = cudaMalloc(out, bytes);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(ODW_ENOMEM, "cudaMalloc(" + std::to_string(bytes) + " bytes) failed"); }
+    }
+    alloc_size[*out] = bytes;
+    return ODW_OK;
+  }
+  void release(void* p) {
+    if (!p) return;
+    auto it = alloc_size.find(p);
+    if (it == alloc_size.end()) { cudaFree(p); return; }
+    pool.emplace(it->second, p); pooled_bytes += it->second;
+    alloc_size.erase(it);
+  }
+  std::map<void*, size_t> alloc_size;
+};
+
+struct odw_scene {
+  odw_engine* eng = nullptr;
+  DScene d{};
+  std::vector<void*> owned;
+  bool use_bvh = false;
+  size_t smem = 0;
+  int n_groups = 0;
+};
+
+struct odw_source {
+  odw_engine* eng = nullptr;
+  DSource d{};
+  std::vector<void*> owned;
+  double max_ray_length_scale = 1, max_intersections_scale = 1;
+  std::vector<int32_t> ignored;
+};
+
+struct odw_result {
+  odw_engine* eng = nullptr;
+  HitBuffers hb{};
+  Counters* dcounters = nullptr;
+  double* dbins = nullptr;
+  DBinning* dbinnings = nullptr;
+  std::vector<DBinning> binnings;
+  size_t total_bins = 0;
+  int32_t* d_nseg = nullptr; double* d_final_point = nullptr; double* d_final_power = nullptr;
+  double* d_in_o = nullptr; double* d_in_d = nullptr; double* d_in_p = nullptr;
+  odw_counts counts{};
+  uint64_t n_rays = 0;
+  float ms = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+extern "C" int odw_abi_version(void) { return ODW_ABI_VERSION; }
+extern "C" const char* odw_last_error(void) { return g_err.c_str(); }
+
+extern "C" int odw_engine_create(int device_id, odw_engine** out) {
+  if (!out) return fail(ODW_EINVAL, "odw_engine_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(ODW_ENODEVICE, std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                               "); this library has no CPU fallback");
+  }
+  if (device_id < 0 || device_id >= n) return fail(ODW_ENODEVICE, "device id " + std::to_string(device_id) + " out of range");
+  CU(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device_id));
+  odw_engine* eng = new odw_engine();
+  eng->device = device_id;
+  eng->sm_count = prop.multiProcessorCount;
+  eng->name = prop.name;
+  CU(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&eng->ev0));
+  CU(cudaEventCreate(&eng->ev1));
+  *out = eng;
+  return ODW_OK;
+}
+
+extern "C" void odw_engine_destroy(odw_engine* eng) {
+  if (!eng) return;
+  cudaSetDevice(eng->device);
+  for (auto& kv : eng->pool) cudaFree(kv.second);
+  if (eng->ev0) cudaEventDestroy(eng->ev0);
+  if (eng->ev1) cudaEventDestroy(eng->ev1);
+  if (eng->stream) cudaStreamDestroy(eng->stream);
+  delete eng;
+}
+
+extern "C" int odw_engine_device_name(const odw_engine* eng, char* buf, int buflen) {
+  if (!eng || !buf || buflen <= 0) return fail(ODW_EINVAL, "odw_engine_device_name: bad argument");
+  snprintf(buf, (size_t)buflen, "%s (%d SMs)", eng->name.c_str(), eng->sm_count);
+  return ODW_OK;
+}
+
+template <typename T>
+static int upload(odw_engine* eng, std::vector<void*>& owned, const T* host, size_t n, const T** dev) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(n, 1)*sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ODW_ENOMEM, "cudaMalloc failed in upload"); }
+  owned.push_back(p);
+  if (n) CU(cudaMemcpy(p, host, n*sizeof(T), cudaMemcpyHostToDevice));
+  *dev = reinterpret_cast<const T*>(p);
+  return ODW_OK;
+}
+
+// ---- SAH BVH over face boxes ---------------------------------------------------------------
+namespace {
+struct Box { double lo[3], hi[3];
+  void reset() { for (int i = 0; i < 3; ++i) { lo[i] = 1e300; hi[i] = -1e300; } }
+  void grow(const Box& b) { for (int i = 0; i < 3; ++i) { lo[i] = std::min(lo[i], b.lo[i]); hi[i] = std::max(hi[i], b.hi[i]); } }
+  double area() const { double d[3] = { hi[0]-lo[0], hi[1]-lo[1], hi[2]-lo[2] }; if (d[0] < 0) return 0; return 2*(d[0]*d[1] + d[1]*d[2] + d[2]*d[0]); }
+};
+
+struct BvhBuilder {
+  const std::vector<Box>& boxes;
+  std::vector<int> prims;
+  std::vector<BvhNode> nodes;
+  explicit BvhBuilder(const std::vector<Box>& b) : boxes(b), prims(b.size()) { std::iota(prims.begin(), prims.end(), 0); }
+
+  static float down(double v) { float f = (float)v; return f > v ? std::nextafter(f, -INFINITY) : f; }
+  static float up(double v) { float f = (float)v; return f < v ? std::nextafter(f, INFINITY) : f; }
+
+  void set_box(BvhNode& n, const Box& b) { for (int i = 0; i < 3; ++i) { n.lo[i] = down(b.lo[i]); n.hi[i] = up(b.hi[i]); } }
+
+  void build() {
+    nodes.reserve(2*boxes.size() + 2);
+    nodes.push_back(BvhNode{});
+    recurse(0, 0, (int)prims.size());
+  }
+
+  void recurse(int node, int first, int count) {
+    Box bb; bb.reset(); Box cb; cb.reset();
+    for (int i = first; i < first + count; ++i) {
+      const Box& b = boxes[prims[i]]; bb.grow(b);
+      for (int a = 0; a < 3; ++a) { double c = 0.5*(b.lo[a] + b.hi[a]); cb.lo[a] = std::min(cb.lo[a], c); cb.hi[a] = std::max(cb.hi[a], c); }
+    }
+    set_box(nodes[node], bb);
+    const int LEAF = 2, NB = 16;
+    int best_axis = -1, best_split = -1; double best_cost = 1e300;
+    if (count > LEAF) {
+      for (int a = 0; a < 3; ++a) {
+        double ext = cb.hi[a] - cb.lo[a];
+        if (ext <= 0) continue;
+        Box bins[NB]; int cnt[NB] = {0};
+        for (auto& b : bins) b.reset();
+        for (int i = first; i < first + count; ++i) {
+          const Box& b = boxes[prims[i]];
+          int k = std::min(NB-1, (int)(NB*((0.5*(b.lo[a] + b.hi[a]) - cb.lo[a])/ext)));
+          bins[k].grow(b); cnt[k]++;
+        }
+        double right_area[NB]; int right_cnt[NB]; Box r; r.reset(); int rc = 0;
+        for (int k = NB-1; k > 0; --k) { r.grow(bins[k]); rc += cnt[k]; right_area[k] = r.area(); right_cnt[k] = rc; }
+        Box l; l.reset(); int lc = 0;
+        for (int k = 0; k < NB-1; ++k) {
+          l.grow(bins[k]); lc += cnt[k];
+          if (lc == 0 || right_cnt[k+1] == 0) continue;
+          double cost = l.area()*lc + right_area[k+1]*right_cnt[k+1];
+          if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+        }
+      }
+    }
+    if (best_axis < 0) {
+      if (count <= 8) { nodes[node].left = first; nodes[node].count = count; return; }
+      // degenerate (all centroids equal): split in the middle
+      int mid = first + count/2;
+      int l = (int)nodes.size(); nodes.push_back(BvhNode{}); nodes.push_back(BvhNode{});
+      nodes[node].left = l; nodes[node].count = 0;
+      recurse(l, first, mid - first); recurse(l + 1, mid, first + count - mid);
+      return;
+    }
+    double ext = cb.hi[best_axis] - cb.lo[best_axis];
+    auto mid_it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](int pi) {
+      const Box& b = boxes[pi];
+      int k = std::min(NB-1, (int)(NB*((0.5*(b.lo[best_axis] + b.hi[best_axis]) - cb.lo[best_axis])/ext)));
+      return k <= best_split;
+    });
+    int mid = (int)(mid_it - prims.begin());
+    int l = (int)nodes.size(); nodes.push_back(BvhNode{}); nodes.push_back(BvhNode{});
+    nodes[node].left = l; nodes[node].count = 0;
+    recurse(l, first, mid - first); recurse(l + 1, mid, first + count - mid);
+  }
+};
+}  // namespace
+
+extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_scene** out) {
+  if (!eng || !sd || !out) return fail(ODW_EINVAL, "odw_scene_create: NULL argument");
+  *out = nullptr;
+  if (sd->n_faces < 0 || sd->n_groups <= 0 || (sd->n_faces > 0 && !sd->faces) || !sd->groups)
+    return fail(ODW_EINVAL, "odw_scene_create: empty or inconsistent description");
+  if (sd->n_seq_steps > 128) return fail(ODW_EUNSUPPORTED, "more than 128 sequential steps");
+  CU(cudaSetDevice(eng->device));
+  std::vector<DFace> faces((size_t)sd->n_faces);
+  std::vector<Box> boxes((size_t)sd->n_faces);
+  for (int i = 0; i < sd->n_faces; ++i) {
+    const odw_face& f = sd->faces[i];
+    if (f.group < 0 || f.group >= sd->n_groups) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": group out of range");
+    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_TORUS) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": unknown surface kind");
+    if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_segs))
+      return fail(ODW_EINVAL, "face " + std::to_string(i) + ": trim segment range out of bounds");
+    DFace& d = faces[(size_t)i];
+    memset(&d, 0, sizeof d);
+    for (int k = 0; k < 3; ++k) { d.o[k] = f.origin[k]; d.x[k] = f.xdir[k]; d.y[k] = f.ydir[k]; d.z[k] = f.zdir[k];
+                                  d.bmin[k] = f.aabb_min[k]; d.bmax[k] = f.aabb_max[k];
+                                  boxes[(size_t)i].lo[k] = f.aabb_min[k]; boxes[(size_t)i].hi[k] = f.aabb_max[k]; }
+    d.p0 = f.p0; d.p1 = f.p1;
+    d.umin = f.uv_min[0]; d.umax = f.uv_max[0]; d.vmin = f.uv_min[1]; d.vmax = f.uv_max[1];
+    d.kind = f.kind; d.trim = f.trim_kind; d.nsign = f.nsign; d.group = f.group;
+    d.seg_first = f.seg_first; d.seg_count = f.seg_count; d.face_id = f.face_id;
+    d.flags = (f.kind != ODW_SURF_PLANE && std::fabs((f.uv_max[0] - f.uv_min[0]) - ODW_TWO_PI) < 1e-9) ? DFACE_FULL_U : 0;
+    for (int s = 0; s < sd->n_seq_steps; ++s)
+      for (int k = sd->seq_offsets[s]; k < sd->seq_offsets[s+1]; ++k)
+        if (sd->seq_groups[k] == f.group) d.seqmask[s >> 6] |= 1ull << (s & 63);
+  }
+  std::vector<DGroup> groups((size_t)sd->n_groups);
+  for (int i = 0; i < sd->n_groups; ++i) {
+    const odw_group& g = sd->groups[i]; DGroup& d = groups[(size_t)i];
+    d.n = g.refractive_index; d.reflectivity = g.reflectivity; d.absorption_length = g.absorption_length;
+    d.lpm = g.grating_lines_per_mm; d.order = g.grating_order;
+    for (int k = 0; k < 3; ++k) d.gdir[k] = g.grating_orientation[k];
+    d.type = g.optical_type; d.record = g.record_hits; d.gtype = g.grating_type; d.pad = 0;
+  }
+  odw_scene* sc = new odw_scene();
+  sc->eng = eng; sc->n_groups = sd->n_groups;
+  int rc;
+  if ((rc = upload(eng, sc->owned, faces.data(), faces.size(), &sc->d.faces))) { odw_scene_destroy(sc); return rc; }
+  if ((rc = upload(eng, sc->owned, sd->segs, (size_t)sd->n_segs, &sc->d.segs))) { odw_scene_destroy(sc); return rc; }
+  if ((rc = upload(eng, sc->owned, groups.data(), groups.size(), &sc->d.groups))) { odw_scene_destroy(sc); return rc; }
+  sc->d.n_faces = sd->n_faces; sc->d.n_segs = sd->n_segs; sc->d.n_groups = sd->n_groups; sc->d.n_seq_steps = sd->n_seq_steps;
+  sc->use_bvh = sd->n_faces > SMEM_FACE_LIMIT;
+  if (sc->use_bvh) {
+    BvhBuilder b(boxes);
+    b.build();
+    if ((rc = upload(eng, sc->owned, b.nodes.data(), b.nodes.size(), &sc->d.bvh))) { odw_scene_destroy(sc); return rc; }
+    if ((rc = upload(eng, sc->owned, b.prims.data(), b.prims.size(), &sc->d.bvh_prims))) { odw_scene_destroy(sc); return rc; }
+    sc->d.n_bvh_nodes = (int)b.nodes.size();
+    sc->smem = 0;
+  } else {
+    sc->smem = std::max<size_t>(16, faces.size()*sizeof(DFace));
+  }
+  *out = sc;
+  return ODW_OK;
+}
+
+extern "C" void odw_scene_destroy(odw_scene* sc) {
+  if (!sc) return;
+  cudaSetDevice(sc->eng->device);
+  for (void* p : sc->owned) cudaFree(p);
+  delete sc;
+}
+
+static std::vector<uint32_t> build_guide(const double* cdf, int n) {
+  std::vector<uint32_t> g(ODW_GUIDE + 1);
+  for (int k = 0; k <= ODW_GUIDE; ++k) {
+    double x = (double)k/(double)ODW_GUIDE;
+    const double* it = std::upper_bound(cdf, cdf + n, x);     // first element > x
+    long j = (it - cdf) - 1;
+    g[(size_t)k] = (uint32_t)std::max<long>(0, j);
+  }
+  return g;
+}
+
+extern "C" int odw_source_create(odw_engine* eng, const odw_source_desc* sd, odw_source** out) {
+  if (!eng || !sd || !out) return fail(ODW_EINVAL, "odw_source_create: NULL argument");
+  *out = nullptr;
+  if (sd->kind != ODW_SRC_POINT_SPHERICAL && sd->kind != ODW_SRC_POINT_COLLIMATED) return fail(ODW_EUNSUPPORTED, "unknown source kind");
+  if (sd->n_first < 2 || sd->n_phi < 2 || !sd->phi_cdf || !sd->first_cdf) return fail(ODW_EINVAL, "odw_source_create: missing CDF tables");
+  if (sd->n_rows != 1 && sd->n_rows != sd->n_phi - 1) return fail(ODW_EINVAL, "odw_source_create: n_rows must be 1 or n_phi-1");
+  for (int r = 0; r < sd->n_rows + 1; ++r) {
+    const double* c = r < sd->n_rows ? sd->first_cdf + (size_t)r*sd->n_first : sd->phi_cdf;
+    int n = r < sd->n_rows ? sd->n_first : sd->n_phi;
+    if (!(c[0] == 0.0) || !(std::fabs(c[n-1] - 1.0) < 1e-12)) return fail(ODW_EINVAL, "odw_source_create: CDF rows must run from 0 to 1");
+  }
+  CU(cudaSetDevice(eng->device));
+  odw_source* s = new odw_source();
+  s->eng = eng;
+  int rc;
+  if ((rc = upload(eng, s->owned, sd->phi_cdf, (size_t)sd->n_phi, &s->d.phi_cdf))) { odw_source_destroy(s); return rc; }
+  if ((rc = upload(eng, s->owned, sd->first_cdf, (size_t)sd->n_rows*sd->n_first, &s->d.first_cdf))) { odw_source_destroy(s); return rc; }
+  std::vector<uint32_t> pg = build_guide(sd->phi_cdf, sd->n_phi), fg;
+  fg.reserve((size_t)sd->n_rows*(ODW_GUIDE + 1));
+  for (int r = 0; r < sd->n_rows; ++r) {
+    std::vector<uint32_t> g = build_guide(sd->first_cdf + (size_t)r*sd->n_first, sd->n_first);
+    fg.insert(fg.end(), g.begin(), g.end());
+  }
+  if ((rc = upload(eng, s->owned, pg.data(), pg.size(), &s->d.phi_guide))) { odw_source_destroy(s); return rc; }
+  if ((rc = upload(eng, s->owned, fg.data(), fg.size(), &s->d.first_guide))) { odw_source_destroy(s); return rc; }
+  s->d.first_lo = sd->first_lo; s->d.first_hi = sd->first_hi; s->d.phi_lo = sd->phi_lo; s->d.phi_hi = sd->phi_hi;
+  s->d.focal = sd->focal_length; s->d.wavelength = sd->wavelength;
+  for (int i = 0; i < 12; ++i) s->d.M[i] = sd->gpM[i];
+  s->d.kind = sd->kind; s->d.source_id = sd->source_id; s->d.n_first = sd->n_first; s->d.n_phi = sd->n_phi; s->d.n_rows = sd->n_rows;
+  s->max_ray_length_scale = sd->max_ray_length_scale > 0 ? sd->max_ray_length_scale : 1.0;
+  s->max_intersections_scale = sd->max_intersections_scale > 0 ? sd->max_intersections_scale : 1.0;
+  if (sd->n_ignored > 0 && sd->ignored_groups) s->ignored.assign(sd->ignored_groups, sd->ignored_groups + sd->n_ignored);
+  *out = s;
+  return ODW_OK;
+}
+
+extern "C" void odw_source_destroy(odw_source* s) {
+  if (!s) return;
+  cudaSetDevice(s->eng->device);
+  for (void* p : s->owned) cudaFree(p);
+  delete s;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" void odw_result_destroy(odw_result* r) {
+  if (!r) return;
+  odw_engine* e = r->eng;
+  cudaSetDevice(e->device);
+  void* ptrs[] = { r->hb.points, r->hb.dirs, r->hb.powers, r->hb.entering, r->hb.ray_index, r->hb.group, r->hb.bounce,
+                   r->hb.face_id, r->dcounters, r->dbins, r->dbinnings, r->d_nseg, r->d_final_point, r->d_final_power,
+                   r->d_in_o, r->d_in_d, r->d_in_p };
+  for (void* p : ptrs) e->release(p);
+  delete r;
+}
+
+static int prepare_result(odw_engine* eng, const odw_scene* sc, const odw_trace_cfg* cfg, uint64_t n_rays, odw_result** out,
+                          TraceParams& p) {
+  odw_result* r = new odw_result();
+  r->eng = eng; r->n_rays = n_rays;
+  *out = r;
+  int rc;
+  uint64_t cap = cfg->store_hits ? (cfg->hit_capacity ? cfg->hit_capacity : std::max<uint64_t>(1024, 2*n_rays)) : 0;
+  r->hb.capacity = cap;
+  if (cap) {
+    if ((rc = eng->alloc((void**)&r->hb.points, cap*24))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.dirs, cap*24))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.powers, cap*8))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.entering, cap))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.ray_index, cap*8))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.group, cap*4))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.bounce, cap*4))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.face_id, cap*4))) return rc;
+  }
+  if ((rc = eng->alloc((void**)&r->dcounters, sizeof(Counters)))) return rc;
+  CU(cudaMemsetAsync(r->dcounters, 0, sizeof(Counters), eng->stream));
+  if (cfg->n_binnings > 0) {
+    if (!cfg->binnings) return fail(ODW_EINVAL, "n_binnings > 0 but binnings is NULL");
+    size_t off = 0;
+    for (int b = 0; b < cfg->n_binnings; ++b) {
+      const odw_binning& s = cfg->binnings[b];
+      if (s.nu <= 0 || s.nv <= 0 || !(s.u_hi > s.u_lo) || !(s.v_hi > s.v_lo) || s.group < 0 || s.group >= sc->n_groups)
+        return fail(ODW_EINVAL, "binning " + std::to_string(b) + ": bad specification");
+      DBinning d{};
+      for (int k = 0; k < 3; ++k) { d.origin[k] = s.origin[k]; d.ua[k] = s.uaxis[k]; d.va[k] = s.vaxis[k]; }
+      d.u_lo = s.u_lo; d.v_lo = s.v_lo; d.u_hi = s.u_hi; d.v_hi = s.v_hi;
+      d.u_scale = s.nu/(s.u_hi - s.u_lo); d.v_scale = s.nv/(s.v_hi - s.v_lo);
+      d.group = s.group; d.nu = s.nu; d.nv = s.nv; d.weighted = s.weighted; d.offset = off;
+      off += (size_t)s.nu*(size_t)s.nv;
+      r->binnings.push_back(d);
+    }
+    r->total_bins = off;
+    if ((rc = eng->alloc((void**)&r->dbins, off*sizeof(double)))) return rc;
+    if ((rc = eng->alloc((void**)&r->dbinnings, r->binnings.size()*sizeof(DBinning)))) return rc;
+    CU(cudaMemsetAsync(r->dbins, 0, off*sizeof(double), eng->stream));
+    CU(cudaMemcpyAsync(r->dbinnings, r->binnings.data(), r->binnings.size()*sizeof(DBinning), cudaMemcpyHostToDevice, eng->stream));
+  }
+  memset(&p, 0, sizeof p);
+  p.scene = sc->d;
+  p.hits = r->hb;
+  p.counters = r->dcounters;
+  p.binnings = r->dbinnings; p.bins = r->dbins; p.n_binnings = cfg->n_binnings;
+  p.n_rays = n_rays;
+  p.max_len = cfg->max_ray_length; p.tol = std::max(cfg->dist_tol, 1e-6); p.power_tol = cfg->power_tol;
+  p.max_isect = cfg->max_intersections; p.sequential = cfg->sequential;
+  p.record_all = cfg->record_all_hits; p.store_hits = cfg->store_hits;
+  return ODW_OK;
+}
+
+static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
+  for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
+}
+
+static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const TraceParams& p, bool mc) {
+  int per_sm = odw_trace_occupancy(mc, sc->use_bvh, sc->smem);
+  if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
+  // persistent grid: a multiple of the SM count, no more blocks than there is work
+  uint64_t want = (p.n_rays + 255)/256;
+  int blocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*(uint64_t)per_sm, std::max<uint64_t>(1, want));
+  CU(cudaEventRecord(eng->ev0, eng->stream));
+  if (p.n_rays > 0) CU(odw_launch_trace(&p, mc, sc->use_bvh, blocks, sc->smem, eng->stream));
+  CU(cudaEventRecord(eng->ev1, eng->stream));
+  Counters c;
+  CU(cudaMemcpyAsync(&c, r->dcounters, sizeof c, cudaMemcpyDeviceToHost, eng->stream));
+  CU(cudaStreamSynchronize(eng->stream));
+  CU(cudaEventElapsedTime(&r->ms, eng->ev0, eng->ev1));
+  r->counts.rays = p.n_rays; r->counts.segments = c.segments; r->counts.hits = c.hits;
+  r->counts.hits_dropped = c.hits_dropped; r->counts.escaped = c.escaped; r->counts.depth_terminated = c.depth_terminated;
+  r->counts.waves = p.n_rays > 0 ? 1 : 0;
+  return c.hits_dropped ? fail(ODW_EOVERFLOW, std::to_string(c.hits_dropped) + " hits did not fit hit_capacity " + std::to_string(p.hits.capacity)) : ODW_OK;
+}
+
+extern "C" int odw_trace_mc(odw_scene* sc, odw_source* src, const odw_trace_cfg* cfg, uint64_t seed, uint64_t first_ray,
+                            uint64_t n_rays, odw_result** out) {
+  if (!sc || !src || !cfg || !out) return fail(ODW_EINVAL, "odw_trace_mc: NULL argument");
+  *out = nullptr;
+  if (sc->eng != src->eng) return fail(ODW_EINVAL, "odw_trace_mc: scene and source belong to different engines");
+  odw_engine* eng = sc->eng;
+  CU(cudaSetDevice(eng->device));
+  TraceParams p;
+  int rc = prepare_result(eng, sc, cfg, n_rays, out, p);
+  if (rc) { odw_result_destroy(*out); *out = nullptr; return rc; }
+  p.src = src->d;
+  p.seed = seed; p.first_ray = first_ray;
+  p.max_len = cfg->max_ray_length*src->max_ray_length_scale;                 // ray.py:48-53
+  p.max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
+  p.wavelength = src->d.wavelength;
+  set_ignore(p, src->ignored.data(), (int)src->ignored.size());
+  rc = run_trace(eng, sc, *out, p, true);
+  if (rc && rc != ODW_EOVERFLOW) { odw_result_destroy(*out); *out = nullptr; }
+  return rc;
+}
+
+extern "C" int odw_sample_mc(odw_source* src, uint64_t seed, uint64_t first_ray, uint64_t n, double* first_var, double* phi,
+                             double* origins, double* directions) {
+  if (!src) return fail(ODW_EINVAL, "odw_sample_mc: NULL source");
+  odw_engine* eng = src->eng;
+  CU(cudaSetDevice(eng->device));
+  double *df = nullptr, *dp = nullptr, *dorg = nullptr, *dd = nullptr;
+  int rc = ODW_OK;
+  if (first_var && (rc = eng->alloc((void**)&df, n*8))) return rc;
+  if (phi && (rc = eng->alloc((void**)&dp, n*8))) return rc;
+  if (origins && (rc = eng->alloc((void**)&dorg, n*24))) return rc;
+  if (directions && (rc = eng->alloc((void**)&dd, n*24))) return rc;
+  int blocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*8, std::max<uint64_t>(1, (n + 255)/256));
+  if (n) CU(odw_launch_sample(&src->d, seed, first_ray, n, df, dp, dorg, dd, blocks, eng->stream));
+  if (first_var) CU(cudaMemcpyAsync(first_var, df, n*8, cudaMemcpyDeviceToHost, eng->stream));
+  if (phi) CU(cudaMemcpyAsync(phi, dp, n*8, cudaMemcpyDeviceToHost, eng->stream));
+  if (origins) CU(cudaMemcpyAsync(origins, dorg, n*24, cudaMemcpyDeviceToHost, eng->stream));
+  if (directions) CU(cudaMemcpyAsync(directions, dd, n*24, cudaMemcpyDeviceToHost, eng->stream));
+  CU(cudaStreamSynchronize(eng->stream));
+  eng->release(df); eng->release(dp); eng->release(dorg); eng->release(dd);
+  return ODW_OK;
+}
+
+extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const double* origins, const double* directions,
+                              const double* powers, const int32_t* ignored_groups, int32_t n_ignored, uint64_t n_rays,
+                              odw_result** out) {
+  if (!sc || !cfg || !out || (n_rays && (!origins || !directions))) return fail(ODW_EINVAL, "odw_trace_rays: NULL argument");
+  *out = nullptr;
+  odw_engine* eng = sc->eng;
+  CU(cudaSetDevice(eng->device));
+  TraceParams p;
+  int rc = prepare_result(eng, sc, cfg, n_rays, out, p);
+  if (rc) { odw_result_destroy(*out); *out = nullptr; return rc; }
+  odw_result* r = *out;
+  auto bail = [&](int code) { odw_result_destroy(r); *out = nullptr; return code; };
+  if ((rc = eng->alloc((void**)&r->d_in_o, n_rays*24))) return bail(rc);
+  if ((rc = eng->alloc((void**)&r->d_in_d, n_rays*24))) return bail(rc);
+  if (powers && (rc = eng->alloc((void**)&r->d_in_p, n_rays*8))) return bail(rc);
+  if ((rc = eng->alloc((void**)&r->d_nseg, n_rays*4))) return bail(rc);
+  if ((rc = eng->alloc((void**)&r->d_final_point, n_rays*24))) return bail(rc);
+  if ((rc = eng->alloc((void**)&r->d_final_power, n_rays*8))) return bail(rc);
+  if (n_rays) {
+    CU(cudaMemcpyAsync(r->d_in_o, origins, n_rays*24, cudaMemcpyHostToDevice, eng->stream));
+    CU(cudaMemcpyAsync(r->d_in_d, directions, n_rays*24, cudaMemcpyHostToDevice, eng->stream));
+    if (powers) CU(cudaMemcpyAsync(r->d_in_p, powers, n_rays*8, cudaMemcpyHostToDevice, eng->stream));
+  }
+  p.in_origins = r->d_in_o; p.in_dirs = r->d_in_d; p.in_powers = powers ? r->d_in_p : nullptr;
+  p.out_nseg = r->d_nseg; p.out_final_point = r->d_final_point; p.out_final_power = r->d_final_power;
+  p.first_ray = 0;
+  p.wavelength = 500.0;
+  set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0);
+  rc = run_trace(eng, sc, r, p, false);
+  if (rc && rc != ODW_EOVERFLOW) return bail(rc);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int odw_result_counts(const odw_result* r, odw_counts* out) {
+  if (!r || !out) return fail(ODW_EINVAL, "odw_result_counts: NULL argument");
+  *out = r->counts;
+  return ODW_OK;
+}
+
+extern "C" int odw_result_kernel_ms(const odw_result* r, double* ms) {
+  if (!r || !ms) return fail(ODW_EINVAL, "odw_result_kernel_ms: NULL argument");
+  *ms = r->ms;
+  return ODW_OK;
+}
+
+extern "C" int odw_result_hits(const odw_result* r, odw_hits_view* v, int sorted, uint64_t* n_out) {
+  if (!r || !v) return fail(ODW_EINVAL, "odw_result_hits: NULL argument");
+  odw_engine* eng = r->eng;
+  CU(cudaSetDevice(eng->device));
+  uint64_t stored = std::min<uint64_t>(r->counts.hits, r->hb.capacity);
+  uint64_t n = std::min<uint64_t>(stored, v->capacity);
+  if (n_out) *n_out = n;
+  if (n == 0) return ODW_OK;
+  cudaStream_t st = eng->stream;
+  if (!sorted) {
+    if (v->points)      CU(cudaMemcpyAsync(v->points, r->hb.points, n*24, cudaMemcpyDeviceToHost, st));
+    if (v->directions)  CU(cudaMemcpyAsync(v->directions, r->hb.dirs, n*24, cudaMemcpyDeviceToHost, st));
+    if (v->powers)      CU(cudaMemcpyAsync(v->powers, r->hb.powers, n*8, cudaMemcpyDeviceToHost, st));
+    if (v->is_entering) CU(cudaMemcpyAsync(v->is_entering, r->hb.entering, n, cudaMemcpyDeviceToHost, st));
+    if (v->ray_index)   CU(cudaMemcpyAsync(v->ray_index, r->hb.ray_index, n*8, cudaMemcpyDeviceToHost, st));
+    if (v->group)       CU(cudaMemcpyAsync(v->group, r->hb.group, n*4, cudaMemcpyDeviceToHost, st));
+    if (v->bounce)      CU(cudaMemcpyAsync(v->bounce, r->hb.bounce, n*4, cudaMemcpyDeviceToHost, st));
+    if (v->face_id)     CU(cudaMemcpyAsync(v->face_id, r->hb.face_id, n*4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return ODW_OK;
+  }
+  // sorted by (ray_index, bounce): the append order of the kernel is not deterministic
+  std::vector<unsigned long long> ray(stored); std::vector<int32_t> bounce(stored);
+  CU(cudaMemcpyAsync(ray.data(), r->hb.ray_index, stored*8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(bounce.data(), r->hb.bounce, stored*4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::vector<uint64_t> order(stored);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+    return ray[a] != ray[b] ? ray[a] < ray[b] : bounce[a] < bounce[b]; });
+  auto gather = [&](void* dst, const void* dsrc, size_t elem) -> int {
+    if (!dst) return ODW_OK;
+    std::vector<unsigned char> tmp(stored*elem);
+    CU(cudaMemcpyAsync(tmp.data(), dsrc, stored*elem, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    unsigned char* o = static_cast<unsigned char*>(dst);
+    for (uint64_t i = 0; i < n; ++i) memcpy(o + i*elem, tmp.data() + order[i]*elem, elem);
+    return ODW_OK;
+  };
+  int rc;
+  if ((rc = gather(v->points, r->hb.points, 24))) return rc;
+  if ((rc = gather(v->directions, r->hb.dirs, 24))) return rc;
+  if ((rc = gather(v->powers, r->hb.powers, 8))) return rc;
+  if ((rc = gather(v->is_entering, r->hb.entering, 1))) return rc;
+  if ((rc = gather(v->ray_index, r->hb.ray_index, 8))) return rc;
+  if ((rc = gather(v->group, r->hb.group, 4))) return rc;
+  if ((rc = gather(v->bounce, r->hb.bounce, 4))) return rc;
+  if ((rc = gather(v->face_id, r->hb.face_id, 4))) return rc;
+  return ODW_OK;
+}
+
+extern "C" int odw_result_histogram(const odw_result* r, int32_t b, double* bins_out) {
+  if (!r || !bins_out) return fail(ODW_EINVAL, "odw_result_histogram: NULL argument");
+  if (b < 0 || b >= (int)r->binnings.size()) return fail(ODW_EINVAL, "odw_result_histogram: binning index out of range");
+  CU(cudaSetDevice(r->eng->device));
+  const DBinning& d = r->binnings[(size_t)b];
+  CU(cudaMemcpy(bins_out, r->dbins + d.offset, (size_t)d.nu*d.nv*sizeof(double), cudaMemcpyDeviceToHost));
+  return ODW_OK;
+}
+
+extern "C" int odw_result_histogram_device(const odw_result* r, int32_t b, void** dptr, uint64_t* n_bins) {
+  if (!r || !dptr) return fail(ODW_EINVAL, "odw_result_histogram_device: NULL argument");
+  if (b < 0 || b >= (int)r->binnings.size()) return fail(ODW_EINVAL, "odw_result_histogram_device: binning index out of range");
+  const DBinning& d = r->binnings[(size_t)b];
+  *dptr = r->dbins + d.offset;
+  if (n_bins) *n_bins = (uint64_t)d.nu*d.nv;
+  return ODW_OK;
+}
+
+extern "C" int odw_result_ray_summary(const odw_result* r, int32_t* n_segments, double* final_points, double* final_powers) {
+  if (!r) return fail(ODW_EINVAL, "odw_result_ray_summary: NULL argument");
+  if (!r->d_nseg) return fail(ODW_EINVAL, "odw_result_ray_summary: only available for odw_trace_rays results");
+  CU(cudaSetDevice(r->eng->device));
+  uint64_t n = r->n_rays;
+  if (n == 0) return ODW_OK;
+  if (n_segments) CU(cudaMemcpy(n_segments, r->d_nseg, n*4, cudaMemcpyDeviceToHost));
+  if (final_points) CU(cudaMemcpy(final_points, r->d_final_point, n*24, cudaMemcpyDeviceToHost));
+  if (final_powers) CU(cudaMemcpy(final_powers, r->d_final_power, n*8, cudaMemcpyDeviceToHost));
+  return ODW_OK;
+}

@@ -1,0 +1,464 @@
+// odw_device.cuh — device-side geometry, optics and sampling for the sm_100a trace kernels.
+//
+// Semantics follow the reference (freecad/optics_design_workbench/freecad_elements/ray.py, cited per
+// function); the arithmetic OCC does for the reference (line/surface intersection, point-on-trimmed-face,
+// normal) is written out in closed form for plane / cylinder / cone / sphere / torus.  Everything is fp64:
+// the acceptance rules work at distTol = 1e-6 mm on scenes of 1e2..1e3 mm.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../../include/odw.h"
+
+#define ODW_TWO_PI 6.283185307179586476925286766559
+
+// Face record as the kernels read it (built once per scene from odw_face).
+struct DFace {
+  double o[3], x[3], y[3], z[3];
+  double p0, p1;
+  double umin, umax, vmin, vmax;
+  double bmin[3], bmax[3];
+  int32_t kind, trim, nsign, group;
+  int32_t seg_first, seg_count, face_id, flags;
+  unsigned long long seqmask[2];   // bit s set <=> the face's group is in SequentialModeElements step s
+};
+#define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
+
+struct DGroup {
+  double n, reflectivity, absorption_length, lpm, order, gdir[3];
+  int32_t type, record, gtype, pad;
+};
+
+struct DBinning {
+  double origin[3], ua[3], va[3];
+  double u_lo, v_lo, u_scale, v_scale, u_hi, v_hi;   // scale = n/(hi-lo)
+  int32_t group, nu, nv, weighted;
+  unsigned long long offset;                         // into the concatenated bins array
+};
+
+struct BvhNode {                   // 32 B: one 256-bit load fetches a node
+  float lo[3], hi[3];
+  int32_t left;                    // inner: index of left child (right = left+1); leaf: first primitive
+  int32_t count;                   // 0 = inner node, >0 = number of primitives in the leaf
+};
+
+struct DScene {
+  const DFace* faces;
+  const odw_trimseg* segs;
+  const DGroup* groups;
+  const BvhNode* bvh;              // nullptr: brute force over all faces
+  const int32_t* bvh_prims;        // face indices in leaf order
+  int32_t n_faces, n_segs, n_groups, n_seq_steps, n_bvh_nodes;
+};
+
+struct DSource {
+  const double* phi_cdf;
+  const double* first_cdf;
+  const uint32_t* phi_guide;       // [GUIDE+1]
+  const uint32_t* first_guide;     // [n_rows][GUIDE+1]
+  double first_lo, first_hi, phi_lo, phi_hi, focal, wavelength;
+  double M[12];                    // rows 0..2 of gpM
+  int32_t kind, source_id, n_first, n_phi, n_rows, pad;
+};
+#define ODW_GUIDE 4096
+
+struct HitBuffers {
+  double* points; double* dirs; double* powers;
+  uint8_t* entering; unsigned long long* ray_index;
+  int32_t* group; int32_t* bounce; int32_t* face_id;
+  unsigned long long capacity;
+};
+
+struct Counters {                  // device-side odw_counts
+  unsigned long long segments, hits, hits_dropped, escaped, depth_terminated, alive_next;
+};
+
+struct TraceParams {
+  DScene scene;
+  DSource src;
+  HitBuffers hits;
+  Counters* counters;
+  const DBinning* binnings; double* bins; int32_t n_binnings;
+  // explicit ray input (nullptr for MC)
+  const double* in_origins; const double* in_dirs; const double* in_powers;
+  // per-ray summary (explicit lists)
+  int32_t* out_nseg; double* out_final_point; double* out_final_power;
+  unsigned long long ignore_mask[4];
+  unsigned long long seed, first_ray, n_rays;
+  double max_len, tol, power_tol, wavelength;
+  int32_t max_isect, sequential, record_all, store_hits;
+};
+
+#ifdef ODW_DEVICE_CODE   // device functions: only the kernel translation unit defines this
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
+__device__ __forceinline__ double dot3(double ax, double ay, double az, const double* b) { return ax*b[0]+ay*b[1]+az*b[2]; }
+
+// ---- Philox4x32-10, counter (ray_lo, ray_hi, source_id, purpose), key = seed -------------
+__device__ __forceinline__ void philox_uniform2(unsigned long long seed, uint32_t source_id, unsigned long long ray,
+                                                uint32_t purpose, double& u0, double& u1) {
+  uint32_t c0 = (uint32_t)ray, c1 = (uint32_t)(ray >> 32), c2 = source_id, c3 = purpose;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u*c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u*c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  unsigned long long a = ((unsigned long long)c0 << 32) | c1, b = ((unsigned long long)c2 << 32) | c3;
+  u0 = (double)(a >> 11)*(1.0/9007199254740992.0);
+  u1 = (double)(b >> 11)*(1.0/9007199254740992.0);
+}
+
+// ---- sampler (reference distributions/random_number_generator.py:413-456,492-500) --------
+__device__ __forceinline__ double linspace_at(double lo, double hi, int n, int i) {
+  return (i >= n-1) ? hi : lo + (double)i*((hi-lo)/(double)(n-1));
+}
+
+// numpy.interp(x, cdf, linspace(lo,hi,n)); guide[k] = last index with cdf[j] <= k/GUIDE
+__device__ __forceinline__ double interp_cdf(double x, const double* __restrict__ cdf, const uint32_t* __restrict__ guide,
+                                             int n, double lo, double hi) {
+  int k = (int)(x*(double)ODW_GUIDE);
+  if (k > ODW_GUIDE-1) k = ODW_GUIDE-1;
+  int a = (int)guide[k], b = (int)guide[k+1] + 1;     // cdf[a] <= x ; answer <= guide[k+1]
+  if (b > n) b = n;
+  while (b - a > 1) {
+    int m = (a + b) >> 1;
+    if (__ldg(cdf + m) <= x) a = m; else b = m;
+  }
+  if (a >= n-1) return hi;
+  double xa = __ldg(cdf + a), xb = __ldg(cdf + a + 1);
+  double fa = linspace_at(lo, hi, n, a);
+  if (xa == x) return fa;
+  double fb = linspace_at(lo, hi, n, a+1);
+  double slope = (fb - fa)/(xb - xa);
+  return slope*(x - xa) + fa;
+}
+
+__device__ __forceinline__ int nearest_row(double phi, double lo, double hi, int n_edges) {
+  int nrows = n_edges - 1;
+  double step = (hi - lo)/(double)(n_edges - 1);
+  int k = (int)floor((phi - lo)/step);
+  k = max(0, min(nrows-1, k));
+  int best = -1; double bestd = 0;
+  for (int i = k-2; i <= k+2; ++i) {
+    if (i < 0 || i >= nrows) continue;
+    double c = (linspace_at(lo, hi, n_edges, i+1) + linspace_at(lo, hi, n_edges, i))/2;
+    double d = fabs(c - phi);
+    if (best < 0 || d < bestd) { best = i; bestd = d; }
+  }
+  return best;
+}
+
+__device__ __forceinline__ void sample_source(const DSource& s, double u_phi, double u_first, double& first, double& phi) {
+  phi = interp_cdf(u_phi, s.phi_cdf, s.phi_guide, s.n_phi, s.phi_lo, s.phi_hi);
+  int row = 0;
+  if (s.n_rows > 1) row = nearest_row(phi, s.phi_lo, s.phi_hi, s.n_phi);
+  first = interp_cdf(u_first, s.first_cdf + (size_t)row*s.n_first, s.first_guide + (size_t)row*(ODW_GUIDE+1),
+                     s.n_first, s.first_lo, s.first_hi);
+}
+
+// PointSourceProxy._makeRay (reference freecad_elements/point_source.py:411-460)
+__device__ __forceinline__ void make_ray(const DSource& s, double first, double phi, double* o, double* d) {
+  double lo[3], ld[3];
+  double sp, cp; sincos(phi, &sp, &cp);
+  if (s.kind == ODW_SRC_POINT_SPHERICAL) {
+    double st, ct; sincos(first, &st, &ct);
+    ld[0] = st*sp; ld[1] = -st*cp; ld[2] = ct;
+    lo[0] = (0.0 - ld[0])*s.focal; lo[1] = (0.0 - ld[1])*s.focal; lo[2] = (1.0 - ld[2])*s.focal;
+  } else {
+    ld[0] = 0; ld[1] = 0; ld[2] = 1;
+    lo[0] = first*cp; lo[1] = -first*sp; lo[2] = 0;
+  }
+  double l = sqrt(dot3(ld, ld));
+  double q[3] = { lo[0]+ld[0]/l, lo[1]+ld[1]/l, lo[2]+ld[2]/l };
+  double p1[3], p2[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    p1[i] = s.M[4*i+0]*lo[0] + s.M[4*i+1]*lo[1] + s.M[4*i+2]*lo[2] + s.M[4*i+3];
+    p2[i] = s.M[4*i+0]*q[0]  + s.M[4*i+1]*q[1]  + s.M[4*i+2]*q[2]  + s.M[4*i+3];
+  }
+  double dx = p2[0]-p1[0], dy = p2[1]-p1[1], dz = p2[2]-p1[2];
+  double dl = sqrt(dx*dx + dy*dy + dz*dz);
+  o[0] = p1[0]; o[1] = p1[1]; o[2] = p1[2];
+  d[0] = dx/dl; d[1] = dy/dl; d[2] = dz/dl;
+}
+
+// ---- polynomial solvers -------------------------------------------------------------------
+__device__ __forceinline__ int solve_quadratic(double a, double b, double c, double* t) {
+  if (a == 0) { if (b == 0) return 0; t[0] = -c/b; return 1; }
+  double disc = b*b - 4*a*c;
+  if (disc < 0) return 0;
+  double sq = sqrt(disc);
+  double q = -0.5*(b + (b >= 0 ? sq : -sq));
+  t[0] = q/a;
+  t[1] = (q != 0) ? c/q : 0.0;
+  return 2;
+}
+
+__device__ __noinline__ int solve_cubic_depressed(double p, double q, double* y) {
+  int n = 0;
+  double disc = q*q/4 + p*p*p/27;
+  if (disc > 0) {
+    double sq = sqrt(disc);
+    y[n++] = cbrt(-q/2 + sq) + cbrt(-q/2 - sq);
+  } else if (p == 0) {
+    y[n++] = cbrt(-q);
+  } else {
+    double m = 2*sqrt(-p/3);
+    double arg = 3*q/(p*m);
+    arg = fmin(1.0, fmax(-1.0, arg));
+    double th = acos(arg)/3;
+    for (int k = 0; k < 3; ++k) y[n++] = m*cos(th - ODW_TWO_PI*k/3);
+  }
+  for (int i = 0; i < n; ++i)
+    for (int it = 0; it < 3; ++it) {
+      double f = (y[i]*y[i] + p)*y[i] + q, df = 3*y[i]*y[i] + p;
+      if (df != 0) y[i] -= f/df;
+    }
+  return n;
+}
+
+// real roots of t^4 + B t^2 + C t + D in [lo, hi]; monotone pieces between the critical points
+__device__ __noinline__ int solve_quartic_depressed(double B, double C, double D, double lo, double hi, double* roots) {
+  double crit[3];
+  int nc = solve_cubic_depressed(B/2, C/4, crit);
+  for (int i = 0; i < nc; ++i) for (int j = i+1; j < nc; ++j)
+    if (crit[j] < crit[i]) { double t = crit[i]; crit[i] = crit[j]; crit[j] = t; }
+  double knots[5]; int nk = 0;
+  knots[nk++] = lo;
+  for (int i = 0; i < nc; ++i) if (crit[i] > lo && crit[i] < hi) knots[nk++] = crit[i];
+  knots[nk++] = hi;
+  int n = 0;
+  for (int i = 0; i+1 < nk; ++i) {
+    double a = knots[i], b = knots[i+1];
+    double fa = ((a*a + B)*a + C)*a + D, fb = ((b*b + B)*b + C)*b + D;
+    if (fa == 0) { roots[n++] = a; continue; }
+    if (i+2 == nk && fb == 0) { roots[n++] = b; continue; }
+    if ((fa > 0) == (fb > 0)) continue;
+    double x = 0.5*(a+b);
+    for (int it = 0; it < 200; ++it) {
+      double f = ((x*x + B)*x + C)*x + D;
+      if ((f > 0) == (fa > 0)) { a = x; fa = f; } else { b = x; fb = f; }
+      double df = (4*x*x + 2*B)*x + C;
+      double xn = (df != 0) ? x - f/df : 0.5*(a+b);
+      if (!(xn > a && xn < b)) xn = 0.5*(a+b);
+      if (fabs(xn - x) <= 1e-16*fmax(1.0, fabs(x))) { x = xn; break; }
+      x = xn;
+    }
+    roots[n++] = x;
+  }
+  return n;
+}
+
+// ---- line / untrimmed surface (ray.py:411, infinite line, all points) ----------------------
+__device__ __noinline__ int line_torus(const DFace& f, const double* w, const double* d, double* t) {
+  double R = f.p0, r = f.p1;
+  double t0 = -dot3(w, d);
+  double o[3] = { w[0]+t0*d[0], w[1]+t0*d[1], w[2]+t0*d[2] };
+  double m = dot3(o, o), rr = (R + r)*(R + r);
+  if (m > rr) return 0;
+  double half = sqrt(rr - m) + 1e-9;
+  double oz = dot3(o, f.z), dz = dot3(d, f.z);
+  double oxy2 = m - oz*oz, dxy2 = 1.0 - dz*dz, g = -oz*dz;
+  double K = m + R*R - r*r;
+  double roots[4];
+  int n = solve_quartic_depressed(2*K - 4*R*R*dxy2, -8*R*R*g, K*K - 4*R*R*oxy2, -half, half, roots);
+  for (int i = 0; i < n; ++i) t[i] = t0 + roots[i];
+  return n;
+}
+
+__device__ __forceinline__ int line_surface(const DFace& f, const double* s, const double* d, double* t) {
+  double w[3] = { s[0]-f.o[0], s[1]-f.o[1], s[2]-f.o[2] };
+  switch (f.kind) {
+    case ODW_SURF_PLANE: {
+      double den = dot3(d, f.z);
+      if (den == 0) return 0;
+      t[0] = -dot3(w, f.z)/den;
+      return 1;
+    }
+    case ODW_SURF_SPHERE:
+      return solve_quadratic(1.0, 2*dot3(w, d), dot3(w, w) - f.p0*f.p0, t);
+    case ODW_SURF_CYLINDER: {
+      double wz = dot3(w, f.z), dz = dot3(d, f.z);
+      double a = 1.0 - dz*dz;
+      if (fabs(a) < 1e-300) return 0;
+      return solve_quadratic(a, 2*(dot3(w, d) - wz*dz), dot3(w, w) - wz*wz - f.p0*f.p0, t);
+    }
+    case ODW_SURF_CONE: {
+      double ta = tan(f.p1);
+      double wz = dot3(w, f.z), dz = dot3(d, f.z);
+      double r0 = f.p0 + wz*ta, r1 = dz*ta;
+      return solve_quadratic(1.0 - dz*dz - r1*r1, 2*(dot3(w, d) - wz*dz - r0*r1), dot3(w, w) - wz*wz - r0*r0, t);
+    }
+    case ODW_SURF_TORUS:
+      return line_torus(f, w, d, t);
+  }
+  return 0;
+}
+
+// ---- point on trimmed face (ray.py:426, distToShape(face) < distTol) in (u,v) space ---------
+__device__ __forceinline__ double wrap_into(double x, double lo) { return x - ODW_TWO_PI*floor((x - lo)/ODW_TWO_PI); }
+
+__device__ __noinline__ bool loops_contain(const DFace& f, const odw_trimseg* __restrict__ segs, double u, double v,
+                                           double su, double sv, double tol) {
+  int crossings = 0;
+  for (int i = 0; i < f.seg_count; ++i) {
+    const odw_trimseg& s = segs[f.seg_first + i];
+    const double* a = s.a;
+    if (s.kind == ODW_SEG_LINE) {
+      if ((a[1] > v) != (a[3] > v)) {
+        double ux = a[0] + (v - a[1])*(a[2] - a[0])/(a[3] - a[1]);
+        if (ux > u) ++crossings;
+      }
+      double ax = a[0]*su, ay = a[1]*sv, bx = a[2]*su, by = a[3]*sv, px = u*su, py = v*sv;
+      double dx = bx-ax, dy = by-ay, l2 = dx*dx + dy*dy;
+      double tt = l2 > 0 ? ((px-ax)*dx + (py-ay)*dy)/l2 : 0;
+      tt = fmin(1.0, fmax(0.0, tt));
+      double qx = ax + tt*dx - px, qy = ay + tt*dy - py;
+      if (sqrt(qx*qx + qy*qy) < tol) return true;
+    } else {
+      double cu = a[0], cv = a[1], r = a[2], a0 = a[3], span = a[4];
+      double dv = v - cv, du = u - cu;
+      bool full = span >= ODW_TWO_PI - 1e-12;
+      if (fabs(dv) < r) {
+        double h = sqrt(r*r - dv*dv);
+        if (full) {
+          if (cu - h > u) ++crossings;
+          if (cu + h > u) ++crossings;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            double ux = k ? cu + h : cu - h;
+            if (ux > u) {
+              double rel = atan2(dv, ux - cu) - a0; rel -= ODW_TWO_PI*floor(rel/ODW_TWO_PI);
+              if (rel <= span) ++crossings;
+            }
+          }
+        }
+      }
+      double rad = sqrt(du*du + dv*dv);
+      if (fabs(rad - r)*fmin(su, sv) < tol) {
+        if (full) return true;
+        double rel = atan2(dv, du) - a0; rel -= ODW_TWO_PI*floor(rel/ODW_TWO_PI);
+        if (rel <= span) return true;
+      }
+    }
+  }
+  return (crossings & 1) != 0;
+}
+
+// P on the untrimmed surface of f.  returns true iff P lies on the trimmed face dilated by tol.
+__device__ __forceinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* __restrict__ segs, const double* P, double tol) {
+  if (f.trim == ODW_TRIM_NONE) return true;
+  double w[3] = { P[0]-f.o[0], P[1]-f.o[1], P[2]-f.o[2] };
+  double x = dot3(w, f.x), y = dot3(w, f.y);
+  double u, v, su = 1, sv = 1;
+  bool uper = true, vper = false;
+  switch (f.kind) {
+    case ODW_SURF_PLANE: u = x; v = y; uper = false; break;
+    case ODW_SURF_CYLINDER: v = dot3(w, f.z); su = f.p0; u = 0; break;
+    case ODW_SURF_CONE: {
+      double sa, ca; sincos(f.p1, &sa, &ca);
+      v = dot3(w, f.z)/ca;
+      double rs = f.p0 + v*sa;
+      if (rs < 0) { x = -x; y = -y; }
+      su = fabs(rs); u = 0; break;
+    }
+    case ODW_SURF_SPHERE: {
+      double sn = fmin(1.0, fmax(-1.0, dot3(w, f.z)/f.p0));
+      v = asin(sn); su = f.p0*sqrt(fmax(0.0, 1 - sn*sn)); sv = f.p0; u = 0; break;
+    }
+    default: {   // torus
+      double rho = sqrt(x*x + y*y);
+      v = atan2(dot3(w, f.z), rho - f.p0);
+      su = rho; sv = f.p1; vper = true; u = 0; break;
+    }
+  }
+  su = fmax(su, 1e-12);
+  double tu = tol/su, tv = tol/sv;
+  if (vper) v = wrap_into(v, f.vmin - tv);
+  if (v < f.vmin - tv || v > f.vmax + tv) return false;
+  if (uper) {
+    if (!(f.flags & DFACE_FULL_U) || f.trim == ODW_TRIM_LOOPS) {
+      u = wrap_into(atan2(y, x), f.umin - tu);
+      if (u < f.umin - tu || u > f.umax + tu) return false;
+    }
+  } else {
+    if (u < f.umin - tu || u > f.umax + tu) return false;
+  }
+  if (f.trim == ODW_TRIM_UVBOX) return true;
+  return loops_contain(f, segs, u, v, su, sv, tol);
+}
+
+// outward unit normal at P (ray.py:463-465 + face orientation)
+__device__ __forceinline__ void outward_normal(const DFace& f, const double* P, double* n) {
+  double w[3] = { P[0]-f.o[0], P[1]-f.o[1], P[2]-f.o[2] };
+  double g[3];
+  switch (f.kind) {
+    case ODW_SURF_PLANE: g[0] = f.z[0]; g[1] = f.z[1]; g[2] = f.z[2]; break;
+    case ODW_SURF_SPHERE: g[0] = w[0]; g[1] = w[1]; g[2] = w[2]; break;
+    case ODW_SURF_CYLINDER: {
+      double z = dot3(w, f.z);
+      g[0] = w[0]-z*f.z[0]; g[1] = w[1]-z*f.z[1]; g[2] = w[2]-z*f.z[2]; break;
+    }
+    case ODW_SURF_CONE: {
+      double sa, ca; sincos(f.p1, &sa, &ca);
+      double z = dot3(w, f.z);
+      double rx = w[0]-z*f.z[0], ry = w[1]-z*f.z[1], rz = w[2]-z*f.z[2];
+      double rho = sqrt(rx*rx + ry*ry + rz*rz);
+      double sg = (f.p0 + z/ca*sa) >= 0 ? 1.0 : -1.0;
+      g[0] = ca*rx/rho - sg*sa*f.z[0]; g[1] = ca*ry/rho - sg*sa*f.z[1]; g[2] = ca*rz/rho - sg*sa*f.z[2]; break;
+    }
+    default: {
+      double z = dot3(w, f.z);
+      double rx = w[0]-z*f.z[0], ry = w[1]-z*f.z[1], rz = w[2]-z*f.z[2];
+      double k = f.p0/sqrt(rx*rx + ry*ry + rz*rz);
+      g[0] = w[0]-k*rx; g[1] = w[1]-k*ry; g[2] = w[2]-k*rz; break;
+    }
+  }
+  double s = (double)f.nsign/sqrt(dot3(g, g));
+  n[0] = g[0]*s; n[1] = g[1]*s; n[2] = g[2]*s;
+}
+
+// ---- Ray.mirror / snellsLaw / lineGrating (ray.py:482-539) ---------------------------------
+__device__ __forceinline__ void mirror_dir(const double* ray, const double* n, double* out) {
+  double k = 2*dot3(ray, n);
+  out[0] = ray[0]-k*n[0]; out[1] = ray[1]-k*n[1]; out[2] = ray[2]-k*n[2];
+}
+
+__device__ __forceinline__ bool snell(const double* ray, double n1, double n2, const double* n, double* out) {
+  double cx = n[1]*ray[2]-n[2]*ray[1], cy = n[2]*ray[0]-n[0]*ray[2], cz = n[0]*ray[1]-n[1]*ray[0];
+  double mu = n1/n2;
+  double root = 1 - mu*mu*(cx*cx + cy*cy + cz*cz);
+  if (root < 0) { mirror_dir(ray, n, out); return true; }
+  // n x ((-n) x ray) = ray (n.n) - n (n.ray)
+  double nn = dot3(n, n), nr = dot3(n, ray), s = sqrt(root);
+  out[0] = mu*(ray[0]*nn - n[0]*nr) + n[0]*s;
+  out[1] = mu*(ray[1]*nn - n[1]*nr) + n[1]*s;
+  out[2] = mu*(ray[2]*nn - n[2]*nr) + n[2]*s;
+  return false;
+}
+
+__device__ __noinline__ void line_grating(const double* ray_in, double n1, double n2, const double* normal, const DGroup& g,
+                                          double wavelength_nm, bool transmission, double* out) {
+  double wl = wavelength_nm/1000.0;
+  double rl = sqrt(dot3(ray_in, ray_in)), nl = sqrt(dot3(normal, normal)), gl = sqrt(dot3(g.gdir, g.gdir));
+  double ray[3], sn[3], gv[3];
+  for (int i = 0; i < 3; ++i) { ray[i] = ray_in[i]/rl; sn[i] = normal[i]/nl; gv[i] = g.gdir[i]/gl; }
+  double P[3] = { gv[1]*sn[2]-gv[2]*sn[1], gv[2]*sn[0]-gv[0]*sn[2], gv[0]*sn[1]-gv[1]*sn[0] };
+  double pl = sqrt(dot3(P, P)); P[0] /= pl; P[1] /= pl; P[2] /= pl;
+  double D[3] = { sn[1]*P[2]-sn[2]*P[1], sn[2]*P[0]-sn[0]*P[2], sn[0]*P[1]-sn[1]*P[0] };
+  double dl = sqrt(dot3(D, D)); D[0] /= dl; D[1] /= dl; D[2] /= dl;
+  double mu = n1/n2, d = 1000.0/g.lpm;
+  double T = (g.order*wl)/(n1*d);
+  double nn = dot3(sn, sn);
+  double V = (mu*dot3(ray, sn))/nn;
+  double W = (mu*mu - 1 + T*T - 2*mu*T*dot3(ray, D))/nn;
+  double sq = sqrt((2*V)*(2*V) - 4*W);
+  double q1 = (-2*V + sq)/2, q2 = (-2*V - sq)/2;
+  double Q = transmission ? fmin(q1, q2) : fmax(q1, q2);
+  for (int i = 0; i < 3; ++i) out[i] = -(mu*ray[i] - T*D[i] + Q*sn[i]);
+}
+#endif  // ODW_DEVICE_CODE

@@ -1,0 +1,312 @@
+// odw_kernels.cu — sm_100a trace kernels.
+//
+// One thread owns one ray for its whole life: the bounce loop of Ray.traceRay (reference
+// freecad_elements/ray.py:36-281) runs in registers, so the only HBM traffic is the hit append (and the
+// explicit-ray input when there is one).  MC rays are generated in the kernel from a Philox4x32-10
+// counter = global ray index, so the result does not depend on how a ray range is split
+// over launches or GPUs.  Small scenes are staged in shared memory and tested face by face (uniform loop,
+// no divergence between lanes of a warp); large scenes walk a BVH with a per-thread short stack.
+#include <cooperative_groups.h>
+#define ODW_DEVICE_CODE
+#include "odw_device.cuh"
+
+namespace cg = cooperative_groups;
+
+struct NearestHit {
+  double tA, tB;     // closest accepted hit overall / closest whose group differs from the current medium
+  int fA, fB;
+};
+
+template <typename FacePtr>
+__device__ __forceinline__ void test_face(const FacePtr faces, int idx, const TraceParams& p, const double* s, const double* dn,
+                                          int medium, int seq_index, double max_len, NearestHit& h) {
+  const DFace& f = faces[idx];
+  if (p.sequential) {
+    if (seq_index >= 128 || !((f.seqmask[seq_index >> 6] >> (seq_index & 63)) & 1ull)) return;
+  }
+  if (f.group < 256 && ((p.ignore_mask[f.group >> 6] >> (f.group & 63)) & 1ull)) return;   // IgnoredOpticalElements
+  const double tol = p.tol;
+  if (f.kind == ODW_SURF_TORUS || f.trim == ODW_TRIM_LOOPS) {
+    // slab test against the face's box (ray.py:390-398 culls with the face BoundBox the same way);
+    // 1/0 = inf is fine here: fmin/fmax drop the NaN of 0*inf
+    double t0 = -1e300, t1 = 1e300;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double inv = 1.0/dn[i];
+      double ta = (f.bmin[i] - tol - s[i])*inv, tb = (f.bmax[i] + tol - s[i])*inv;
+      t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+    }
+    if (t0 > t1) return;
+  }
+  double ts[4];
+  int nt = line_surface(f, s, dn, ts);
+  for (int k = 0; k < nt; ++k) {
+    double t = ts[k];
+    if (!(t > tol)) continue;                                        // ray.py:424  |P - start| > distTol (and forward)
+    if (!(t < max_len + tol) || !(t < h.tA + 2*tol)) continue;        // ray.py:425,432,440
+    double P[3] = { s[0]+t*dn[0], s[1]+t*dn[1], s[2]+t*dn[2] };
+    if (!on_trimmed_face(f, p.scene.segs, P, tol)) continue;         // ray.py:426
+    if (t < h.tA) { h.tA = t; h.fA = idx; }
+    if (f.group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
+  }
+}
+
+// Ray.findNearestIntersection (ray.py:290-452): brute force over faces staged in shared memory
+__device__ __forceinline__ int find_nearest_smem(const DFace* sfaces, const TraceParams& p, const double* s, const double* dn,
+                                                 int medium, int seq_index, double max_len, double& t_out) {
+  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.fA = -1; h.fB = -1;
+  const int n = p.scene.n_faces;
+  for (int i = 0; i < n; ++i) test_face(sfaces, i, p, s, dn, medium, seq_index, max_len, h);
+  if (h.fA < 0) return -1;
+  if (h.fB >= 0 && h.tB < h.tA + 2*p.tol) { t_out = h.tB; return h.fB; }   // prefer "not the current medium" (ray.py:445-452)
+  t_out = h.tA; return h.fA;
+}
+
+// same rule, faces reached through a BVH over face boxes (replaces the shell/face BoundBox culls of ray.py:345-404)
+__device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const double* s, const double* dn,
+                                                int medium, int seq_index, double max_len, double& t_out) {
+  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.fA = -1; h.fB = -1;
+  const BvhNode* __restrict__ nodes = p.scene.bvh;
+  const double tol = p.tol;
+  double inv[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) inv[i] = 1.0/dn[i];
+  int stack[48]; int sp = 0;
+  stack[sp++] = 0;
+  while (sp > 0) {
+    int ni = stack[--sp];
+    // one 32-byte node = two 128-bit loads
+    const float4* np4 = reinterpret_cast<const float4*>(nodes + ni);
+    float4 a = __ldg(np4), b = __ldg(np4 + 1);
+    double lo[3] = { a.x, a.y, a.z }, hi[3] = { a.w, b.x, b.y };
+    int left = __float_as_int(b.z), count = __float_as_int(b.w);
+    double t0 = -tol, t1 = fmin(max_len + tol, h.tA + 2*tol);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double ta = (lo[i] - tol - s[i])*inv[i], tb = (hi[i] + tol - s[i])*inv[i];
+      t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+    }
+    if (t0 > t1) continue;
+    if (count == 0) {
+      if (sp < 46) { stack[sp++] = left; stack[sp++] = left + 1; }
+    } else {
+      for (int k = 0; k < count; ++k)
+        test_face(p.scene.faces, __ldg(p.scene.bvh_prims + left + k), p, s, dn, medium, seq_index, max_len, h);
+    }
+  }
+  if (h.fA < 0) return -1;
+  if (h.fB >= 0 && h.tB < h.tA + 2*tol) { t_out = h.tB; return h.fB; }
+  t_out = h.tA; return h.fA;
+}
+
+// OpticalGroupProxy.onRayHit -> SimulationResults.addRayHit (optical_group.py:206-209, results_store.py:641-648):
+// warp-aggregated append (one atomic per converged group of lanes) + optional detector binning
+__device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long long ray, int bounce, int group, int face_id,
+                                           const double* P, const double* dir, double power, bool entering,
+                                           unsigned int& n_hits, unsigned int& n_dropped) {
+  for (int b = 0; b < p.n_binnings; ++b) {
+    const DBinning& bn = p.binnings[b];
+    if (bn.group != group) continue;
+    double w[3] = { P[0]-bn.origin[0], P[1]-bn.origin[1], P[2]-bn.origin[2] };
+    double x = dot3(w, bn.ua), y = dot3(w, bn.va);
+    if (x >= bn.u_lo && x <= bn.u_hi && y >= bn.v_lo && y <= bn.v_hi) {
+      int ix = min(bn.nu-1, (int)((x - bn.u_lo)*bn.u_scale));
+      int iy = min(bn.nv-1, (int)((y - bn.v_lo)*bn.v_scale));
+      atomicAdd(p.bins + bn.offset + (size_t)ix*bn.nv + iy, bn.weighted ? power : 1.0);
+    }
+  }
+  ++n_hits;
+  if (!p.store_hits) return;
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(&p.counters->hits, (unsigned long long)g.size());
+  base = g.shfl(base, 0);
+  unsigned long long slot = base + g.thread_rank();
+  if (slot >= p.hits.capacity) { ++n_dropped; return; }
+  double* hp = p.hits.points + 3*slot; hp[0] = P[0]; hp[1] = P[1]; hp[2] = P[2];
+  double* hd = p.hits.dirs + 3*slot;   hd[0] = dir[0]; hd[1] = dir[1]; hd[2] = dir[2];
+  p.hits.powers[slot] = power;
+  p.hits.entering[slot] = entering ? 1 : 0;
+  p.hits.ray_index[slot] = ray;
+  p.hits.group[slot] = group;
+  p.hits.bounce[slot] = bounce;
+  p.hits.face_id[slot] = face_id;
+}
+
+template <bool MC, bool BVH>
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DFace* sfaces = reinterpret_cast<DFace*>(smem_raw);
+  if (!BVH) {
+    // stage the scene: 16-byte vector copies, coalesced
+    const int4* src = reinterpret_cast<const int4*>(p.scene.faces);
+    int4* dst = reinterpret_cast<int4*>(smem_raw);
+    const int n16 = (int)((size_t)p.scene.n_faces*sizeof(DFace)/16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+  }
+  const DGroup* __restrict__ groups = p.scene.groups;
+  unsigned int nseg_acc = 0, nhit_acc = 0, ndrop_acc = 0, nesc_acc = 0, ndepth_acc = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < p.n_rays; i += stride) {
+    const unsigned long long ray = p.first_ray + i;
+    double point[3], dir[3], power;
+    if (MC) {
+      double u0, u1, first, phi;
+      philox_uniform2(p.seed, (uint32_t)p.src.source_id, ray, 0u, u0, u1);
+      sample_source(p.src, u0, u1, first, phi);
+      make_ray(p.src, first, phi, point, dir);
+      power = 1.0;
+    } else {
+      const double* o = p.in_origins + 3*i; const double* d = p.in_dirs + 3*i;
+      point[0] = o[0]; point[1] = o[1]; point[2] = o[2];
+      dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
+      power = p.in_powers ? p.in_powers[i] : 1.0;
+    }
+    int medium = -1, seq_index = 0, n_isect = 0, nseg = 0;
+    for (;;) {
+      if (n_isect >= p.max_isect) { ++ndepth_acc; break; }                     // ray.py:96-98
+      ++n_isect;
+      double dl = sqrt(dot3(dir, dir));
+      double dn[3] = { dir[0]/dl, dir[1]/dl, dir[2]/dl };
+      double t;
+      int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
+                   : find_nearest_smem(sfaces, p, point, dn, medium, seq_index, p.max_len, t);
+      if (fi < 0) {                                                            // ray.py:105-109
+        point[0] += dn[0]*p.max_len; point[1] += dn[1]*p.max_len; point[2] += dn[2]*p.max_len;
+        ++nseg; ++nesc_acc;
+        break;
+      }
+      const DFace& f = BVH ? p.scene.faces[fi] : sfaces[fi];
+      const int fgroup = f.group;
+      const DGroup& g = groups[fgroup];
+      point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];
+      ++nseg;                                                                  // ray.py:117
+      if (medium >= 0) {                                                       // ray.py:120-125 (multiplicative)
+        double L = groups[medium].absorption_length;
+        if (L == 0) power = 0; else if (isfinite(L)) power *= exp(-t/L);
+      }
+      double nrm[3];
+      outward_normal(f, point, nrm);
+      const bool entering = dot3(dn, nrm) < 0;                                 // ray.py:473-480
+      if (entering) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
+      if (g.record || p.record_all)
+        record_hit(p, ray, n_isect-1, fgroup, f.face_id, point, dir, power, entering, nhit_acc, ndrop_acc);
+      switch (g.type) {
+        case ODW_OPT_MIRROR: {                                                 // ray.py:146-161
+          double o[3]; mirror_dir(dir, nrm, o);
+          dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+          power *= g.reflectivity; ++seq_index;
+          break;
+        }
+        case ODW_OPT_LENS: {                                                   // ray.py:165-211
+          double n1 = medium >= 0 ? groups[medium].n : 1.0, n2 = 1.0;
+          if (entering) { medium = fgroup; n2 = g.n; }
+          double o[3];
+          bool tir = snell(dn, n1, n2, nrm, o);
+          dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+          if (!entering && !tir && medium == fgroup) { medium = -1; ++seq_index; }
+          break;
+        }
+        case ODW_OPT_GRATING: {                                                // ray.py:216-268
+          double o[3];
+          if (g.gtype == ODW_GRATING_REFLECTION) {
+            if (entering) {
+              double n = medium >= 0 ? groups[medium].n : 1.0;
+              line_grating(dn, n, n, nrm, g, p.wavelength, false, o);
+              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2]; ++seq_index;
+            }
+          } else if (entering) {
+            if (medium >= 0) { power = 0; break; }                             // the reference raises ValueError here
+            medium = fgroup;
+            line_grating(dn, 1.0, g.n, nrm, g, p.wavelength, true, o);
+            dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+          } else {
+            double n1 = medium >= 0 ? groups[medium].n : 1.0;
+            bool tir = snell(dn, n1, 1.0, nrm, o);
+            dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+            if (!tir) { medium = -1; ++seq_index; }
+          }
+          break;
+        }
+        case ODW_OPT_ABSORBER: power = 0; ++seq_index; break;                  // ray.py:271-273
+        default: ++seq_index; break;                                           // Vacuum, ray.py:276-277
+      }
+      if (power < p.power_tol) break;                                          // ray.py:280
+    }
+    nseg_acc += nseg;
+    if (!MC) {
+      if (p.out_nseg) p.out_nseg[i] = nseg;
+      if (p.out_final_point) { double* q = p.out_final_point + 3*i; q[0] = point[0]; q[1] = point[1]; q[2] = point[2]; }
+      if (p.out_final_power) p.out_final_power[i] = power;
+    }
+  }
+  // per-warp reduction of the counters, one atomic per warp and counter
+  nseg_acc = __reduce_add_sync(0xffffffffu, nseg_acc);
+  nhit_acc = __reduce_add_sync(0xffffffffu, nhit_acc);
+  ndrop_acc = __reduce_add_sync(0xffffffffu, ndrop_acc);
+  nesc_acc = __reduce_add_sync(0xffffffffu, nesc_acc);
+  ndepth_acc = __reduce_add_sync(0xffffffffu, ndepth_acc);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&p.counters->segments, (unsigned long long)nseg_acc);
+    if (!p.store_hits) atomicAdd(&p.counters->hits, (unsigned long long)nhit_acc);
+    if (ndrop_acc) atomicAdd(&p.counters->hits_dropped, (unsigned long long)ndrop_acc);
+    if (nesc_acc) atomicAdd(&p.counters->escaped, (unsigned long long)nesc_acc);
+    if (ndepth_acc) atomicAdd(&p.counters->depth_terminated, (unsigned long long)ndepth_acc);
+  }
+}
+
+// draws only (odw_sample_mc): same Philox counters and tables as the MC trace kernel
+__global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long long seed, unsigned long long first_ray,
+                                                     unsigned long long n, double* first_out, double* phi_out,
+                                                     double* origins, double* dirs) {
+  const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {
+    double u0, u1, first, phi, o[3], d[3];
+    philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, u0, u1);
+    sample_source(src, u0, u1, first, phi);
+    make_ray(src, first, phi, o, d);
+    if (first_out) first_out[i] = first;
+    if (phi_out) phi_out[i] = phi;
+    if (origins) { origins[3*i] = o[0]; origins[3*i+1] = o[1]; origins[3*i+2] = o[2]; }
+    if (dirs) { dirs[3*i] = d[0]; dirs[3*i+1] = d[1]; dirs[3*i+2] = d[2]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers used by odw_api.cu
+
+extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int blocks, size_t smem, cudaStream_t st) {
+  if (mc) {
+    if (bvh) trace_kernel<true, true><<<blocks, 256, 0, st>>>(*p);
+    else {
+      cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      trace_kernel<true, false><<<blocks, 256, smem, st>>>(*p);
+    }
+  } else {
+    if (bvh) trace_kernel<false, true><<<blocks, 256, 0, st>>>(*p);
+    else {
+      cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      trace_kernel<false, false><<<blocks, 256, smem, st>>>(*p);
+    }
+  }
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
+                                         unsigned long long n, double* first_out, double* phi_out, double* origins,
+                                         double* dirs, int blocks, cudaStream_t st) {
+  sample_kernel<<<blocks, 256, 0, st>>>(*src, seed, first_ray, n, first_out, phi_out, origins, dirs);
+  return cudaGetLastError();
+}
+
+extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem) {
+  int nb = 0;
+  if (mc && bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, true>, 256, 0);
+  else if (mc) { cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, 256, smem); }
+  else if (bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, true>, 256, 0);
+  else { cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, 256, smem); }
+  return nb;
+}
