@@ -139,6 +139,12 @@ extern "C" int odw_engine_device_name(const odw_engine* eng, char* buf, int bufl
   return ODW_OK;
 }
 
+extern "C" int odw_engine_stream(const odw_engine* eng, void** stream_out) {
+  if (!eng || !stream_out) return fail(ODW_EINVAL, "odw_engine_stream: bad argument");
+  *stream_out = (void*)eng->stream;
+  return ODW_OK;
+}
+
 template <typename T>
 static int upload(odw_engine* eng, std::vector<void*>& owned, const T* host, size_t n, const T** dev) {
   void* p = nullptr;

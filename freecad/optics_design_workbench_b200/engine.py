@@ -18,7 +18,7 @@ from . import _abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libodw_b200.so')
 
-EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name',
+EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name', 'odw_engine_stream',
            'odw_scene_create', 'odw_scene_destroy', 'odw_source_create', 'odw_source_destroy',
            'odw_trace_mc', 'odw_sample_mc', 'odw_trace_rays', 'odw_result_counts', 'odw_result_hits',
            'odw_result_histogram', 'odw_result_histogram_device', 'odw_result_ray_summary',
@@ -60,6 +60,7 @@ def load_library():
   L.odw_engine_create.argtypes = [C.c_int, C.POINTER(vp)]
   L.odw_engine_destroy.argtypes = [vp]; L.odw_engine_destroy.restype = None
   L.odw_engine_device_name.argtypes = [vp, C.c_char_p, C.c_int]
+  L.odw_engine_stream.argtypes = [vp, C.POINTER(vp)]
   L.odw_scene_create.argtypes = [vp, vp, C.POINTER(vp)]
   L.odw_scene_destroy.argtypes = [vp]; L.odw_scene_destroy.restype = None
   L.odw_source_create.argtypes = [vp, vp, C.POINTER(vp)]
@@ -226,6 +227,12 @@ class Engine:
     buf = C.create_string_buffer(256)
     _check(load_library().odw_engine_device_name(self._h, buf, 256))
     return buf.value.decode()
+
+  def stream_handle(self):
+    'raw cudaStream_t of the engine (wrap with torch.cuda.ExternalStream to record events on it)'
+    st = C.c_void_p()
+    _check(load_library().odw_engine_stream(self._h, C.byref(st)))
+    return st.value or 0
 
   def scene(self, scene):
     return DeviceScene(self, scene)

@@ -218,7 +218,14 @@ class FCStdDocument:
     return []
 
   def parents(self, obj):
-    return [self.objects[n] for n in self.order if obj.Name in self.children(self.objects[n])]
+    '''
+    Containers claiming obj.  A plain App::DocumentObjectGroup inside an App::Part lists its members a
+    second time (the Part's Group holds them too); such a group adds no placement and no new instance,
+    so it only counts as a parent when no geometric container claims the object.
+    '''
+    ps = [self.objects[n] for n in self.order if obj.Name in self.children(self.objects[n])]
+    geo = [p for p in ps if not p.TypeId.startswith('App::DocumentObjectGroup')]
+    return geo if geo else ps
 
   def links_to(self, obj):
     return [self.objects[n] for n in self.order

@@ -132,7 +132,7 @@ def point_in_segs(segs, u, v):
   '''
   Even-odd test of (u, v) against trim segments given as (kind, a) tuples or SEG_DTYPE rows:
   count crossings of the half-line {(u', v): u' > u}.  numpy restatement used by tests/export;
-  the oracle (oracle/odw_oracle.c) and the CUDA kernel implement the same rule.
+  the CUDA kernel (csrc/odw_device.cuh loops_contain) implements the same rule.
   '''
   crossings = 0
   for s in segs:

@@ -232,6 +232,8 @@ const char* odw_last_error(void);
 int  odw_engine_create(int device_id, odw_engine** out);
 void odw_engine_destroy(odw_engine*);
 int  odw_engine_device_name(const odw_engine*, char* buf, int buflen);
+/* the cudaStream_t every kernel/copy of this engine is issued on (so callers can time it with events) */
+int  odw_engine_stream(const odw_engine*, void** stream_out);
 
 int  odw_scene_create(odw_engine*, const odw_scene_desc*, odw_scene** out);
 void odw_scene_destroy(odw_scene*);

@@ -1,0 +1,65 @@
+'''
+The C-ABI library loads and exports every symbol include/odw.h declares; without a GPU the product path
+fails loudly instead of falling back to anything on the CPU.  No compute calls here.
+'''
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from freecad.optics_design_workbench_b200 import engine, _abi
+from freecad.optics_design_workbench_b200.scene_export import scene as sc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+  text = open(os.path.join(ROOT, 'include', 'odw.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(odw_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+  lib = engine.load_library()
+  names = declared_functions()
+  assert len(names) >= 19
+  for n in names:
+    assert hasattr(lib, n), f'{n} declared in include/odw.h but not exported by libodw_b200.so'
+  assert set(names) == set(engine.EXPORTS)
+  assert lib.odw_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+  'numpy dtypes / ctypes structs mirror the C structs (sizes the kernels rely on)'
+  assert sc.FACE_DTYPE.itemsize == 224 and sc.SEG_DTYPE.itemsize == 48
+  assert sc.SHELL_DTYPE.itemsize == 64 and sc.GROUP_DTYPE.itemsize == 80
+  assert C.sizeof(_abi.SceneDesc) == 24+6*8
+  assert C.sizeof(_abi.Counts) == 64
+  assert C.sizeof(_abi.HitsView) == 72
+  assert C.sizeof(_abi.Binning) == 16+9*8+4*8
+  assert C.sizeof(_abi.SourceDesc) == 24+8*8+16*8+3*8
+  assert C.sizeof(_abi.TraceCfg) == 3*8+6*4+8+8
+
+
+@pytest.mark.skipif(os.environ.get('ODW_EXPECT_GPU') == '1', reason='GPU box')
+def test_no_cpu_fallback_without_device():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('a CUDA device is present')
+  with pytest.raises(engine.EngineError) as e:
+    engine.Engine(0)
+  assert e.value.code == _abi.ODW_ENODEVICE
+  assert 'no CPU fallback' in str(e.value)
+
+
+def test_product_package_does_not_import_oracle():
+  'the oracle is test infrastructure: nothing under the product package may import it'
+  pkg = os.path.join(ROOT, 'freecad', 'optics_design_workbench_b200')
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+        text = open(os.path.join(dirpath, f)).read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f'{f} imports oracle'
+        assert 'odw_oracle' not in text, f'{f} references the oracle library'

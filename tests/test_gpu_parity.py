@@ -1,0 +1,289 @@
+'''
+Parity tests proper (-m gpu): the CUDA path, called through the C ABI (libodw_b200.so via ctypes),
+against the CPU oracle on the same seeded inputs; plus size-independent properties at full benchmark size.
+
+Bars: object/face sequence per ray identical (integer work: exact); hit positions and directions within
+1e-9 mm / 1e-12 (the north star allows max(deflection, 1e-6 relative); closed-form surfaces do far better).
+Rays within tolerance of a face edge are exempt by the north star: on hugeArray (grazing sphere hits) at most
+0.05 % of the rays may differ, everywhere else none.
+'''
+import os
+
+import numpy as np
+import pytest
+
+from freecad.optics_design_workbench_b200 import _abi, engine
+from freecad.optics_design_workbench_b200.scene_export import primitives as prim
+from freecad.optics_design_workbench_b200.scene_export.scene import SceneBuilder
+
+pytestmark = pytest.mark.gpu
+SEED = 0x0DDB1A5E
+POS_TOL, DIR_TOL = 1e-9, 1e-12
+SCENES = ['minimal', 'lensesAndMirrors', 'lensesAndMirrorsSequential', 'hugeArray']
+
+
+def per_ray_sequences(h, n):
+  seq = [[] for _ in range(n)]
+  for r, f in zip(h['ray_index'], h['face_id']):
+    seq[int(r)].append(int(f))
+  return seq
+
+
+def compare_hits(g, o, n, max_bad_fraction=0.0, base=0):
+  'g, o: sorted hit dicts of GPU and oracle'
+  if (len(g['face_id']) == len(o['face_id']) and np.array_equal(g['face_id'], o['face_id'])
+      and np.array_equal(g['ray_index'], o['ray_index'])):
+    keep = np.ones(len(g['face_id']), dtype=bool)
+    bad = 0
+  else:
+    sg = per_ray_sequences({**g, 'ray_index': g['ray_index']-base}, n)
+    so = per_ray_sequences({**o, 'ray_index': o['ray_index']-base}, n)
+    bad_rays = {i for i in range(n) if sg[i] != so[i]}
+    bad = len(bad_rays)
+    assert bad <= max_bad_fraction*n, f'{bad} of {n} rays have different face sequences'
+    mg = ~np.isin(g['ray_index']-base, list(bad_rays))
+    mo = ~np.isin(o['ray_index']-base, list(bad_rays))
+    g = {k: v[mg] for k, v in g.items()}
+    o = {k: v[mo] for k, v in o.items()}
+  assert np.array_equal(g['group'], o['group']) and np.array_equal(g['bounce'], o['bounce'])
+  assert np.array_equal(g['is_entering'], o['is_entering'])
+  assert np.abs(g['points']-o['points']).max(initial=0) < POS_TOL
+  assert np.abs(g['directions']-o['directions']).max(initial=0) < DIR_TOL
+  assert np.abs(g['powers']-o['powers']).max(initial=0) < 1e-14
+  return bad
+
+
+@pytest.mark.parametrize('name', SCENES)
+def test_sampler_matches_oracle(name, gpu_engine, oracle, sims):
+  sim = sims(name)
+  sa = sim.source_args(0)
+  dsrc = gpu_engine.source(sa)
+  n = 100000
+  g = dsrc.sample(SEED, 5_000_000_000, n)          # counters beyond 2^32 exercise the 64-bit Philox counter
+  o = oracle.sample_mc(sa, SEED, 5_000_000_000, n)
+  assert np.abs(g['first']-o['first']).max() < 1e-15
+  assert np.abs(g['phi']-o['phi']).max() < 1e-14
+  assert np.abs(g['origins']-o['origins']).max() < 1e-12
+  assert np.abs(g['directions']-o['directions']).max() < 1e-14
+
+
+def test_sampler_phi_dependent_tables(gpu_engine, oracle):
+  'conditional rows (n_rows = n_phi-1) + nearest-row rule, incl. the collimated (r, phi) kind'
+  from freecad.optics_design_workbench_b200.distributions import build_tables
+  for expr, var, dom, kind in (('(exp(-theta**2/0.05)*(1+0.8*cos(phi)**2))*abs(sin(theta))', 'theta', (0, np.pi/3), 0),
+                               ('(exp(-r**2/4)*(2+sin(phi)))*abs(r)', 'r', (0, 6), 1)):
+    t = build_tables(expr, var, dom, (0.3, 5.1), 2001, 41)
+    m = prim.translation(1, 2, 3) @ prim.rotation((1, 1, 0), 0.4)
+    sa = _abi.SourceArgs(t, kind=kind, source_id=3, gpM=m, focal_length=0.0 if kind else 2.5)
+    g = gpu_engine.source(sa).sample(11, 0, 50000)
+    o = oracle.sample_mc(sa, 11, 0, 50000)
+    for k in ('first', 'phi', 'origins', 'directions'):
+      assert np.abs(g[k]-o[k]).max() < 1e-13, k
+
+
+@pytest.mark.parametrize('name', SCENES)
+def test_monte_carlo_hits_match_oracle(name, gpu_engine, oracle, sims):
+  'every intersection recorded: per-ray face sequence, positions, directions, powers, isEntering'
+  sim = sims(name)
+  n = 30000
+  cap = n*(int(sim.settings['MaxIntersections']) if name == 'hugeArray' else 10)
+  cfg = sim.cfg(record_all_hits=True, hit_capacity=cap)
+  sa = sim.source_args(0)
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sa)
+  with ds.trace_mc(dsrc, cfg, SEED, 1000, n) as res:
+    gc, gh = res.counts, res.hits(sort=True)
+  o = oracle.trace_mc(sim.scene, sa, cfg, SEED, 1000, n, hit_capacity=cap, threads=0)
+  bad = compare_hits(gh, o['hits'], n, max_bad_fraction=5e-4 if name == 'hugeArray' else 0.0, base=1000)
+  if bad == 0:
+    assert gc == o['counts']
+  else:
+    assert abs(gc['segments']-o['counts']['segments']) <= 100*bad
+
+
+@pytest.mark.parametrize('name', ['minimal', 'lensesAndMirrors', 'lensesAndMirrorsSequential'])
+def test_recorded_hits_only(name, gpu_engine, oracle, sims):
+  'default RecordHits flags: what the reference would store (absorber hits only)'
+  sim = sims(name)
+  n = 50000
+  cfg = sim.cfg(hit_capacity=2*n)
+  sa = sim.source_args(0)
+  with gpu_engine.scene(sim.scene).trace_mc(gpu_engine.source(sa), cfg, SEED, 0, n) as res:
+    gc, gh = res.counts, res.hits(sort=True)
+  o = oracle.trace_mc(sim.scene, sa, cfg, SEED, 0, n, hit_capacity=2*n, threads=0)
+  assert gc == o['counts']
+  compare_hits(gh, o['hits'], n)
+  assert set(gh['group']) == {len(sim.scene.groups)-1}
+
+
+def explicit_fan(n=2000, spread=0.02, seed=5):
+  rng = np.random.default_rng(seed)
+  th, ph = np.abs(rng.normal(0, spread, n)), rng.uniform(0, 2*np.pi, n)
+  d = np.stack([np.sin(th)*np.sin(ph), -np.sin(th)*np.cos(ph), np.cos(th)], axis=-1)
+  return np.zeros_like(d), d
+
+
+@pytest.mark.parametrize('name', ['minimal', 'lensesAndMirrors', 'lensesAndMirrorsSequential'])
+def test_explicit_ray_list_matches_oracle(name, gpu_engine, oracle, sims):
+  'odw_trace_rays (fans / replay / parity path): hits, per-ray segment count, final point and power'
+  sim = sims(name)
+  o_, d_ = explicit_fan(spread=0.05)          # wide enough that some rays miss the optics
+  d_ = d_*np.linspace(0.5, 2.0, len(d_))[:, None]    # directions need not be unit (traceRay normalises where needed)
+  p_ = np.linspace(0.1, 1.0, len(d_))
+  cfg = sim.cfg(record_all_hits=True, hit_capacity=20*len(d_))
+  with gpu_engine.scene(sim.scene).trace_rays(cfg, o_, d_, p_) as res:
+    gc, gh, gs = res.counts, res.hits(sort=True), res.ray_summary()
+  o = oracle.trace_rays(sim.scene, cfg, o_, d_, p_, hit_capacity=20*len(d_))
+  assert gc == o['counts']
+  compare_hits(gh, o['hits'], len(d_))
+  assert np.array_equal(gs['n_segments'], o['n_segments'])
+  assert np.abs(gs['final_points']-o['final_points']).max() < 1e-8
+  assert np.abs(gs['final_powers']-o['final_powers']).max() < 1e-14
+  assert gc['escaped'] > 0
+
+
+def procedural_scene():
+  b = SceneBuilder()
+  lens = b.add_group('Lens', 'Lens', optical_type='Lens', refractive_index=1.6)
+  b.add_shape(lens, prim.plano_convex_lens(30.0, 6.0, 0.8), prim.translation(0, 0, 20) @ prim.rotation((1, 0, 0), 0.05))
+  b.add_shape(lens, prim.cone(4.0, 2.0, 5.0), prim.translation(12, 0, 18))
+  mir = b.add_group('Mirror', 'Mirror', optical_type='Mirror', reflectivity=0.9)
+  b.add_shape(mir, prim.cylinder(3.0, 8.0), prim.translation(-12, 0, 30) @ prim.rotation((0, 1, 0), 1.2))
+  b.add_shape(mir, prim.torus(8.0, 1.5), prim.translation(0, 0, 45))
+  vac = b.add_group('Vac', 'Vac', optical_type='Vacuum', record_hits=True)
+  b.add_shape(vac, prim.box(40, 40, 2), prim.translation(-20, -20, 55))
+  gr = b.add_group('Grating', 'Grating', optical_type='Grating', grating_type='Transmission', refractive_index=1.5,
+                   grating_lines_per_mm=300, grating_order=1, grating_orientation=(0, 1, 0))
+  b.add_shape(gr, prim.box(60, 60, 1), prim.translation(-30, -30, 62))
+  ab = b.add_group('Abs', 'Abs', optical_type='Absorber', record_hits=True)
+  b.add_shape(ab, prim.disc(60.0), prim.translation(0, 0, 80))
+  b.add_shape(ab, prim.sphere(2.0), prim.translation(0, 9, 35))
+  return b.build()
+
+
+def test_procedural_scene_all_surface_and_optical_types(gpu_engine, oracle):
+  'cone, cylinder, torus, sphere cap, disc (arc loop), mirror/lens/vacuum/transmission grating/absorber, TIR'
+  sc = procedural_scene()
+  o_, d_ = explicit_fan(n=20000, spread=0.25, seed=9)
+  cfg = _abi.CfgArgs(max_ray_length=300.0, dist_tol=1e-6, max_intersections=50, record_all_hits=True, hit_capacity=60*len(d_))
+  with gpu_engine.scene(sc).trace_rays(cfg, o_, d_) as res:
+    gc, gh, gs = res.counts, res.hits(sort=True), res.ray_summary()
+  o = oracle.trace_rays(sc, cfg, o_, d_, wavelength=500.0, hit_capacity=60*len(d_), threads=0)
+  bad = compare_hits(gh, o['hits'], len(d_), max_bad_fraction=1e-3)
+  assert bad <= 20
+  kinds = {int(sc.faces[f]['kind']) for f in np.unique(gh['face_id'])}
+  assert kinds == {1, 2, 3, 4, 5}
+  assert set(np.unique(gh['group'])) == {0, 1, 2, 3, 4}
+
+
+def test_bvh_path_equals_brute_force_semantics(gpu_engine, oracle):
+  'a >64-face scene takes the BVH kernel; the oracle (exhaustive loops) is the arbiter'
+  rng = np.random.default_rng(2)
+  b = SceneBuilder()
+  groups = [b.add_group('L', 'L', optical_type='Lens', refractive_index=1.4),
+            b.add_group('M', 'M', optical_type='Mirror'),
+            b.add_group('A', 'A', optical_type='Absorber', record_hits=True)]
+  for i in range(40):
+    c = rng.uniform(-15, 15, 3) + [0, 0, 40]
+    if i % 2:
+      b.add_shape(groups[i % 3], prim.box(*rng.uniform(1, 4, 3)), prim.translation(*c) @ prim.rotation(rng.normal(size=3), rng.uniform(0, 3)))
+    else:
+      b.add_shape(groups[i % 3], prim.sphere(rng.uniform(0.5, 2.5)), prim.translation(*c))
+  sc = b.build()
+  assert len(sc.faces) > 64
+  o_, d_ = explicit_fan(n=30000, spread=0.3, seed=4)
+  cfg = _abi.CfgArgs(max_ray_length=200.0, max_intersections=30, record_all_hits=True, hit_capacity=40*len(d_))
+  with gpu_engine.scene(sc).trace_rays(cfg, o_, d_) as res:
+    gh = res.hits(sort=True)
+  o = oracle.trace_rays(sc, cfg, o_, d_, hit_capacity=40*len(d_), threads=0)
+  assert compare_hits(gh, o['hits'], len(d_), max_bad_fraction=1e-3) <= 30
+
+
+def test_edge_cases_empty_overflow_and_errors(gpu_engine, sims):
+  sim = sims('lensesAndMirrors')
+  ds = gpu_engine.scene(sim.scene)
+  dsrc = gpu_engine.source(sim.source_args(0))
+  # empty inputs
+  with ds.trace_mc(dsrc, sim.cfg(), SEED, 0, 0) as res:
+    assert res.counts['rays'] == 0 and res.counts['segments'] == 0 and len(res.hits()['powers']) == 0
+  with ds.trace_rays(sim.cfg(), np.zeros((0, 3)), np.zeros((0, 3))) as res:
+    assert res.counts['segments'] == 0
+  # hit buffer too small: complete counters, ODW_EOVERFLOW reported, stored prefix valid
+  with ds.trace_mc(dsrc, sim.cfg(hit_capacity=100), SEED, 0, 5000) as res:
+    assert res.overflow and res.counts['hits_dropped'] > 0
+    assert res.counts['hits'] == res.counts['hits_dropped']+100
+    assert len(res.hits()['powers']) == 100
+  # malformed descriptions fail loudly
+  bad = sims('minimal').scene
+  import copy
+  sc2 = copy.copy(bad)
+  sc2.faces = bad.faces.copy()
+  sc2.faces['group'][0] = 7
+  with pytest.raises(engine.EngineError):
+    gpu_engine.scene(sc2)
+  with pytest.raises(engine.EngineError):
+    engine.Engine(99)
+
+
+def test_count_only_and_histogram_modes(gpu_engine, oracle, sims):
+  'device binning == numpy.histogram2d of the stored hit list (reference jupyter_utils/histogram.py:54 semantics)'
+  sim = sims('lensesAndMirrors')
+  n = 200000
+  absorber = len(sim.scene.groups)-1
+  spec = dict(group=absorber, nu=40, nv=30, origin=(-68.86, 0, 73), uaxis=(1, 0, 0), vaxis=(0, 1, 0),
+              u_range=(-0.4, 0.4), v_range=(-0.3, 0.3))
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  with ds.trace_mc(dsrc, sim.cfg(binnings=[spec], hit_capacity=2*n), SEED, 0, n) as res:
+    hist, hits, c1 = res.histogram(0), res.hits(sort=False), res.counts
+  x, y = hits['points'][:, 0]+68.86, hits['points'][:, 1]
+  ref, _, _ = np.histogram2d(x, y, bins=(40, 30), range=((-0.4, 0.4), (-0.3, 0.3)))
+  assert hist.sum() > 0.5*n
+  assert np.abs(hist-ref).sum() <= 2            # a hit exactly on a bin edge may fall either side
+  with ds.trace_mc(dsrc, sim.cfg(binnings=[spec], store_hits=False), SEED, 0, n) as res:
+    assert np.array_equal(res.histogram(0), hist) and res.counts['hits'] == c1['hits']
+    assert res.counts['segments'] == c1['segments']
+  o = oracle.trace_mc(sim.scene, sim.source_args(0), sim.cfg(binnings=[spec], store_hits=False), SEED, 0, n, threads=0)
+  assert np.abs(o['histograms'][0]-hist).sum() <= 2
+
+
+def test_range_splitting_is_invariant(gpu_engine, sims):
+  'Philox counter = global ray index: tracing [0,n) equals tracing [0,k) and [k,n) (GPU-count invariance, SURVEY §8e)'
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n, k = 100000, 37777
+  cfg = sim.cfg(hit_capacity=2*n)
+  with ds.trace_mc(dsrc, cfg, SEED, 0, n) as res:
+    whole, cw = res.hits(sort=True), res.counts
+  parts, segs = [], 0
+  for first, cnt in ((0, k), (k, n-k)):
+    with ds.trace_mc(dsrc, cfg, SEED, first, cnt) as res:
+      parts.append(res.hits(sort=True)); segs += res.counts['segments']
+  assert segs == cw['segments']
+  for key in whole:
+    assert np.array_equal(np.concatenate([p[key] for p in parts]), whole[key]), key
+
+
+def test_full_size_properties(gpu_engine, sims):
+  '''
+  BASELINE.json configs[1] size (1e8 rays, lensesAndMirrors): size-independent properties instead of an
+  oracle run — counter identities, every stored hit lies on the absorber's entry faces, power 1, unique rays.
+  '''
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n = int(os.environ.get('ODW_FULL_RAYS', '100000000'))
+  cfg = sim.cfg(hit_capacity=n+1024)
+  with ds.trace_mc(dsrc, cfg, SEED, 0, n) as res:
+    c = res.counts
+    assert c['hits_dropped'] == 0 and c['rays'] == n and c['depth_terminated'] == 0
+    # each ray: 7 segments when it reaches the absorber, fewer (ending with an escape segment) otherwise
+    assert c['hits']+c['escaped'] == n
+    assert 6.99*n < c['segments'] <= 7*n
+    arrays = _abi.HitArrays(c['hits'])
+    h = res.hits(sort=False, into=arrays)
+  assert len(h['powers']) == c['hits']
+  assert np.all(h['powers'] == 1.0) and np.all(h['is_entering'] == 1) and np.all(h['group'] == 3)
+  z = h['points'][:, 2]
+  on_box = np.abs(z-73.0) < 1e-9
+  assert on_box.mean() > 0.999                        # the rest end on the torus
+  assert np.unique(h['ray_index']).size == c['hits']  # one recorded hit per ray at most
+  # beam centre and symmetric spread on the detector (on-axis answer of SURVEY.md Appendix B)
+  assert abs(h['points'][on_box, 0].mean()+68.857864) < 1e-3 and abs(h['points'][on_box, 1].mean()) < 1e-3
