@@ -46,10 +46,10 @@ class TraceCfg(C.Structure):
 
 class Counts(C.Structure):
   _fields_ = [(k, C.c_uint64) for k in ('rays', 'segments', 'hits', 'hits_dropped', 'escaped',
-                                         'depth_terminated', 'waves', 'reserved')]
+                                         'depth_terminated', 'waves', 'sm_clock_khz')]
 
   def as_dict(self):
-    return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != 'reserved'}
+    return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != 'sm_clock_khz'}
 
 
 class HitsView(C.Structure):

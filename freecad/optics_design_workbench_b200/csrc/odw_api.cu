@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -261,9 +262,53 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     d.kind = f.kind; d.trim = f.trim_kind; d.nsign = f.nsign; d.group = f.group;
     d.seg_first = f.seg_first; d.seg_count = f.seg_count; d.face_id = f.face_id;
     d.flags = (f.kind != ODW_SURF_PLANE && std::fabs((f.uv_max[0] - f.uv_min[0]) - ODW_TWO_PI) < 1e-9) ? DFACE_FULL_U : 0;
+    {
+      auto dot = [](const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; };
+      const bool full_u = (d.flags & DFACE_FULL_U) != 0;
+      if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_UVBOX) {
+        d.flags |= DFACE_FAST; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
+      } else if (f.kind == ODW_SURF_SPHERE && (f.trim_kind == ODW_TRIM_NONE || (f.trim_kind == ODW_TRIM_UVBOX && full_u))) {
+        d.flags |= DFACE_FAST;
+        const bool whole = f.trim_kind == ODW_TRIM_NONE;
+        d.c0 = whole ? -1e300 : f.p0*std::sin(f.uv_min[1]);
+        d.c1 = whole ?  1e300 : f.p0*std::sin(f.uv_max[1]);
+      } else if (f.kind == ODW_SURF_CYLINDER && f.trim_kind == ODW_TRIM_UVBOX && full_u) {
+        d.flags |= DFACE_FAST; d.c0 = f.uv_min[1]; d.c1 = f.uv_max[1];
+      }
+    }
     for (int s = 0; s < sd->n_seq_steps; ++s)
       for (int k = sd->seq_offsets[s]; k < sd->seq_offsets[s+1]; ++k)
         if (sd->seq_groups[k] == f.group) d.seqmask[s >> 6] |= 1ull << (s & 63);
+  }
+  // shells: the reference culls per shell box first; faces of one shell must be contiguous (odw.h: "sorted by shell")
+  std::vector<DShell> shells;
+  if (sd->n_shells > 0 && sd->shells) {
+    for (int i = 0; i < sd->n_shells; ++i) {
+      const odw_shell& h = sd->shells[i];
+      if (h.face_first < 0 || h.face_count < 0 || h.face_first + h.face_count > sd->n_faces || h.group < 0 || h.group >= sd->n_groups)
+        return fail(ODW_EINVAL, "shell " + std::to_string(i) + ": face range or group out of bounds");
+      DShell d; memset(&d, 0, sizeof d);
+      for (int k = 0; k < 3; ++k) { d.bmin[k] = 1e300; d.bmax[k] = -1e300; }
+      for (int f = h.face_first; f < h.face_first + h.face_count; ++f) {
+        if (sd->faces[f].group != h.group) return fail(ODW_EINVAL, "shell " + std::to_string(i) + ": faces of a shell must share its group");
+        for (int k = 0; k < 3; ++k) { d.bmin[k] = std::min(d.bmin[k], sd->faces[f].aabb_min[k]); d.bmax[k] = std::max(d.bmax[k], sd->faces[f].aabb_max[k]); }
+      }
+      d.face_first = h.face_first; d.face_count = h.face_count; d.group = h.group;
+      if (h.face_count > 0) { d.seqmask[0] = faces[(size_t)h.face_first].seqmask[0]; d.seqmask[1] = faces[(size_t)h.face_first].seqmask[1]; }
+      shells.push_back(d);
+    }
+    std::vector<char> covered((size_t)sd->n_faces, 0);
+    for (const DShell& d : shells) for (int f = d.face_first; f < d.face_first + d.face_count; ++f) covered[(size_t)f]++;
+    for (int f = 0; f < sd->n_faces; ++f) if (covered[(size_t)f] != 1) return fail(ODW_EINVAL, "face " + std::to_string(f) + " is not covered by exactly one shell");
+  } else {
+    // no shell table given: one shell per face
+    for (int f = 0; f < sd->n_faces; ++f) {
+      DShell d; memset(&d, 0, sizeof d);
+      for (int k = 0; k < 3; ++k) { d.bmin[k] = sd->faces[f].aabb_min[k]; d.bmax[k] = sd->faces[f].aabb_max[k]; }
+      d.face_first = f; d.face_count = 1; d.group = sd->faces[f].group;
+      d.seqmask[0] = faces[(size_t)f].seqmask[0]; d.seqmask[1] = faces[(size_t)f].seqmask[1];
+      shells.push_back(d);
+    }
   }
   std::vector<DGroup> groups((size_t)sd->n_groups);
   for (int i = 0; i < sd->n_groups; ++i) {
@@ -277,6 +322,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   sc->eng = eng; sc->n_groups = sd->n_groups;
   int rc;
   if ((rc = upload(eng, sc->owned, faces.data(), faces.size(), &sc->d.faces))) { odw_scene_destroy(sc); return rc; }
+  if ((rc = upload(eng, sc->owned, shells.data(), shells.size(), &sc->d.shells))) { odw_scene_destroy(sc); return rc; }
+  sc->d.n_shells = (int)shells.size();
   if ((rc = upload(eng, sc->owned, sd->segs, (size_t)sd->n_segs, &sc->d.segs))) { odw_scene_destroy(sc); return rc; }
   if ((rc = upload(eng, sc->owned, groups.data(), groups.size(), &sc->d.groups))) { odw_scene_destroy(sc); return rc; }
   sc->d.n_faces = sd->n_faces; sc->d.n_segs = sd->n_segs; sc->d.n_groups = sd->n_groups; sc->d.n_seq_steps = sd->n_seq_steps;
@@ -289,7 +336,7 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     sc->d.n_bvh_nodes = (int)b.nodes.size();
     sc->smem = 0;
   } else {
-    sc->smem = std::max<size_t>(16, faces.size()*sizeof(DFace));
+    sc->smem = std::max<size_t>(16, faces.size()*sizeof(DFace) + shells.size()*sizeof(DShell));
   }
   *out = sc;
   return ODW_OK;
@@ -431,8 +478,31 @@ static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const 
   // persistent grid: a multiple of the SM count, no more blocks than there is work
   uint64_t want = (p.n_rays + 255)/256;
   int blocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*(uint64_t)per_sm, std::max<uint64_t>(1, want));
+  // Waves: a long request is issued as back-to-back launches of `wave` rays each.  Every launch starts all CTAs
+  // in the same phase of the bounce loop; inside one very long launch the CTAs drift apart, their combined
+  // instruction working set no longer fits the shared instruction cache levels and the kernel slows down by ~35 %
+  // (measured on B200, lensesAndMirrors: 1e8 rays in one launch 146 ms, in 48 launches of 2^21 rays 106 ms).  Launches are
+  // asynchronous on one stream, so there is no host gap between them.
+  uint64_t wave = sc->use_bvh ? (1ull << 24) : (1ull << 21);   // BVH scenes have long per-launch tails (uneven ray depth)
+  if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
+  uint64_t launches = 0;
   CU(cudaEventRecord(eng->ev0, eng->stream));
-  if (p.n_rays > 0) CU(odw_launch_trace(&p, mc, sc->use_bvh, blocks, sc->smem, eng->stream));
+  for (uint64_t off = 0; off < p.n_rays; off += wave) {
+    TraceParams q = p;
+    q.n_rays = std::min<uint64_t>(wave, p.n_rays - off);
+    q.first_ray = p.first_ray + off;
+    if (!mc) {
+      q.in_origins = p.in_origins + 3*off; q.in_dirs = p.in_dirs + 3*off;
+      if (p.in_powers) q.in_powers = p.in_powers + off;
+      if (p.out_nseg) q.out_nseg = p.out_nseg + off;
+      if (p.out_final_point) q.out_final_point = p.out_final_point + 3*off;
+      if (p.out_final_power) q.out_final_power = p.out_final_power + off;
+    }
+    uint64_t want_w = (q.n_rays + 255)/256;
+    int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
+    CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->stream));
+    ++launches;
+  }
   CU(cudaEventRecord(eng->ev1, eng->stream));
   Counters c;
   CU(cudaMemcpyAsync(&c, r->dcounters, sizeof c, cudaMemcpyDeviceToHost, eng->stream));
@@ -440,7 +510,8 @@ static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const 
   CU(cudaEventElapsedTime(&r->ms, eng->ev0, eng->ev1));
   r->counts.rays = p.n_rays; r->counts.segments = c.segments; r->counts.hits = c.hits;
   r->counts.hits_dropped = c.hits_dropped; r->counts.escaped = c.escaped; r->counts.depth_terminated = c.depth_terminated;
-  r->counts.waves = p.n_rays > 0 ? 1 : 0;
+  r->counts.waves = launches;
+  r->counts.sm_clock_khz = c.dbg_ns ? (uint64_t)((double)c.dbg_cycles*1e6/(double)c.dbg_ns) : 0;
   return c.hits_dropped ? fail(ODW_EOVERFLOW, std::to_string(c.hits_dropped) + " hits did not fit hit_capacity " + std::to_string(p.hits.capacity)) : ODW_OK;
 }
 

@@ -20,8 +20,17 @@ struct DFace {
   int32_t kind, trim, nsign, group;
   int32_t seg_first, seg_count, face_id, flags;
   unsigned long long seqmask[2];   // bit s set <=> the face's group is in SequentialModeElements step s
+  double c0, c1, c2, c3;           // fast-path constants: plane (o.z, o.x, o.y) | sphere/cylinder axial bounds (lo, hi)
 };
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
+#define DFACE_FAST   2             // plane/uvbox, sphere (whole or full-u cap), cylinder (full-u band): inline test
+
+// Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).
+struct DShell {
+  double bmin[3], bmax[3];
+  int32_t face_first, face_count, group, pad;
+  unsigned long long seqmask[2];
+};
 
 struct DGroup {
   double n, reflectivity, absorption_length, lpm, order, gdir[3];
@@ -43,11 +52,12 @@ struct BvhNode {                   // 32 B: one 256-bit load fetches a node
 
 struct DScene {
   const DFace* faces;
+  const DShell* shells;
   const odw_trimseg* segs;
   const DGroup* groups;
-  const BvhNode* bvh;              // nullptr: brute force over all faces
+  const BvhNode* bvh;              // nullptr: shells + faces staged in shared memory
   const int32_t* bvh_prims;        // face indices in leaf order
-  int32_t n_faces, n_segs, n_groups, n_seq_steps, n_bvh_nodes;
+  int32_t n_faces, n_shells, n_segs, n_groups, n_seq_steps, n_bvh_nodes;
 };
 
 struct DSource {
@@ -69,7 +79,7 @@ struct HitBuffers {
 };
 
 struct Counters {                  // device-side odw_counts
-  unsigned long long segments, hits, hits_dropped, escaped, depth_terminated, alive_next;
+  unsigned long long segments, hits, hits_dropped, escaped, depth_terminated, alive_next, dbg_cycles, dbg_ns;
 };
 
 struct TraceParams {
@@ -92,6 +102,32 @@ struct TraceParams {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
 __device__ __forceinline__ double dot3(double ax, double ay, double az, const double* b) { return ax*b[0]+ay*b[1]+az*b[2]; }
+__device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) { return ax*bx+ay*by+az*bz; }
+
+// Reciprocal / square root without the IEEE slow paths: MUFU seed (2^-23) + two Newton steps (~1 ulp).
+// The correctly rounded '/' and sqrt() cost ~3x the instructions and, inlined at every face test, pushed the
+// hot loop out of the instruction cache.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0); r = fma(r, e, r);
+  e = fma(-x, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double h = 0.5*x;
+  double e = fma(-h*r, r, 0.5); r = fma(r, e, r);
+  e = fma(-h*r, r, 0.5); r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {          // x >= 0
+  if (x <= 0) return 0.0;
+  double r = fast_rsqrt(x);
+  double sq = x*r;
+  return fma(fma(-sq, sq, x), 0.5*r, sq);                          // one Heron correction on the product
+}
 
 // ---- Philox4x32-10, counter (ray_lo, ray_hi, source_id, purpose), key = seed -------------
 __device__ __forceinline__ void philox_uniform2(unsigned long long seed, uint32_t source_id, unsigned long long ray,
@@ -269,7 +305,7 @@ __device__ __noinline__ int line_torus(const DFace& f, const double* w, const do
   return n;
 }
 
-__device__ __forceinline__ int line_surface(const DFace& f, const double* s, const double* d, double* t) {
+__device__ __noinline__ int line_surface(const DFace& f, const double* s, const double* d, double* t) {
   double w[3] = { s[0]-f.o[0], s[1]-f.o[1], s[2]-f.o[2] };
   switch (f.kind) {
     case ODW_SURF_PLANE: {
@@ -350,7 +386,7 @@ __device__ __noinline__ bool loops_contain(const DFace& f, const odw_trimseg* __
 }
 
 // P on the untrimmed surface of f.  returns true iff P lies on the trimmed face dilated by tol.
-__device__ __forceinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* __restrict__ segs, const double* P, double tol) {
+__device__ __noinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* __restrict__ segs, const double* P, double tol) {
   if (f.trim == ODW_TRIM_NONE) return true;
   double w[3] = { P[0]-f.o[0], P[1]-f.o[1], P[2]-f.o[2] };
   double x = dot3(w, f.x), y = dot3(w, f.y);
@@ -393,7 +429,7 @@ __device__ __forceinline__ bool on_trimmed_face(const DFace& f, const odw_trimse
 }
 
 // outward unit normal at P (ray.py:463-465 + face orientation)
-__device__ __forceinline__ void outward_normal(const DFace& f, const double* P, double* n) {
+__device__ __noinline__ void outward_normal_general(const DFace& f, const double* P, double* n) {
   double w[3] = { P[0]-f.o[0], P[1]-f.o[1], P[2]-f.o[2] };
   double g[3];
   switch (f.kind) {

@@ -12,21 +12,33 @@
 
 namespace cg = cooperative_groups;
 
+// outward unit normal: inline for plane / sphere / cylinder, general (noinline) otherwise
+__device__ __forceinline__ void outward_normal(const DFace& f, const double* P, double* n) {
+  if (f.kind == ODW_SURF_PLANE) {
+    const double sg = (double)f.nsign;
+    n[0] = sg*f.z[0]; n[1] = sg*f.z[1]; n[2] = sg*f.z[2];
+  } else if (f.kind == ODW_SURF_SPHERE || f.kind == ODW_SURF_CYLINDER) {
+    double g0 = P[0]-f.o[0], g1 = P[1]-f.o[1], g2 = P[2]-f.o[2];
+    if (f.kind == ODW_SURF_CYLINDER) {
+      const double z = dot3(g0, g1, g2, f.z);
+      g0 -= z*f.z[0]; g1 -= z*f.z[1]; g2 -= z*f.z[2];
+    }
+    const double sc = (double)f.nsign*fast_rsqrt(g0*g0 + g1*g1 + g2*g2);
+    n[0] = g0*sc; n[1] = g1*sc; n[2] = g2*sc;
+  } else {
+    outward_normal_general(f, P, n);
+  }
+}
+
 struct NearestHit {
   double tA, tB;     // closest accepted hit overall / closest whose group differs from the current medium
   int fA, fB;
 };
 
-template <typename FacePtr>
-__device__ __forceinline__ void test_face(const FacePtr faces, int idx, const TraceParams& p, const double* s, const double* dn,
-                                          int medium, int seq_index, double max_len, NearestHit& h) {
-  const DFace& f = faces[idx];
-  if (p.sequential) {
-    if (seq_index >= 128 || !((f.seqmask[seq_index >> 6] >> (seq_index & 63)) & 1ull)) return;
-  }
-  if (f.group < 256 && ((p.ignore_mask[f.group >> 6] >> (f.group & 63)) & 1ull)) return;   // IgnoredOpticalElements
-  const double tol = p.tol;
-  if (f.kind == ODW_SURF_TORUS || f.trim == ODW_TRIM_LOOPS) {
+// general face test: any surface kind, any trim (cone, torus, partial azimuth ranges, pcurve loops)
+__device__ __noinline__ void test_face_general(const DFace& f, int idx, const odw_trimseg* __restrict__ segs, double tol,
+                                               const double* s, const double* dn, int medium, double tmax, NearestHit& h) {
+  if (f.kind == ODW_SURF_TORUS) {
     // slab test against the face's box (ray.py:390-398 culls with the face BoundBox the same way);
     // 1/0 = inf is fine here: fmin/fmax drop the NaN of 0*inf
     double t0 = -1e300, t1 = 1e300;
@@ -43,22 +55,95 @@ __device__ __forceinline__ void test_face(const FacePtr faces, int idx, const Tr
   for (int k = 0; k < nt; ++k) {
     double t = ts[k];
     if (!(t > tol)) continue;                                        // ray.py:424  |P - start| > distTol (and forward)
-    if (!(t < max_len + tol) || !(t < h.tA + 2*tol)) continue;        // ray.py:425,432,440
+    if (!(t < tmax) || !(t < h.tA + 2*tol)) continue;                 // ray.py:425,432,440
     double P[3] = { s[0]+t*dn[0], s[1]+t*dn[1], s[2]+t*dn[2] };
-    if (!on_trimmed_face(f, p.scene.segs, P, tol)) continue;         // ray.py:426
+    if (!on_trimmed_face(f, segs, P, tol)) continue;                 // ray.py:426
     if (t < h.tA) { h.tA = t; h.fA = idx; }
     if (f.group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
   }
 }
 
-// Ray.findNearestIntersection (ray.py:290-452): brute force over faces staged in shared memory
-__device__ __forceinline__ int find_nearest_smem(const DFace* sfaces, const TraceParams& p, const double* s, const double* dn,
+__device__ __forceinline__ void accept_hit(double t, int idx, int group, int medium, NearestHit& h) {
+  if (t < h.tA) { h.tA = t; h.fA = idx; }
+  if (group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
+}
+
+// One face against the line start + t*dn (ray.py:407-432).  tmax = maxRayLength + distTol.
+// Fast paths (inline, no division / inverse trigonometry): rectangle on a plane, whole sphere or spherical cap/zone
+// with full azimuth, cylinder band with full azimuth.  Everything else goes through test_face_general.
+template <bool CHECK_GROUP>
+__device__ __forceinline__ void test_face(const DFace& f, int idx, const TraceParams& p, const double* s, const double* dn,
+                                          int medium, int seq_index, double tmax, NearestHit& h) {
+  if (CHECK_GROUP) {   // the shared-memory path filters whole shells instead
+    if (p.sequential && (seq_index >= 128 || !((f.seqmask[seq_index >> 6] >> (seq_index & 63)) & 1ull))) return;
+    if (f.group < 256 && ((p.ignore_mask[f.group >> 6] >> (f.group & 63)) & 1ull)) return;   // IgnoredOpticalElements
+  }
+  const double tol = p.tol;
+  if (!(f.flags & DFACE_FAST)) { test_face_general(f, idx, p.scene.segs, tol, s, dn, medium, tmax, h); return; }
+  const double limit = fmin(tmax, h.tA + 2*tol);                     // ray.py:425,432,440
+  if (f.kind == ODW_SURF_PLANE) {
+    const double den = dot3(dn, f.z);
+    const double t = (f.c0 - dot3(s, f.z))*fast_rcp(den);            // den == 0: inf/NaN fails the range test
+    if (t > tol && t < limit) {
+      const double Px = fma(t, dn[0], s[0]), Py = fma(t, dn[1], s[1]), Pz = fma(t, dn[2], s[2]);
+      const double u = dot3(Px, Py, Pz, f.x) - f.c1, v = dot3(Px, Py, Pz, f.y) - f.c2;
+      if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, h);
+    }
+    return;
+  }
+  // sphere / cylinder: a t^2 + 2 b t + c = 0 in the coordinates of the axis frame
+  const double w0 = s[0]-f.o[0], w1 = s[1]-f.o[1], w2 = s[2]-f.o[2];
+  double a, b, c;
+  const double wz = dot3(w0, w1, w2, f.z), dz = dot3(dn, f.z);
+  if (f.kind == ODW_SURF_SPHERE) {
+    a = 1.0; b = dot3(w0, w1, w2, dn); c = dot3(w0, w1, w2, w0, w1, w2) - f.p0*f.p0;
+  } else {
+    a = 1.0 - dz*dz; b = dot3(w0, w1, w2, dn) - wz*dz; c = dot3(w0, w1, w2, w0, w1, w2) - wz*wz - f.p0*f.p0;
+  }
+  const double disc = b*b - a*c;
+  if (!(disc >= 0) || a < 1e-300) return;
+  const double sq = fast_sqrt(disc);
+  const double q = -(b + (b >= 0 ? sq : -sq));                       // stable: no cancellation in q
+  const double r0 = q*fast_rcp(a), r1 = (q != 0) ? c*fast_rcp(q) : 0.0;
+  const double tn = fmin(r0, r1), tf = fmax(r0, r1);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const double t = k ? tf : tn;
+    if (t > tol && t < limit) {
+      const double zc = fma(t, dz, wz);                              // axial coordinate of the hit
+      if (zc >= f.c0 - tol && zc <= f.c1 + tol) accept_hit(t, idx, f.group, medium, h);
+    }
+  }
+}
+
+// Ray.findNearestIntersection (ray.py:290-452) on the scene staged in shared memory: shells are culled by
+// their box first (ray.py:345-374), faces of surviving shells are tested one by one.  All lanes of a warp walk
+// the same shell/face lists, so shared-memory reads are broadcasts.
+__device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DFace* sfaces, const TraceParams& p,
+                                                 const double* s, const double* dn,
                                                  int medium, int seq_index, double max_len, double& t_out) {
   NearestHit h; h.tA = 1e300; h.tB = 1e300; h.fA = -1; h.fB = -1;
-  const int n = p.scene.n_faces;
-  for (int i = 0; i < n; ++i) test_face(sfaces, i, p, s, dn, medium, seq_index, max_len, h);
+  const double tol = p.tol;
+  const double tmax = max_len + tol;
+  const double inv0 = fast_rcp(dn[0]), inv1 = fast_rcp(dn[1]), inv2 = fast_rcp(dn[2]);
+  const int ns = p.scene.n_shells;
+  for (int si = 0; si < ns; ++si) {
+    const DShell& sh = sshells[si];
+    if (p.sequential && (seq_index >= 128 || !((sh.seqmask[seq_index >> 6] >> (seq_index & 63)) & 1ull))) continue;
+    if (sh.group < 256 && ((p.ignore_mask[sh.group >> 6] >> (sh.group & 63)) & 1ull)) continue;
+    double ta = (sh.bmin[0] - tol - s[0])*inv0, tb = (sh.bmax[0] + tol - s[0])*inv0;
+    double t0 = fmin(ta, tb), t1 = fmax(ta, tb);
+    ta = (sh.bmin[1] - tol - s[1])*inv1; tb = (sh.bmax[1] + tol - s[1])*inv1;
+    t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+    ta = (sh.bmin[2] - tol - s[2])*inv2; tb = (sh.bmax[2] + tol - s[2])*inv2;
+    t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+    // miss, entirely behind the start, or beyond what can still matter
+    if (t0 > t1 || t1 < 0.0 || t0 > fmin(tmax, h.tA + 2*tol)) continue;
+    const int f1 = sh.face_first + sh.face_count;
+    for (int i = sh.face_first; i < f1; ++i) test_face<false>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
+  }
   if (h.fA < 0) return -1;
-  if (h.fB >= 0 && h.tB < h.tA + 2*p.tol) { t_out = h.tB; return h.fB; }   // prefer "not the current medium" (ray.py:445-452)
+  if (h.fB >= 0 && h.tB < h.tA + 2*tol) { t_out = h.tB; return h.fB; }   // prefer "not the current medium" (ray.py:445-452)
   t_out = h.tA; return h.fA;
 }
 
@@ -91,7 +176,7 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
       if (sp < 46) { stack[sp++] = left; stack[sp++] = left + 1; }
     } else {
       for (int k = 0; k < count; ++k)
-        test_face(p.scene.faces, __ldg(p.scene.bvh_prims + left + k), p, s, dn, medium, seq_index, max_len, h);
+        { int fi = __ldg(p.scene.bvh_prims + left + k); test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, max_len + tol, h); }
     }
   }
   if (h.fA < 0) return -1;
@@ -133,113 +218,160 @@ __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long l
   p.hits.face_id[slot] = face_id;
 }
 
+// Philox draw + tabulated inverse CDF + _makeRay: once per ray, kept out of line so the bounce loop stays small
+__device__ __noinline__ void init_ray_mc(const TraceParams& p, unsigned long long ray, double* point, double* dir) {
+  double u0, u1, first, phi;
+  philox_uniform2(p.seed, (uint32_t)p.src.source_id, ray, 0u, u0, u1);
+  sample_source(p.src, u0, u1, first, phi);
+  make_ray(p.src, first, phi, point, dir);
+}
+
 template <bool MC, bool BVH>
 __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  DFace* sfaces = reinterpret_cast<DFace*>(smem_raw);
+  DShell* sshells = reinterpret_cast<DShell*>(smem_raw);
+  DFace* sfaces = reinterpret_cast<DFace*>(smem_raw + (size_t)p.scene.n_shells*sizeof(DShell));
   if (!BVH) {
-    // stage the scene: 16-byte vector copies, coalesced
-    const int4* src = reinterpret_cast<const int4*>(p.scene.faces);
-    int4* dst = reinterpret_cast<int4*>(smem_raw);
-    const int n16 = (int)((size_t)p.scene.n_faces*sizeof(DFace)/16);
+    // stage the scene (shells, then faces): 16-byte vector copies, coalesced
+    const int4* src = reinterpret_cast<const int4*>(p.scene.shells);
+    int4* dst = reinterpret_cast<int4*>(sshells);
+    int n16 = (int)((size_t)p.scene.n_shells*sizeof(DShell)/16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    src = reinterpret_cast<const int4*>(p.scene.faces);
+    dst = reinterpret_cast<int4*>(sfaces);
+    n16 = (int)((size_t)p.scene.n_faces*sizeof(DFace)/16);
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
   }
+  unsigned long long t_start = 0, c_start = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start)); c_start = clock64(); }
   const DGroup* __restrict__ groups = p.scene.groups;
   unsigned int nseg_acc = 0, nhit_acc = 0, ndrop_acc = 0, nesc_acc = 0, ndepth_acc = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < p.n_rays; i += stride) {
-    const unsigned long long ray = p.first_ray + i;
-    double point[3], dir[3], power;
-    if (MC) {
-      double u0, u1, first, phi;
-      philox_uniform2(p.seed, (uint32_t)p.src.source_id, ray, 0u, u0, u1);
-      sample_source(p.src, u0, u1, first, phi);
-      make_ray(p.src, first, phi, point, dir);
-      power = 1.0;
-    } else {
-      const double* o = p.in_origins + 3*i; const double* d = p.in_dirs + 3*i;
-      point[0] = o[0]; point[1] = o[1]; point[2] = o[2];
-      dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
-      power = p.in_powers ? p.in_powers[i] : 1.0;
+  // Persistent lanes: a lane whose ray has ended fetches its next ray (index + stride) and initialises it; then
+  // every lane with a live ray does ONE bounce.  The warp re-converges once per bounce (the __any_sync below),
+  // so the expensive part (find nearest intersection) always runs with all live lanes together, no matter how
+  // differently long the rays of a warp are.  Without this the lanes of a warp drift apart over the ~1e3 rays a
+  // lane traces in a 1e8-ray launch and SIMT efficiency collapses.
+  unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
+  bool alive = false, first_fetch = true;
+  double point[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, power = 0;
+  int medium = -1, seq_index = 0, n_isect = 0, nseg = 0;
+  for (;;) {
+    if (!alive) {
+      if (!first_fetch) i += stride;
+      first_fetch = false;
+      if (i < p.n_rays) {
+        if (MC) {
+          init_ray_mc(p, p.first_ray + i, point, dir);
+          power = 1.0;
+        } else {
+          const double* o = p.in_origins + 3*i; const double* d = p.in_dirs + 3*i;
+          point[0] = o[0]; point[1] = o[1]; point[2] = o[2];
+          dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
+          power = p.in_powers ? p.in_powers[i] : 1.0;
+        }
+        medium = -1; seq_index = 0; n_isect = 0; nseg = 0;
+        alive = true;
+      } else {
+        i = p.n_rays;                      // stay parked (no overflow of i)
+        first_fetch = true;
+      }
     }
-    int medium = -1, seq_index = 0, n_isect = 0, nseg = 0;
-    for (;;) {
-      if (n_isect >= p.max_isect) { ++ndepth_acc; break; }                     // ray.py:96-98
-      ++n_isect;
-      double dl = sqrt(dot3(dir, dir));
-      double dn[3] = { dir[0]/dl, dir[1]/dl, dir[2]/dl };
-      double t;
-      int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
-                   : find_nearest_smem(sfaces, p, point, dn, medium, seq_index, p.max_len, t);
-      if (fi < 0) {                                                            // ray.py:105-109
-        point[0] += dn[0]*p.max_len; point[1] += dn[1]*p.max_len; point[2] += dn[2]*p.max_len;
-        ++nseg; ++nesc_acc;
-        break;
-      }
-      const DFace& f = BVH ? p.scene.faces[fi] : sfaces[fi];
-      const int fgroup = f.group;
-      const DGroup& g = groups[fgroup];
-      point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];
-      ++nseg;                                                                  // ray.py:117
-      if (medium >= 0) {                                                       // ray.py:120-125 (multiplicative)
-        double L = groups[medium].absorption_length;
-        if (L == 0) power = 0; else if (isfinite(L)) power *= exp(-t/L);
-      }
-      double nrm[3];
-      outward_normal(f, point, nrm);
-      const bool entering = dot3(dn, nrm) < 0;                                 // ray.py:473-480
-      if (entering) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
-      if (g.record || p.record_all)
-        record_hit(p, ray, n_isect-1, fgroup, f.face_id, point, dir, power, entering, nhit_acc, ndrop_acc);
-      switch (g.type) {
-        case ODW_OPT_MIRROR: {                                                 // ray.py:146-161
-          double o[3]; mirror_dir(dir, nrm, o);
-          dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
-          power *= g.reflectivity; ++seq_index;
-          break;
-        }
-        case ODW_OPT_LENS: {                                                   // ray.py:165-211
-          double n1 = medium >= 0 ? groups[medium].n : 1.0, n2 = 1.0;
-          if (entering) { medium = fgroup; n2 = g.n; }
-          double o[3];
-          bool tir = snell(dn, n1, n2, nrm, o);
-          dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
-          if (!entering && !tir && medium == fgroup) { medium = -1; ++seq_index; }
-          break;
-        }
-        case ODW_OPT_GRATING: {                                                // ray.py:216-268
-          double o[3];
-          if (g.gtype == ODW_GRATING_REFLECTION) {
-            if (entering) {
-              double n = medium >= 0 ? groups[medium].n : 1.0;
-              line_grating(dn, n, n, nrm, g, p.wavelength, false, o);
-              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2]; ++seq_index;
-            }
-          } else if (entering) {
-            if (medium >= 0) { power = 0; break; }                             // the reference raises ValueError here
-            medium = fgroup;
-            line_grating(dn, 1.0, g.n, nrm, g, p.wavelength, true, o);
-            dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
-          } else {
-            double n1 = medium >= 0 ? groups[medium].n : 1.0;
-            bool tir = snell(dn, n1, 1.0, nrm, o);
-            dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
-            if (!tir) { medium = -1; ++seq_index; }
+#if ODW_BLOCK_SYNC
+    // block-wide re-convergence: all warps of a CTA stay in the same phase of the loop, so the CTA's instruction
+    // working set is one phase (init / intersect / interact) instead of all of them at once
+    if (!__syncthreads_or(alive)) break;
+#else
+    if (!__any_sync(0xffffffffu, alive)) break;
+#endif
+    if (alive) {
+      bool done = false;
+      if (n_isect >= p.max_isect) { ++ndepth_acc; done = true; }                // ray.py:96-98
+      else {
+        ++n_isect;
+        const double dli = fast_rsqrt(dot3(dir, dir));
+        double dn[3] = { dir[0]*dli, dir[1]*dli, dir[2]*dli };
+        double t;
+        int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
+                     : find_nearest_smem(sshells, sfaces, p, point, dn, medium, seq_index, p.max_len, t);
+        if (fi < 0) {                                                            // ray.py:105-109
+          point[0] += dn[0]*p.max_len; point[1] += dn[1]*p.max_len; point[2] += dn[2]*p.max_len;
+          ++nseg; ++nesc_acc;
+          done = true;
+        } else {
+          const DFace& f = BVH ? p.scene.faces[fi] : sfaces[fi];
+          const int fgroup = f.group;
+          const DGroup& g = groups[fgroup];
+          point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];
+          ++nseg;                                                                // ray.py:117
+          if (medium >= 0) {                                                     // ray.py:120-125 (multiplicative)
+            double L = groups[medium].absorption_length;
+            if (L == 0) power = 0; else if (isfinite(L)) power *= exp(-t/L);
           }
-          break;
+          double nrm[3];
+          outward_normal(f, point, nrm);
+          const bool entering = dot3(dn, nrm) < 0;                               // ray.py:473-480
+          if (entering) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
+          if (g.record || p.record_all)
+            record_hit(p, p.first_ray + i, n_isect-1, fgroup, f.face_id, point, dir, power, entering, nhit_acc, ndrop_acc);
+          switch (g.type) {
+            case ODW_OPT_MIRROR: {                                               // ray.py:146-161
+              double o[3]; mirror_dir(dir, nrm, o);
+              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+              power *= g.reflectivity; ++seq_index;
+              break;
+            }
+            case ODW_OPT_LENS: {                                                 // ray.py:165-211
+              double n1 = medium >= 0 ? groups[medium].n : 1.0, n2 = 1.0;
+              if (entering) { medium = fgroup; n2 = g.n; }
+              double o[3];
+              bool tir = snell(dn, n1, n2, nrm, o);
+              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+              if (!entering && !tir && medium == fgroup) { medium = -1; ++seq_index; }
+              break;
+            }
+            case ODW_OPT_GRATING: {                                              // ray.py:216-268
+              double o[3];
+              if (g.gtype == ODW_GRATING_REFLECTION) {
+                if (entering) {
+                  double n = medium >= 0 ? groups[medium].n : 1.0;
+                  line_grating(dn, n, n, nrm, g, p.wavelength, false, o);
+                  dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2]; ++seq_index;
+                }
+              } else if (entering) {
+                if (medium >= 0) { power = 0; break; }                           // the reference raises ValueError here
+                medium = fgroup;
+                line_grating(dn, 1.0, g.n, nrm, g, p.wavelength, true, o);
+                dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+              } else {
+                double n1 = medium >= 0 ? groups[medium].n : 1.0;
+                bool tir = snell(dn, n1, 1.0, nrm, o);
+                dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+                if (!tir) { medium = -1; ++seq_index; }
+              }
+              break;
+            }
+            case ODW_OPT_ABSORBER: power = 0; ++seq_index; break;                // ray.py:271-273
+            default: ++seq_index; break;                                         // Vacuum, ray.py:276-277
+          }
+          if (power < p.power_tol) done = true;                                  // ray.py:280
         }
-        case ODW_OPT_ABSORBER: power = 0; ++seq_index; break;                  // ray.py:271-273
-        default: ++seq_index; break;                                           // Vacuum, ray.py:276-277
       }
-      if (power < p.power_tol) break;                                          // ray.py:280
+      if (done) {
+        nseg_acc += nseg;
+        if (!MC) {
+          if (p.out_nseg) p.out_nseg[i] = nseg;
+          if (p.out_final_point) { double* q = p.out_final_point + 3*i; q[0] = point[0]; q[1] = point[1]; q[2] = point[2]; }
+          if (p.out_final_power) p.out_final_power[i] = power;
+        }
+        alive = false;
+      }
     }
-    nseg_acc += nseg;
-    if (!MC) {
-      if (p.out_nseg) p.out_nseg[i] = nseg;
-      if (p.out_final_point) { double* q = p.out_final_point + 3*i; q[0] = point[0]; q[1] = point[1]; q[2] = point[2]; }
-      if (p.out_final_power) p.out_final_power[i] = power;
-    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    p.counters->dbg_cycles = clock64() - c_start; p.counters->dbg_ns = t_end - t_start;
   }
   // per-warp reduction of the counters, one atomic per warp and counter
   nseg_acc = __reduce_add_sync(0xffffffffu, nseg_acc);

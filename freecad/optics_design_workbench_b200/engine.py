@@ -93,7 +93,7 @@ class TraceResult:
     self.overflow = overflow
 
   def close(self):
-    if self._h:
+    if getattr(self, '_h', None):
       load_library().odw_result_destroy(self._h)
       self._h = None
 
@@ -110,6 +110,13 @@ class TraceResult:
     c = _abi.Counts()
     _check(load_library().odw_result_counts(self._h, C.addressof(c)))
     return c.as_dict()
+
+  @property
+  def sm_clock_mhz(self):
+    'effective SM clock the trace kernel saw (clock64 / globaltimer of CTA 0)'
+    c = _abi.Counts()
+    _check(load_library().odw_result_counts(self._h, C.addressof(c)))
+    return c.sm_clock_khz/1e3
 
   @property
   def kernel_ms(self):
@@ -157,7 +164,7 @@ class DeviceScene:
     self._h = h
 
   def close(self):
-    if self._h:
+    if getattr(self, '_h', None):
       load_library().odw_scene_destroy(self._h)
       self._h = None
 
@@ -193,7 +200,7 @@ class DeviceSource:
     self._h = h
 
   def close(self):
-    if self._h:
+    if getattr(self, '_h', None):
       load_library().odw_source_destroy(self._h)
       self._h = None
 
@@ -219,7 +226,7 @@ class Engine:
     self.device_id = device_id
 
   def close(self):
-    if self._h:
+    if getattr(self, '_h', None):
       load_library().odw_engine_destroy(self._h)
       self._h = None
 

@@ -205,7 +205,7 @@ typedef struct odw_counts {
   uint64_t escaped;              /* rays ending with a no-intersection segment (ray.py:105-109) */
   uint64_t depth_terminated;     /* rays stopped by maxIntersections (ray.py:96-98) */
   uint64_t waves;                /* kernel launches of the bounce loop */
-  uint64_t reserved;
+  uint64_t sm_clock_khz;         /* effective SM clock observed inside the kernel (clock64 / globaltimer of CTA 0), kHz */
 } odw_counts;
 
 /* Host copy-out target for hit lists.  Any pointer may be NULL (that column is skipped). */

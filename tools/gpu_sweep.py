@@ -18,9 +18,9 @@ def main():
       best = 1e9
       for rep in range(4):
         with ds.trace_mc(dsrc, cfg, 0x0DDB1A5E, rep*n, n) as res:
-          c, ms = res.counts, res.kernel_ms
+          c, ms, mhz = res.counts, res.kernel_ms, res.sm_clock_mhz
         best = min(best, ms)
-      print(f'{name} n={n:.1e} store={store}: best {best:.2f} ms, last {ms:.2f} ms -> {c["segments"]/best*1e3:.3e} seg/s ({best*1e6/n:.2f} ns/ray)', flush=True)
+      print(f'{name} n={n:.1e} store={store}: best {best:.2f} ms, last {ms:.2f} ms -> {c["segments"]/best*1e3:.3e} seg/s ({best*1e6/n:.2f} ns/ray) sm {mhz:.0f} MHz', flush=True)
 
 if __name__ == '__main__':
   main()
