@@ -89,9 +89,10 @@ class ClockSampler:
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append(line.strip())
+      self.rows.append((time.perf_counter(), line.strip()))
 
-  def stop(self):
+  def stop(self, t0=None, t1=None):
+    'summary of the samples taken between perf_counter times t0 and t1 (all samples if too few fall inside)'
     if not self.proc:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
     time.sleep(0.15)
@@ -101,7 +102,9 @@ class ClockSampler:
     except Exception:
       self.proc.kill()
     sm, smax, reasons, power = [], [], set(), []
-    for r in self.rows:
+    inside = [r for t, r in self.rows if t0 is not None and t0 <= t <= t1 + 0.12]
+    rows = inside if len(inside) >= 2 else [r for _, r in self.rows]
+    for r in rows:
       c = [x.strip() for x in r.split(',')]
       if len(c) < 9:
         continue
@@ -116,7 +119,7 @@ class ClockSampler:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
     sm.sort()
     return dict(sm_mhz=sm[len(sm)//2], sm_max_mhz=max(smax), power_w_max=max(power), samples=len(sm),
-                reasons=sorted(reasons))
+                samples_in_timed_region=len(inside), reasons=sorted(reasons))
 
 
 def cpu_baseline(sim, threads, sample_rays, kind_label):
@@ -219,14 +222,15 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
+  clocks = ClockSampler(local_rank)
+  if rank == 0:
+    clocks.start()
   # ---- warm-up
   for w in range(args.warmup):
     step(10_000 + w).close()
   # ---- timed region: device-resident hot path
   barrier()
-  clocks = ClockSampler(local_rank)
-  if rank == 0:
-    clocks.start()
+  t_region0 = time.perf_counter()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   kernel_ms, segs, hits, launches = 0.0, 0, 0, 0
   ev0.record(stream)
@@ -239,7 +243,8 @@ def main():
   ev1.record(stream)
   barrier()
   elapsed_ms = ev0.elapsed_time(ev1)
-  clk = clocks.stop() if rank == 0 else None
+  t_region1 = time.perf_counter()
+  sm_clock_in_kernel = None
 
   # ---- e2e: the same call with HOST result buffers (pinned), D2H inside the timed region
   e2e = None
@@ -255,13 +260,10 @@ def main():
     view.points, view.directions, view.powers = t_points.data_ptr(), t_dirs.data_ptr(), t_pow.data_ptr()
     view.is_entering, view.group = t_ent.data_ptr(), t_grp.data_ptr()
     import ctypes as C
-    L = engine.load_library()
+    cfg_host = sim.cfg(store_hits=True)
     def e2e_step(k):
-      with step(k) as res:
-        got = C.c_uint64(0)
-        rc = L.odw_result_hits(res._h, C.addressof(view), 0, C.byref(got))
-        assert rc == 0, L.odw_last_error()
-        return res.counts, got.value
+      first = (k*world + rank)*n_rays
+      return dscene.trace_mc_host(dsrc, cfg_host, SEED, first, n_rays, view)
     e2e_step(20_000)
     barrier()
     t0 = time.perf_counter()
@@ -269,11 +271,13 @@ def main():
     for k in range(args.steps):
       c, got = e2e_step(k)
       e_segs += c['segments']; e_hits += got
+      assert c['hits_dropped'] == 0, c
     barrier()
     e_dt = time.perf_counter()-t0
     d2h = int(e_hits/args.steps*(24+24+8+1+4))
     h2d = C.sizeof(_abi.TraceCfg) + 3*8     # the call's scalar arguments; MC rays are generated on the device
     e2e = dict(seconds=e_dt, segments=e_segs, d2h=d2h, h2d=h2d)
+  clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
 
   # ---- reduce over ranks: max time, summed work
   if distributed:
@@ -287,6 +291,8 @@ def main():
     kernel_ms_max, e_seconds = kernel_ms, (e2e['seconds'] if e2e else 0.0)
     segs_all, hits_all, launches_all, e_segs_all = segs, hits, launches, (e2e['segments'] if e2e else 0)
 
+  if rank == 0 and clk is None:
+    clk = clocks.stop(t_region0, t_region1)
   if rank == 0:
     value = segs_all/(elapsed_ms*1e-3)
     peak, peak_src = measured_peak()
@@ -317,7 +323,8 @@ def main():
       clocks=clk)
     if e2e:
       line['e2e'] = dict(value=e_segs_all/e_seconds, unit=UNIT, h2d_bytes_per_step=e2e['h2d'], d2h_bytes_per_step=e2e['d2h'],
-                         note='odw_trace_mc + odw_result_hits into pinned host arrays (points, directions, powers, isEntering, group)')
+                         note='odw_trace_mc_host: hit lists (points, directions, powers, isEntering, group) delivered into pinned host arrays, '
+                              'device->host copy of chunk c overlapped with the trace of chunk c+1')
     if not args.no_cpu_baseline:
       cb, _, _ = cpu_baseline(sim, 1, args.cpu_sample_rays, 'scalar C restatement (oracle/odw_oracle.c), 1 thread')
       line['cpu_baseline'] = cb

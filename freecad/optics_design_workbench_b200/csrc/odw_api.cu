@@ -29,7 +29,10 @@ struct odw_engine {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks (odw_trace_mc_host)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_trace[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+  Counters* pinned_counters = nullptr;  // [2], page-locked
   std::string name;
   // size-keyed pool so that per-call result buffers are not re-allocated every step
   std::multimap<size_t, void*> pool;
@@ -118,8 +121,11 @@ extern "C" int odw_engine_create(int device_id, odw_engine** out) {
   eng->sm_count = prop.multiProcessorCount;
   eng->name = prop.name;
   CU(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&eng->ev0));
   CU(cudaEventCreate(&eng->ev1));
+  for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&eng->ev_trace[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&eng->ev_copy[i], cudaEventDisableTiming)); }
+  CU(cudaHostAlloc((void**)&eng->pinned_counters, 2*sizeof(Counters), cudaHostAllocDefault));
   *out = eng;
   return ODW_OK;
 }
@@ -130,6 +136,9 @@ extern "C" void odw_engine_destroy(odw_engine* eng) {
   for (auto& kv : eng->pool) cudaFree(kv.second);
   if (eng->ev0) cudaEventDestroy(eng->ev0);
   if (eng->ev1) cudaEventDestroy(eng->ev1);
+  for (int i = 0; i < 2; ++i) { if (eng->ev_trace[i]) cudaEventDestroy(eng->ev_trace[i]); if (eng->ev_copy[i]) cudaEventDestroy(eng->ev_copy[i]); }
+  if (eng->pinned_counters) cudaFreeHost(eng->pinned_counters);
+  if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   if (eng->stream) cudaStreamDestroy(eng->stream);
   delete eng;
 }
@@ -472,12 +481,12 @@ static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
   for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
 }
 
-static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const TraceParams& p, bool mc) {
+// Issues the trace of p.n_rays rays as back-to-back launches on the engine stream (no synchronisation).
+static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams& p, bool mc, uint64_t* launches) {
   int per_sm = odw_trace_occupancy(mc, sc->use_bvh, sc->smem);
   if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
   // persistent grid: a multiple of the SM count, no more blocks than there is work
-  uint64_t want = (p.n_rays + 255)/256;
-  int blocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*(uint64_t)per_sm, std::max<uint64_t>(1, want));
+  const int blocks = eng->sm_count*per_sm;
   // Waves: a long request is issued as back-to-back launches of `wave` rays each.  Every launch starts all CTAs
   // in the same phase of the bounce loop; inside one very long launch the CTAs drift apart, their combined
   // instruction working set no longer fits the shared instruction cache levels and the kernel slows down by ~35 %
@@ -485,8 +494,6 @@ static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const 
   // asynchronous on one stream, so there is no host gap between them.
   uint64_t wave = sc->use_bvh ? (1ull << 24) : (1ull << 21);   // BVH scenes have long per-launch tails (uneven ray depth)
   if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
-  uint64_t launches = 0;
-  CU(cudaEventRecord(eng->ev0, eng->stream));
   for (uint64_t off = 0; off < p.n_rays; off += wave) {
     TraceParams q = p;
     q.n_rays = std::min<uint64_t>(wave, p.n_rays - off);
@@ -501,8 +508,16 @@ static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const 
     uint64_t want_w = (q.n_rays + 255)/256;
     int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
     CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->stream));
-    ++launches;
+    if (launches) ++*launches;
   }
+  return ODW_OK;
+}
+
+static int run_trace(odw_engine* eng, const odw_scene* sc, odw_result* r, const TraceParams& p, bool mc) {
+  uint64_t launches = 0;
+  CU(cudaEventRecord(eng->ev0, eng->stream));
+  int rc = launch_waves(eng, sc, p, mc, &launches);
+  if (rc) return rc;
   CU(cudaEventRecord(eng->ev1, eng->stream));
   Counters c;
   CU(cudaMemcpyAsync(&c, r->dcounters, sizeof c, cudaMemcpyDeviceToHost, eng->stream));
@@ -534,6 +549,89 @@ extern "C" int odw_trace_mc(odw_scene* sc, odw_source* src, const odw_trace_cfg*
   rc = run_trace(eng, sc, *out, p, true);
   if (rc && rc != ODW_EOVERFLOW) { odw_result_destroy(*out); *out = nullptr; }
   return rc;
+}
+
+// Monte-Carlo trace with HOST result buffers: the ray range is processed in chunks; while chunk c+1 is traced on the
+// compute stream, the hit columns of chunk c go device->host on the copy stream (double-buffered device hit lists).
+// This is the call the plugin's runSimulationIteration replacement makes when it wants hit lists on the host
+// (reference results_store.py:641-648 appends to Python lists; here the rows land in the caller's arrays).
+extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace_cfg* cfg, uint64_t seed, uint64_t first_ray,
+                                 uint64_t n_rays, const odw_hits_view* host, uint64_t* n_hits_out, odw_counts* counts_out) {
+  if (!sc || !src || !cfg || !host) return fail(ODW_EINVAL, "odw_trace_mc_host: NULL argument");
+  if (sc->eng != src->eng) return fail(ODW_EINVAL, "odw_trace_mc_host: scene and source belong to different engines");
+  if (cfg->n_binnings > 0) return fail(ODW_EUNSUPPORTED, "odw_trace_mc_host: use odw_trace_mc for device binning");
+  odw_engine* eng = sc->eng;
+  CU(cudaSetDevice(eng->device));
+  uint64_t chunk = 1ull << 23;
+  if (const char* w = getenv("ODW_HOST_CHUNK")) { long long v = atoll(w); if (v > 0) chunk = (uint64_t)v; }
+  chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(n_rays, 1));
+  odw_trace_cfg ccfg = *cfg;
+  ccfg.store_hits = 1;
+  ccfg.hit_capacity = std::max<uint64_t>(1024, 2*chunk);
+  odw_result* r[2] = {nullptr, nullptr};
+  TraceParams p[2];
+  auto cleanup = [&]() { odw_result_destroy(r[0]); odw_result_destroy(r[1]); };
+  for (int b = 0; b < 2; ++b) {
+    int rc = prepare_result(eng, sc, &ccfg, chunk, &r[b], p[b]);
+    if (rc) { cleanup(); return rc; }
+    p[b].src = src->d; p[b].seed = seed;
+    p[b].max_len = cfg->max_ray_length*src->max_ray_length_scale;
+    p[b].max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
+    p[b].wavelength = src->d.wavelength;
+    set_ignore(p[b], src->ignored.data(), (int)src->ignored.size());
+  }
+  const uint64_t n_chunks = (n_rays + chunk - 1)/chunk;
+  odw_counts total; memset(&total, 0, sizeof total);
+  total.rays = n_rays;
+  uint64_t stored = 0, dropped_host = 0, launches = 0;
+  auto issue = [&](uint64_t c) -> int {        // queue the trace of chunk c on the compute stream
+    const int b = (int)(c & 1);
+    if (c >= 2) CU(cudaStreamWaitEvent(eng->stream, eng->ev_copy[b], 0));   // buffer b still being copied out
+    CU(cudaMemsetAsync(r[b]->dcounters, 0, sizeof(Counters), eng->stream));
+    p[b].first_ray = first_ray + c*chunk;
+    p[b].n_rays = std::min<uint64_t>(chunk, n_rays - c*chunk);
+    int rc = launch_waves(eng, sc, p[b], true, &launches);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&eng->pinned_counters[b], r[b]->dcounters, sizeof(Counters), cudaMemcpyDeviceToHost, eng->stream));
+    CU(cudaEventRecord(eng->ev_trace[b], eng->stream));
+    return ODW_OK;
+  };
+  int rc = ODW_OK;
+  if (n_chunks > 0 && (rc = issue(0))) { cleanup(); return rc; }
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int b = (int)(c & 1);
+    if (c + 1 < n_chunks && (rc = issue(c + 1))) { cleanup(); return rc; }
+    CU(cudaEventSynchronize(eng->ev_trace[b]));
+    const Counters k = eng->pinned_counters[b];
+    total.segments += k.segments; total.hits += k.hits; total.hits_dropped += k.hits_dropped;
+    total.escaped += k.escaped; total.depth_terminated += k.depth_terminated;
+    if (k.dbg_ns) total.sm_clock_khz = (uint64_t)((double)k.dbg_cycles*1e6/(double)k.dbg_ns);
+    uint64_t have = std::min<uint64_t>(k.hits, r[b]->hb.capacity);
+    uint64_t n = std::min<uint64_t>(have, host->capacity > stored ? host->capacity - stored : 0);
+    dropped_host += have - n;
+    cudaStream_t cs = eng->copy_stream;
+    const HitBuffers& hb = r[b]->hb;
+    if (n) {
+      if (host->points)      CU(cudaMemcpyAsync(host->points + 3*stored, hb.points, n*24, cudaMemcpyDeviceToHost, cs));
+      if (host->directions)  CU(cudaMemcpyAsync(host->directions + 3*stored, hb.dirs, n*24, cudaMemcpyDeviceToHost, cs));
+      if (host->powers)      CU(cudaMemcpyAsync(host->powers + stored, hb.powers, n*8, cudaMemcpyDeviceToHost, cs));
+      if (host->is_entering) CU(cudaMemcpyAsync(host->is_entering + stored, hb.entering, n, cudaMemcpyDeviceToHost, cs));
+      if (host->ray_index)   CU(cudaMemcpyAsync(host->ray_index + stored, hb.ray_index, n*8, cudaMemcpyDeviceToHost, cs));
+      if (host->group)       CU(cudaMemcpyAsync(host->group + stored, hb.group, n*4, cudaMemcpyDeviceToHost, cs));
+      if (host->bounce)      CU(cudaMemcpyAsync(host->bounce + stored, hb.bounce, n*4, cudaMemcpyDeviceToHost, cs));
+      if (host->face_id)     CU(cudaMemcpyAsync(host->face_id + stored, hb.face_id, n*4, cudaMemcpyDeviceToHost, cs));
+    }
+    CU(cudaEventRecord(eng->ev_copy[b], cs));
+    stored += n;
+  }
+  CU(cudaStreamSynchronize(eng->copy_stream));
+  CU(cudaStreamSynchronize(eng->stream));
+  cleanup();
+  total.waves = launches;
+  total.hits_dropped += dropped_host;
+  if (n_hits_out) *n_hits_out = stored;
+  if (counts_out) *counts_out = total;
+  return total.hits_dropped ? fail(ODW_EOVERFLOW, std::to_string(total.hits_dropped) + " hits did not fit the host / chunk hit buffers") : ODW_OK;
 }
 
 extern "C" int odw_sample_mc(odw_source* src, uint64_t seed, uint64_t first_ray, uint64_t n, double* first_var, double* phi,

@@ -7,6 +7,9 @@
 // over launches or GPUs.  Small scenes are staged in shared memory and tested face by face (uniform loop,
 // no divergence between lanes of a warp); large scenes walk a BVH with a per-thread short stack.
 #include <cooperative_groups.h>
+#ifndef ODW_BLOCK_SYNC
+#define ODW_BLOCK_SYNC 1
+#endif
 #define ODW_DEVICE_CODE
 #include "odw_device.cuh"
 

@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, 'libodw_b200.so')
 
 EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name', 'odw_engine_stream',
            'odw_scene_create', 'odw_scene_destroy', 'odw_source_create', 'odw_source_destroy',
-           'odw_trace_mc', 'odw_sample_mc', 'odw_trace_rays', 'odw_result_counts', 'odw_result_hits',
+           'odw_trace_mc', 'odw_trace_mc_host', 'odw_sample_mc', 'odw_trace_rays', 'odw_result_counts', 'odw_result_hits',
            'odw_result_histogram', 'odw_result_histogram_device', 'odw_result_ray_summary',
            'odw_result_kernel_ms', 'odw_result_destroy']
 
@@ -66,6 +66,7 @@ def load_library():
   L.odw_source_create.argtypes = [vp, vp, C.POINTER(vp)]
   L.odw_source_destroy.argtypes = [vp]; L.odw_source_destroy.restype = None
   L.odw_trace_mc.argtypes = [vp, vp, vp, u64, u64, u64, C.POINTER(vp)]
+  L.odw_trace_mc_host.argtypes = [vp, vp, vp, u64, u64, u64, vp, C.POINTER(u64), vp]
   L.odw_sample_mc.argtypes = [vp, u64, u64, u64, vp, vp, vp, vp]
   L.odw_trace_rays.argtypes = [vp, vp, vp, vp, vp, vp, i32, u64, C.POINTER(vp)]
   L.odw_result_counts.argtypes = [vp, vp]
@@ -183,6 +184,17 @@ class DeviceScene:
                                               ign.ctypes.data if len(ign) else None, len(ign), len(o), C.byref(h)),
                 allow=(_abi.ODW_EOVERFLOW,))
     return TraceResult(h, cfg, overflow=(rc == _abi.ODW_EOVERFLOW))
+
+  def trace_mc_host(self, source, cfg, seed, first_ray, n_rays, hits_view):
+    '''
+    odw_trace_mc_host: hit rows are written into the host arrays behind `hits_view` (an _abi.HitsView, ideally
+    over page-locked memory) while later chunks are still being traced.  Returns (counts dict, rows written).
+    '''
+    got, counts = C.c_uint64(0), _abi.Counts()
+    _check(load_library().odw_trace_mc_host(self._h, source._h, C.addressof(cfg.cfg), int(seed), int(first_ray),
+                                            int(n_rays), C.addressof(hits_view), C.byref(got), C.addressof(counts)),
+           allow=(_abi.ODW_EOVERFLOW,))
+    return counts.as_dict(), got.value
 
   def trace_mc(self, source, cfg, seed, first_ray, n_rays):
     h = C.c_void_p()

@@ -246,6 +246,12 @@ void odw_source_destroy(odw_source*);
 int  odw_trace_mc(odw_scene*, odw_source*, const odw_trace_cfg*, uint64_t seed,
                   uint64_t first_ray, uint64_t n_rays, odw_result** out);
 
+/* Monte-Carlo trace with the hit list delivered straight into HOST arrays (page-locked memory recommended): the
+ * range is traced in chunks and the device->host copy of chunk c overlaps the trace of chunk c+1.  Rows are appended
+ * in chunk order (unsorted inside a chunk).  *n_hits_out = rows written; counts_out may be NULL. */
+int  odw_trace_mc_host(odw_scene*, odw_source*, const odw_trace_cfg*, uint64_t seed, uint64_t first_ray, uint64_t n_rays,
+                       const odw_hits_view* host, uint64_t* n_hits_out, odw_counts* counts_out);
+
 /* Same draws as odw_trace_mc, returned instead of traced (parity of the sampler):
  * first_var[n] (theta | r), phi[n], origins[n][3], directions[n][3]; any may be NULL. */
 int  odw_sample_mc(odw_source*, uint64_t seed, uint64_t first_ray, uint64_t n_rays,

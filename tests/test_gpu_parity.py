@@ -253,6 +253,29 @@ def test_count_only_and_histogram_modes(gpu_engine, oracle, sims):
   assert np.abs(o['histograms'][0]-hist).sum() <= 2
 
 
+def test_host_delivery_equals_device_hit_list(gpu_engine, sims):
+  'odw_trace_mc_host (chunked, copy overlapped with compute) delivers exactly the rows of odw_trace_mc'
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n = 300000
+  os.environ['ODW_HOST_CHUNK'] = '70000'       # several chunks, last one ragged
+  try:
+    arrays = _abi.HitArrays(n+16)
+    counts, got = ds.trace_mc_host(dsrc, sim.cfg(), SEED, 123, n, arrays.view)
+  finally:
+    del os.environ['ODW_HOST_CHUNK']
+  host = arrays.trimmed(got, sort=True)
+  with ds.trace_mc(dsrc, sim.cfg(hit_capacity=2*n), SEED, 123, n) as res:
+    dev, c = res.hits(sort=True), res.counts
+  assert got == c['hits'] and counts['segments'] == c['segments'] and counts['escaped'] == c['escaped']
+  for key in dev:
+    assert np.array_equal(host[key], dev[key]), key
+  # too small a host buffer: reported, prefix still valid
+  small = _abi.HitArrays(1000)
+  counts, got = ds.trace_mc_host(dsrc, sim.cfg(), SEED, 123, n, small.view)
+  assert got == 1000 and counts['hits_dropped'] == c['hits']-1000
+
+
 def test_range_splitting_is_invariant(gpu_engine, sims):
   'Philox counter = global ray index: tracing [0,n) equals tracing [0,k) and [k,n) (GPU-count invariance, SURVEY §8e)'
   sim = sims('lensesAndMirrors')
