@@ -73,6 +73,7 @@ struct odw_scene {
   bool use_bvh = false;
   size_t smem = 0;
   int n_groups = 0;
+  double extent = 0;                    // max |coordinate| over all face boxes
 };
 
 struct odw_source {
@@ -80,6 +81,7 @@ struct odw_source {
   DSource d{};
   std::vector<void*> owned;
   double max_ray_length_scale = 1, max_intersections_scale = 1;
+  double origin_bound = 0;              // max |coordinate| a ray origin of this source can have
   std::vector<int32_t> ignored;
 };
 
@@ -291,33 +293,35 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   }
   // shells: the reference culls per shell box first; faces of one shell must be contiguous (odw.h: "sorted by shell")
   std::vector<DShell> shells;
+  double extent = 0;                           // max |coordinate| of the scene (feeds the fp32 culling margin)
+  auto make_shell = [&](int face_first, int face_count, int group) {
+    DShell d; memset(&d, 0, sizeof d);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int f = face_first; f < face_first + face_count; ++f)
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], sd->faces[f].aabb_min[k]); hi[k] = std::max(hi[k], sd->faces[f].aabb_max[k]); }
+    for (int k = 0; k < 3; ++k) {
+      d.lo[k] = BvhBuilder::down(lo[k]); d.hi[k] = BvhBuilder::up(hi[k]);
+      if (face_count > 0) extent = std::max(extent, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+    }
+    d.face_first = face_first; d.face_count = face_count; d.group = group;
+    if (face_count > 0) { d.seqmask[0] = faces[(size_t)face_first].seqmask[0]; d.seqmask[1] = faces[(size_t)face_first].seqmask[1]; }
+    return d;
+  };
   if (sd->n_shells > 0 && sd->shells) {
     for (int i = 0; i < sd->n_shells; ++i) {
       const odw_shell& h = sd->shells[i];
       if (h.face_first < 0 || h.face_count < 0 || h.face_first + h.face_count > sd->n_faces || h.group < 0 || h.group >= sd->n_groups)
         return fail(ODW_EINVAL, "shell " + std::to_string(i) + ": face range or group out of bounds");
-      DShell d; memset(&d, 0, sizeof d);
-      for (int k = 0; k < 3; ++k) { d.bmin[k] = 1e300; d.bmax[k] = -1e300; }
-      for (int f = h.face_first; f < h.face_first + h.face_count; ++f) {
+      for (int f = h.face_first; f < h.face_first + h.face_count; ++f)
         if (sd->faces[f].group != h.group) return fail(ODW_EINVAL, "shell " + std::to_string(i) + ": faces of a shell must share its group");
-        for (int k = 0; k < 3; ++k) { d.bmin[k] = std::min(d.bmin[k], sd->faces[f].aabb_min[k]); d.bmax[k] = std::max(d.bmax[k], sd->faces[f].aabb_max[k]); }
-      }
-      d.face_first = h.face_first; d.face_count = h.face_count; d.group = h.group;
-      if (h.face_count > 0) { d.seqmask[0] = faces[(size_t)h.face_first].seqmask[0]; d.seqmask[1] = faces[(size_t)h.face_first].seqmask[1]; }
-      shells.push_back(d);
+      shells.push_back(make_shell(h.face_first, h.face_count, h.group));
     }
     std::vector<char> covered((size_t)sd->n_faces, 0);
     for (const DShell& d : shells) for (int f = d.face_first; f < d.face_first + d.face_count; ++f) covered[(size_t)f]++;
     for (int f = 0; f < sd->n_faces; ++f) if (covered[(size_t)f] != 1) return fail(ODW_EINVAL, "face " + std::to_string(f) + " is not covered by exactly one shell");
   } else {
     // no shell table given: one shell per face
-    for (int f = 0; f < sd->n_faces; ++f) {
-      DShell d; memset(&d, 0, sizeof d);
-      for (int k = 0; k < 3; ++k) { d.bmin[k] = sd->faces[f].aabb_min[k]; d.bmax[k] = sd->faces[f].aabb_max[k]; }
-      d.face_first = f; d.face_count = 1; d.group = sd->faces[f].group;
-      d.seqmask[0] = faces[(size_t)f].seqmask[0]; d.seqmask[1] = faces[(size_t)f].seqmask[1];
-      shells.push_back(d);
-    }
+    for (int f = 0; f < sd->n_faces; ++f) shells.push_back(make_shell(f, 1, sd->faces[f].group));
   }
   std::vector<DGroup> groups((size_t)sd->n_groups);
   for (int i = 0; i < sd->n_groups; ++i) {
@@ -328,7 +332,7 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     d.type = g.optical_type; d.record = g.record_hits; d.gtype = g.grating_type; d.pad = 0;
   }
   odw_scene* sc = new odw_scene();
-  sc->eng = eng; sc->n_groups = sd->n_groups;
+  sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
   int rc;
   if ((rc = upload(eng, sc->owned, faces.data(), faces.size(), &sc->d.faces))) { odw_scene_destroy(sc); return rc; }
   if ((rc = upload(eng, sc->owned, shells.data(), shells.size(), &sc->d.shells))) { odw_scene_destroy(sc); return rc; }
@@ -398,6 +402,18 @@ extern "C" int odw_source_create(odw_engine* eng, const odw_source_desc* sd, odw
   s->d.focal = sd->focal_length; s->d.wavelength = sd->wavelength;
   for (int i = 0; i < 12; ++i) s->d.M[i] = sd->gpM[i];
   s->d.kind = sd->kind; s->d.source_id = sd->source_id; s->d.n_first = sd->n_first; s->d.n_phi = sd->n_phi; s->d.n_rows = sd->n_rows;
+  {
+    // _makeRay: |local origin| <= 2|f| per component (spherical) or max |r| (collimated), then gpM
+    const double r = sd->kind == ODW_SRC_POINT_SPHERICAL ? 2*std::fabs(sd->focal_length)
+                                                         : std::max(std::fabs(sd->first_lo), std::fabs(sd->first_hi));
+    double b = 0;
+    for (int i = 0; i < 3; ++i) {
+      double row = std::fabs(sd->gpM[4*i+3]);
+      for (int k = 0; k < 3; ++k) row += r*std::fabs(sd->gpM[4*i+k]);
+      b = std::max(b, row);
+    }
+    s->origin_bound = b;
+  }
   s->max_ray_length_scale = sd->max_ray_length_scale > 0 ? sd->max_ray_length_scale : 1.0;
   s->max_intersections_scale = sd->max_intersections_scale > 0 ? sd->max_intersections_scale : 1.0;
   if (sd->n_ignored > 0 && sd->ignored_groups) s->ignored.assign(sd->ignored_groups, sd->ignored_groups + sd->n_ignored);
@@ -477,6 +493,16 @@ static int prepare_result(odw_engine* eng, const odw_scene* sc, const odw_trace_
   return ODW_OK;
 }
 
+// Widening of the fp32 culling boxes (shells, BVH nodes).  The slab test runs in fp32 on the ray origin rounded to
+// fp32: origin rounding <= 2^-24 |s|, each slab distance carries <= 3 roundings (2^-22 relative) of |b - s| <= E and
+// of t <= max_len.  A box widened by distTol + 2e-6 E (about 8x that bound) therefore contains every point the exact
+// fp64 test of the reference rule (box enlarged by distTol, ray.py:353-364) would accept.
+static void set_cull_margin(TraceParams& p, const odw_scene* sc, double origin_bound) {
+  const double E = sc->extent + origin_bound + p.max_len;
+  p.cull_margin = std::nextafter((float)(p.tol + 2e-6*E), INFINITY);
+  p.origin_bound = (float)origin_bound;
+}
+
 static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
   for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
 }
@@ -546,6 +572,7 @@ extern "C" int odw_trace_mc(odw_scene* sc, odw_source* src, const odw_trace_cfg*
   p.max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
   p.wavelength = src->d.wavelength;
   set_ignore(p, src->ignored.data(), (int)src->ignored.size());
+  set_cull_margin(p, sc, src->origin_bound);
   rc = run_trace(eng, sc, *out, p, true);
   if (rc && rc != ODW_EOVERFLOW) { odw_result_destroy(*out); *out = nullptr; }
   return rc;
@@ -579,6 +606,7 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
     p[b].max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
     p[b].wavelength = src->d.wavelength;
     set_ignore(p[b], src->ignored.data(), (int)src->ignored.size());
+    set_cull_margin(p[b], sc, src->origin_bound);
   }
   const uint64_t n_chunks = (n_rays + chunk - 1)/chunk;
   odw_counts total; memset(&total, 0, sizeof total);
@@ -684,6 +712,10 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   p.first_ray = 0;
   p.wavelength = 500.0;
   set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0);
+  double origin_bound = 0;
+  for (uint64_t i = 0; i < 3*n_rays; ++i) origin_bound = std::max(origin_bound, std::fabs(origins[i]));
+  if (!std::isfinite(origin_bound)) return bail(fail(ODW_EINVAL, "odw_trace_rays: non-finite ray origin"));
+  set_cull_margin(p, sc, origin_bound);
   rc = run_trace(eng, sc, r, p, false);
   if (rc && rc != ODW_EOVERFLOW) return bail(rc);
   return rc;

@@ -25,11 +25,14 @@ struct DFace {
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
 #define DFACE_FAST   2             // plane/uvbox, sphere (whole or full-u cap), cylinder (full-u band): inline test
 
-// Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).
-struct DShell {
-  double bmin[3], bmax[3];
-  int32_t face_first, face_count, group, pad;
+// Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).  The box is fp32,
+// rounded outward; the kernel widens it by TraceParams::cull_margin (distTol + the fp32 error bound of the slab
+// test) while staging it into shared memory, so the fp32 test can only over-accept, never reject a true hit.
+struct DShell {                    // 64 B
+  float lo[3], hi[3];
+  int32_t face_first, face_count;
   unsigned long long seqmask[2];
+  int32_t group, pad[3];
 };
 
 struct DGroup {
@@ -96,6 +99,8 @@ struct TraceParams {
   unsigned long long seed, first_ray, n_rays;
   double max_len, tol, power_tol, wavelength;
   int32_t max_isect, sequential, record_all, store_hits;
+  float cull_margin;                 // widening of the fp32 shell / BVH boxes, see odw_api.cu cull_margin()
+  float origin_bound;                // max |coordinate| of any ray origin of this launch (host-side bound)
 };
 
 #ifdef ODW_DEVICE_CODE   // device functions: only the kernel translation unit defines this

@@ -35,6 +35,7 @@ __device__ __forceinline__ void outward_normal(const DFace& f, const double* P, 
 
 struct NearestHit {
   double tA, tB;     // closest accepted hit overall / closest whose group differs from the current medium
+  double lim;        // min(maxRayLength + distTol, tA + 2 distTol): nothing at or beyond it can be chosen (ray.py:425,432,440)
   int fA, fB;
 };
 
@@ -58,16 +59,16 @@ __device__ __noinline__ void test_face_general(const DFace& f, int idx, const od
   for (int k = 0; k < nt; ++k) {
     double t = ts[k];
     if (!(t > tol)) continue;                                        // ray.py:424  |P - start| > distTol (and forward)
-    if (!(t < tmax) || !(t < h.tA + 2*tol)) continue;                 // ray.py:425,432,440
+    if (!(t < h.lim)) continue;                                      // ray.py:425,432,440
     double P[3] = { s[0]+t*dn[0], s[1]+t*dn[1], s[2]+t*dn[2] };
     if (!on_trimmed_face(f, segs, P, tol)) continue;                 // ray.py:426
-    if (t < h.tA) { h.tA = t; h.fA = idx; }
+    if (t < h.tA) { h.tA = t; h.fA = idx; h.lim = fmin(h.lim, t + 2*tol); }
     if (f.group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
   }
 }
 
-__device__ __forceinline__ void accept_hit(double t, int idx, int group, int medium, NearestHit& h) {
-  if (t < h.tA) { h.tA = t; h.fA = idx; }
+__device__ __forceinline__ void accept_hit(double t, int idx, int group, int medium, double tol, NearestHit& h) {
+  if (t < h.tA) { h.tA = t; h.fA = idx; h.lim = fmin(h.lim, t + 2*tol); }
   if (group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
 }
 
@@ -83,14 +84,14 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
   }
   const double tol = p.tol;
   if (!(f.flags & DFACE_FAST)) { test_face_general(f, idx, p.scene.segs, tol, s, dn, medium, tmax, h); return; }
-  const double limit = fmin(tmax, h.tA + 2*tol);                     // ray.py:425,432,440
+  const double limit = h.lim;
   if (f.kind == ODW_SURF_PLANE) {
     const double den = dot3(dn, f.z);
     const double t = (f.c0 - dot3(s, f.z))*fast_rcp(den);            // den == 0: inf/NaN fails the range test
     if (t > tol && t < limit) {
       const double Px = fma(t, dn[0], s[0]), Py = fma(t, dn[1], s[1]), Pz = fma(t, dn[2], s[2]);
       const double u = dot3(Px, Py, Pz, f.x) - f.c1, v = dot3(Px, Py, Pz, f.y) - f.c2;
-      if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, h);
+      if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, tol, h);
     }
     return;
   }
@@ -114,7 +115,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
     const double t = k ? tf : tn;
     if (t > tol && t < limit) {
       const double zc = fma(t, dz, wz);                              // axial coordinate of the hit
-      if (zc >= f.c0 - tol && zc <= f.c1 + tol) accept_hit(t, idx, f.group, medium, h);
+      if (zc >= f.c0 - tol && zc <= f.c1 + tol) accept_hit(t, idx, f.group, medium, tol, h);
     }
   }
 }
@@ -122,28 +123,36 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
 // Ray.findNearestIntersection (ray.py:290-452) on the scene staged in shared memory: shells are culled by
 // their box first (ray.py:345-374), faces of surviving shells are tested one by one.  All lanes of a warp walk
 // the same shell/face lists, so shared-memory reads are broadcasts.
+// The shell cull is a conservative fp32 slab test (boxes widened by cull_margin while staging, see odw_api.cu):
+// it only decides which faces get the exact fp64 test, so it cannot change a result.  In fp64 this cull was 45 %
+// of all executed instructions (fmin/fmax on doubles are multi-instruction sequences; FMNMX is one).
 __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DFace* sfaces, const TraceParams& p,
                                                  const double* s, const double* dn,
                                                  int medium, int seq_index, double max_len, double& t_out) {
-  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.fA = -1; h.fB = -1;
   const double tol = p.tol;
   const double tmax = max_len + tol;
-  const double inv0 = fast_rcp(dn[0]), inv1 = fast_rcp(dn[1]), inv2 = fast_rcp(dn[2]);
+  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = tmax; h.fA = -1; h.fB = -1;
+  const float sx = (float)s[0], sy = (float)s[1], sz = (float)s[2];
+  const float ix = __frcp_rn((float)dn[0]), iy = __frcp_rn((float)dn[1]), iz = __frcp_rn((float)dn[2]);   // 1/0 = inf is fine
+  float limf = (float)tmax*1.000002f;                                  // nothing beyond this can still matter
+  const bool seq_off = !p.sequential;
+  const bool seq_dead = seq_index >= 128;
+  const int sw = (seq_index >> 6) & 1, sb = seq_index & 63;
   const int ns = p.scene.n_shells;
   for (int si = 0; si < ns; ++si) {
     const DShell& sh = sshells[si];
-    if (p.sequential && (seq_index >= 128 || !((sh.seqmask[seq_index >> 6] >> (seq_index & 63)) & 1ull))) continue;
-    if (sh.group < 256 && ((p.ignore_mask[sh.group >> 6] >> (sh.group & 63)) & 1ull)) continue;
-    double ta = (sh.bmin[0] - tol - s[0])*inv0, tb = (sh.bmax[0] + tol - s[0])*inv0;
-    double t0 = fmin(ta, tb), t1 = fmax(ta, tb);
-    ta = (sh.bmin[1] - tol - s[1])*inv1; tb = (sh.bmax[1] + tol - s[1])*inv1;
-    t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
-    ta = (sh.bmin[2] - tol - s[2])*inv2; tb = (sh.bmax[2] + tol - s[2])*inv2;
-    t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+    if (!seq_off && (seq_dead || !((sh.seqmask[sw] >> sb) & 1ull))) continue;
+    float ta = (sh.lo[0] - sx)*ix, tb = (sh.hi[0] - sx)*ix;             // NaN (0*inf) is dropped by fminf/fmaxf
+    float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+    ta = (sh.lo[1] - sy)*iy; tb = (sh.hi[1] - sy)*iy;
+    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+    ta = (sh.lo[2] - sz)*iz; tb = (sh.hi[2] - sz)*iz;
+    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
     // miss, entirely behind the start, or beyond what can still matter
-    if (t0 > t1 || t1 < 0.0 || t0 > fmin(tmax, h.tA + 2*tol)) continue;
+    if (t0 > t1 || t1 < 0.0f || t0 > limf) continue;
     const int f1 = sh.face_first + sh.face_count;
     for (int i = sh.face_first; i < f1; ++i) test_face<false>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
+    limf = (float)h.lim*1.000002f;
   }
   if (h.fA < 0) return -1;
   if (h.fB >= 0 && h.tB < h.tA + 2*tol) { t_out = h.tB; return h.fB; }   // prefer "not the current medium" (ray.py:445-452)
@@ -153,9 +162,9 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
 // same rule, faces reached through a BVH over face boxes (replaces the shell/face BoundBox culls of ray.py:345-404)
 __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const double* s, const double* dn,
                                                 int medium, int seq_index, double max_len, double& t_out) {
-  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.fA = -1; h.fB = -1;
-  const BvhNode* __restrict__ nodes = p.scene.bvh;
   const double tol = p.tol;
+  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = max_len + tol; h.fA = -1; h.fB = -1;
+  const BvhNode* __restrict__ nodes = p.scene.bvh;
   double inv[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) inv[i] = 1.0/dn[i];
@@ -229,8 +238,11 @@ __device__ __noinline__ void init_ray_mc(const TraceParams& p, unsigned long lon
   make_ray(p.src, first, phi, point, dir);
 }
 
+#ifndef ODW_MIN_BLOCKS
+#define ODW_MIN_BLOCKS 2
+#endif
 template <bool MC, bool BVH>
-__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(256, ODW_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DShell* sshells = reinterpret_cast<DShell*>(smem_raw);
   DFace* sfaces = reinterpret_cast<DFace*>(smem_raw + (size_t)p.scene.n_shells*sizeof(DShell));
@@ -244,6 +256,19 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     dst = reinterpret_cast<int4*>(sfaces);
     n16 = (int)((size_t)p.scene.n_faces*sizeof(DFace)/16);
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+    // widen the fp32 shell boxes by the culling margin; shells of ignored groups (IgnoredOpticalElements,
+    // generic_source.py:23-37 / find.py:79-104) are moved out of reach (a point at 3e38) and lose their faces
+    for (int i = threadIdx.x; i < p.scene.n_shells; i += blockDim.x) {
+      DShell& sh = sshells[i];
+      const bool ignored = sh.group < 256 && ((p.ignore_mask[sh.group >> 6] >> (sh.group & 63)) & 1ull);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        sh.lo[k] = ignored ? 3.0e38f : __fsub_rd(sh.lo[k], p.cull_margin);
+        sh.hi[k] = ignored ? 3.0e38f : __fadd_ru(sh.hi[k], p.cull_margin);
+      }
+      if (ignored) sh.face_count = 0;
+    }
     __syncthreads();
   }
   unsigned long long t_start = 0, c_start = 0;

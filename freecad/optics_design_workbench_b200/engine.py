@@ -16,7 +16,7 @@ import numpy as np
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libodw_b200.so')
+LIB_PATH = os.environ.get('ODW_LIB') or os.path.join(_HERE, 'libodw_b200.so')   # ODW_LIB: developer override (kernel variants)
 
 EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name', 'odw_engine_stream',
            'odw_scene_create', 'odw_scene_destroy', 'odw_source_create', 'odw_source_destroy',
