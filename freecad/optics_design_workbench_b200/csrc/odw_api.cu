@@ -17,6 +17,7 @@ extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long 
                                          unsigned long long n, double* first_out, double* phi_out, double* origins,
                                          double* dirs, int blocks, cudaStream_t st);
 extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem);
+extern "C" int odw_trace_threads(void);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -278,6 +279,12 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
       const bool full_u = (d.flags & DFACE_FULL_U) != 0;
       if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_UVBOX) {
         d.flags |= DFACE_FAST; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
+      } else if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_LOOPS && f.seg_count == 1 &&
+                 sd->segs[f.seg_first].kind == ODW_SEG_ARC && sd->segs[f.seg_first].a[4] >= ODW_TWO_PI - 1e-12) {
+        // a disc: the single trim loop is one full circle (centre a[0], a[1], radius a[2])
+        const odw_trimseg& c = sd->segs[f.seg_first];
+        d.flags |= DFACE_FAST | DFACE_DISC; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
+        d.umin = c.a[0]; d.vmin = c.a[1]; d.umax = c.a[2]; d.vmax = c.a[2];
       } else if (f.kind == ODW_SURF_SPHERE && (f.trim_kind == ODW_TRIM_NONE || (f.trim_kind == ODW_TRIM_UVBOX && full_u))) {
         d.flags |= DFACE_FAST;
         const bool whole = f.trim_kind == ODW_TRIM_NONE;
@@ -531,7 +538,8 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
       if (p.out_final_point) q.out_final_point = p.out_final_point + 3*off;
       if (p.out_final_power) q.out_final_power = p.out_final_power + off;
     }
-    uint64_t want_w = (q.n_rays + 255)/256;
+    const uint64_t tpb = (uint64_t)odw_trace_threads();
+    uint64_t want_w = (q.n_rays + tpb - 1)/tpb;
     int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
     CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->stream));
     if (launches) ++*launches;

@@ -23,7 +23,8 @@ struct DFace {
   double c0, c1, c2, c3;           // fast-path constants: plane (o.z, o.x, o.y) | sphere/cylinder axial bounds (lo, hi)
 };
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
-#define DFACE_FAST   2             // plane/uvbox, sphere (whole or full-u cap), cylinder (full-u band): inline test
+#define DFACE_FAST   2             // plane/uvbox, plane/disc, sphere (whole or full-u cap), cylinder (full-u band): inline test
+#define DFACE_DISC   4             // plane whose only trim loop is one full circle: umin,vmin = centre, umax = radius
 
 // Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).  The box is fp32,
 // rounded outward; the kernel widens it by TraceParams::cull_margin (distTol + the fp32 error bound of the slab
@@ -434,7 +435,7 @@ __device__ __noinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* 
 }
 
 // outward unit normal at P (ray.py:463-465 + face orientation)
-__device__ __noinline__ void outward_normal_general(const DFace& f, const double* P, double* n) {
+__device__ __forceinline__ void outward_normal_general(const DFace& f, const double* P, double* n) {
   double w[3] = { P[0]-f.o[0], P[1]-f.o[1], P[2]-f.o[2] };
   double g[3];
   switch (f.kind) {
@@ -482,8 +483,13 @@ __device__ __forceinline__ bool snell(const double* ray, double n1, double n2, c
   return false;
 }
 
-__device__ __noinline__ void line_grating(const double* ray_in, double n1, double n2, const double* normal, const DGroup& g,
-                                          double wavelength_nm, bool transmission, double* out) {
+struct Vec3 { double x, y, z; };
+// by value in, by value out: pointers to the caller's ray state would pin it to local memory
+__device__ __noinline__ Vec3 line_grating(double rx, double ry, double rz, double n1, double n2, double nx, double ny, double nz,
+                                          const DGroup* gp, double wavelength_nm, bool transmission) {
+  const DGroup& g = *gp;
+  const double ray_in[3] = { rx, ry, rz }, normal[3] = { nx, ny, nz };
+  double out[3];
   double wl = wavelength_nm/1000.0;
   double rl = sqrt(dot3(ray_in, ray_in)), nl = sqrt(dot3(normal, normal)), gl = sqrt(dot3(g.gdir, g.gdir));
   double ray[3], sn[3], gv[3];
@@ -501,5 +507,7 @@ __device__ __noinline__ void line_grating(const double* ray_in, double n1, doubl
   double q1 = (-2*V + sq)/2, q2 = (-2*V - sq)/2;
   double Q = transmission ? fmin(q1, q2) : fmax(q1, q2);
   for (int i = 0; i < 3; ++i) out[i] = -(mu*ray[i] - T*D[i] + Q*sn[i]);
+  Vec3 r; r.x = out[0]; r.y = out[1]; r.z = out[2];
+  return r;
 }
 #endif  // ODW_DEVICE_CODE

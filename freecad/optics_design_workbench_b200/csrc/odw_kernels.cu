@@ -15,7 +15,7 @@
 
 namespace cg = cooperative_groups;
 
-// outward unit normal: inline for plane / sphere / cylinder, general (noinline) otherwise
+// outward unit normal: short paths for plane / sphere / cylinder, general otherwise
 __device__ __forceinline__ void outward_normal(const DFace& f, const double* P, double* n) {
   if (f.kind == ODW_SURF_PLANE) {
     const double sg = (double)f.nsign;
@@ -39,9 +39,14 @@ struct NearestHit {
   int fA, fB;
 };
 
-// general face test: any surface kind, any trim (cone, torus, partial azimuth ranges, pcurve loops)
-__device__ __noinline__ void test_face_general(const DFace& f, int idx, const odw_trimseg* __restrict__ segs, double tol,
-                                               const double* s, const double* dn, int medium, double tmax, NearestHit& h) {
+// general face test: any surface kind, any trim (cone, torus, partial azimuth ranges, pcurve loops).  Out of line and
+// called BY VALUE: a pointer to the caller's ray state would force that state into local memory for the whole
+// kernel.  Returns the smallest t in (tol, lim) whose point lies on the trimmed face, or +inf.  (All hits of one face
+// share its group, so only the nearest one can win either slot of NearestHit.)
+__device__ __noinline__ double general_nearest(const DFace* fp, const odw_trimseg* __restrict__ segs, double tol,
+                                               double sx, double sy, double sz, double dx, double dy, double dz, double lim) {
+  const DFace& f = *fp;
+  const double s[3] = { sx, sy, sz }, dn[3] = { dx, dy, dz };
   if (f.kind == ODW_SURF_TORUS) {
     // slab test against the face's box (ray.py:390-398 culls with the face BoundBox the same way);
     // 1/0 = inf is fine here: fmin/fmax drop the NaN of 0*inf
@@ -52,19 +57,20 @@ __device__ __noinline__ void test_face_general(const DFace& f, int idx, const od
       double ta = (f.bmin[i] - tol - s[i])*inv, tb = (f.bmax[i] + tol - s[i])*inv;
       t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
     }
-    if (t0 > t1) return;
+    if (t0 > t1) return 1e300;
   }
   double ts[4];
   int nt = line_surface(f, s, dn, ts);
+  double best = 1e300;
   for (int k = 0; k < nt; ++k) {
     double t = ts[k];
     if (!(t > tol)) continue;                                        // ray.py:424  |P - start| > distTol (and forward)
-    if (!(t < h.lim)) continue;                                      // ray.py:425,432,440
+    if (!(t < lim) || !(t < best)) continue;                         // ray.py:425,432,440
     double P[3] = { s[0]+t*dn[0], s[1]+t*dn[1], s[2]+t*dn[2] };
     if (!on_trimmed_face(f, segs, P, tol)) continue;                 // ray.py:426
-    if (t < h.tA) { h.tA = t; h.fA = idx; h.lim = fmin(h.lim, t + 2*tol); }
-    if (f.group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
+    best = t;
   }
+  return best;
 }
 
 __device__ __forceinline__ void accept_hit(double t, int idx, int group, int medium, double tol, NearestHit& h) {
@@ -83,7 +89,11 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
     if (f.group < 256 && ((p.ignore_mask[f.group >> 6] >> (f.group & 63)) & 1ull)) return;   // IgnoredOpticalElements
   }
   const double tol = p.tol;
-  if (!(f.flags & DFACE_FAST)) { test_face_general(f, idx, p.scene.segs, tol, s, dn, medium, tmax, h); return; }
+  if (!(f.flags & DFACE_FAST)) {
+    const double t = general_nearest(&f, p.scene.segs, tol, s[0], s[1], s[2], dn[0], dn[1], dn[2], h.lim);
+    if (t < 1e299) accept_hit(t, idx, f.group, medium, tol, h);
+    return;
+  }
   const double limit = h.lim;
   if (f.kind == ODW_SURF_PLANE) {
     const double den = dot3(dn, f.z);
@@ -91,7 +101,11 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
     if (t > tol && t < limit) {
       const double Px = fma(t, dn[0], s[0]), Py = fma(t, dn[1], s[1]), Pz = fma(t, dn[2], s[2]);
       const double u = dot3(Px, Py, Pz, f.x) - f.c1, v = dot3(Px, Py, Pz, f.y) - f.c2;
-      if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, tol, h);
+      if (f.flags & DFACE_DISC) {
+        // one full circle as the only trim loop (every lens flat): distance of P to the disc < tol  <=>  rho < r + tol
+        const double du = u - f.umin, dv = v - f.vmin, rr = f.umax + tol;
+        if (du*du + dv*dv < rr*rr) accept_hit(t, idx, f.group, medium, tol, h);
+      } else if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, tol, h);
     }
     return;
   }
@@ -231,18 +245,24 @@ __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long l
 }
 
 // Philox draw + tabulated inverse CDF + _makeRay: once per ray, kept out of line so the bounce loop stays small
-__device__ __noinline__ void init_ray_mc(const TraceParams& p, unsigned long long ray, double* point, double* dir) {
+struct RayInit { double o[3], d[3]; };
+__device__ __noinline__ RayInit init_ray_mc(const TraceParams& p, unsigned long long ray) {
   double u0, u1, first, phi;
+  RayInit r;
   philox_uniform2(p.seed, (uint32_t)p.src.source_id, ray, 0u, u0, u1);
   sample_source(p.src, u0, u1, first, phi);
-  make_ray(p.src, first, phi, point, dir);
+  make_ray(p.src, first, phi, r.o, r.d);
+  return r;
 }
 
 #ifndef ODW_MIN_BLOCKS
 #define ODW_MIN_BLOCKS 2
 #endif
+#ifndef ODW_THREADS
+#define ODW_THREADS 256          // threads per CTA of the trace kernel
+#endif
 template <bool MC, bool BVH>
-__global__ void __launch_bounds__(256, ODW_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
+__global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DShell* sshells = reinterpret_cast<DShell*>(smem_raw);
   DFace* sfaces = reinterpret_cast<DFace*>(smem_raw + (size_t)p.scene.n_shells*sizeof(DShell));
@@ -291,7 +311,9 @@ __global__ void __launch_bounds__(256, ODW_MIN_BLOCKS) trace_kernel(const __grid
       first_fetch = false;
       if (i < p.n_rays) {
         if (MC) {
-          init_ray_mc(p, p.first_ray + i, point, dir);
+          const RayInit r = init_ray_mc(p, p.first_ray + i);
+          point[0] = r.o[0]; point[1] = r.o[1]; point[2] = r.o[2];
+          dir[0] = r.d[0]; dir[1] = r.d[1]; dir[2] = r.d[2];
           power = 1.0;
         } else {
           const double* o = p.in_origins + 3*i; const double* d = p.in_dirs + 3*i;
@@ -364,14 +386,14 @@ __global__ void __launch_bounds__(256, ODW_MIN_BLOCKS) trace_kernel(const __grid
               if (g.gtype == ODW_GRATING_REFLECTION) {
                 if (entering) {
                   double n = medium >= 0 ? groups[medium].n : 1.0;
-                  line_grating(dn, n, n, nrm, g, p.wavelength, false, o);
-                  dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2]; ++seq_index;
+                  const Vec3 q = line_grating(dn[0], dn[1], dn[2], n, n, nrm[0], nrm[1], nrm[2], &g, p.wavelength, false);
+                  dir[0] = q.x; dir[1] = q.y; dir[2] = q.z; ++seq_index;
                 }
               } else if (entering) {
                 if (medium >= 0) { power = 0; break; }                           // the reference raises ValueError here
                 medium = fgroup;
-                line_grating(dn, 1.0, g.n, nrm, g, p.wavelength, true, o);
-                dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+                const Vec3 q = line_grating(dn[0], dn[1], dn[2], 1.0, g.n, nrm[0], nrm[1], nrm[2], &g, p.wavelength, true);
+                dir[0] = q.x; dir[1] = q.y; dir[2] = q.z;
               } else {
                 double n1 = medium >= 0 ? groups[medium].n : 1.0;
                 bool tir = snell(dn, n1, 1.0, nrm, o);
@@ -438,16 +460,16 @@ __global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long 
 
 extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int blocks, size_t smem, cudaStream_t st) {
   if (mc) {
-    if (bvh) trace_kernel<true, true><<<blocks, 256, 0, st>>>(*p);
+    if (bvh) trace_kernel<true, true><<<blocks, ODW_THREADS, 0, st>>>(*p);
     else {
       cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      trace_kernel<true, false><<<blocks, 256, smem, st>>>(*p);
+      trace_kernel<true, false><<<blocks, ODW_THREADS, smem, st>>>(*p);
     }
   } else {
-    if (bvh) trace_kernel<false, true><<<blocks, 256, 0, st>>>(*p);
+    if (bvh) trace_kernel<false, true><<<blocks, ODW_THREADS, 0, st>>>(*p);
     else {
       cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      trace_kernel<false, false><<<blocks, 256, smem, st>>>(*p);
+      trace_kernel<false, false><<<blocks, ODW_THREADS, smem, st>>>(*p);
     }
   }
   return cudaGetLastError();
@@ -460,13 +482,15 @@ extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long 
   return cudaGetLastError();
 }
 
+extern "C" int odw_trace_threads(void) { return ODW_THREADS; }
+
 extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem) {
   int nb = 0;
-  if (mc && bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, true>, 256, 0);
+  if (mc && bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, true>, ODW_THREADS, 0);
   else if (mc) { cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, 256, smem); }
-  else if (bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, true>, 256, 0);
+                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, ODW_THREADS, smem); }
+  else if (bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, true>, ODW_THREADS, 0);
   else { cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, 256, smem); }
+         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, ODW_THREADS, smem); }
   return nb;
 }
