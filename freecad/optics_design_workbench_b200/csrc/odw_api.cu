@@ -75,6 +75,10 @@ struct odw_scene {
   size_t smem = 0;
   int n_groups = 0;
   double extent = 0;                    // max |coordinate| over all face boxes
+  std::vector<BvhNode2> bvh_host;       // un-widened device nodes (boxes rounded outward)
+  std::vector<BvhNode2> bvh_staging;    // widened copy being uploaded
+  BvhNode2* bvh_dev = nullptr;
+  float bvh_margin = -1.0f;             // margin the device copy currently carries
 };
 
 struct odw_source {
@@ -192,10 +196,37 @@ struct BvhBuilder {
   void build() {
     nodes.reserve(2*boxes.size() + 2);
     nodes.push_back(BvhNode{});
-    recurse(0, 0, (int)prims.size());
+    recurse(0, 0, (int)prims.size(), 0);
   }
 
-  void recurse(int node, int first, int count) {
+  // Inner nodes in device layout: both child boxes in the parent (see BvhNode2).
+  std::vector<BvhNode2> wide() const {
+    std::vector<int> index(nodes.size(), -1);
+    int n_inner = 0;
+    for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].count == 0) index[i] = n_inner++;
+    std::vector<BvhNode2> out((size_t)std::max(n_inner, 1));
+    auto set_child = [&](BvhNode2& w, int k, const BvhNode* c) {
+      float* lo = k ? w.lo1 : w.lo0; float* hi = k ? w.hi1 : w.hi0;
+      if (!c) { for (int a = 0; a < 3; ++a) { lo[a] = 3.0e38f; hi[a] = 3.0e38f; } w.child[k] = 0; w.count[k] = -1; return; }
+      for (int a = 0; a < 3; ++a) { lo[a] = c->lo[a]; hi[a] = c->hi[a]; }
+      if (c->count == 0) { w.child[k] = index[(size_t)(c - nodes.data())]; w.count[k] = 0; }
+      else { w.child[k] = c->left; w.count[k] = c->count; }
+    };
+    if (n_inner == 0) {                     // the root is a leaf (or the scene is empty)
+      set_child(out[0], 0, prims.empty() ? nullptr : &nodes[0]);
+      set_child(out[0], 1, nullptr);
+      return out;
+    }
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      if (nodes[i].count != 0) continue;
+      BvhNode2& w = out[(size_t)index[i]];
+      set_child(w, 0, &nodes[(size_t)nodes[i].left]);
+      set_child(w, 1, &nodes[(size_t)nodes[i].left + 1]);
+    }
+    return out;
+  }
+
+  void recurse(int node, int first, int count, int depth) {
     Box bb; bb.reset(); Box cb; cb.reset();
     for (int i = first; i < first + count; ++i) {
       const Box& b = boxes[prims[i]]; bb.grow(b);
@@ -204,7 +235,7 @@ struct BvhBuilder {
     set_box(nodes[node], bb);
     const int LEAF = 2, NB = 16;
     int best_axis = -1, best_split = -1; double best_cost = 1e300;
-    if (count > LEAF) {
+    if (count > LEAF && depth < 24) {      // deeper than 24: median splits only, so the depth stays below 24 + log2(n) < ODW_BVH_STACK
       for (int a = 0; a < 3; ++a) {
         double ext = cb.hi[a] - cb.lo[a];
         if (ext <= 0) continue;
@@ -227,12 +258,12 @@ struct BvhBuilder {
       }
     }
     if (best_axis < 0) {
-      if (count <= 8) { nodes[node].left = first; nodes[node].count = count; return; }
-      // degenerate (all centroids equal): split in the middle
+      if (count <= (depth < 24 ? 8 : LEAF)) { nodes[node].left = first; nodes[node].count = count; return; }
+      // degenerate (all centroids equal) or too deep: split in the middle
       int mid = first + count/2;
       int l = (int)nodes.size(); nodes.push_back(BvhNode{}); nodes.push_back(BvhNode{});
       nodes[node].left = l; nodes[node].count = 0;
-      recurse(l, first, mid - first); recurse(l + 1, mid, first + count - mid);
+      recurse(l, first, mid - first, depth + 1); recurse(l + 1, mid, first + count - mid, depth + 1);
       return;
     }
     double ext = cb.hi[best_axis] - cb.lo[best_axis];
@@ -244,7 +275,7 @@ struct BvhBuilder {
     int mid = (int)(mid_it - prims.begin());
     int l = (int)nodes.size(); nodes.push_back(BvhNode{}); nodes.push_back(BvhNode{});
     nodes[node].left = l; nodes[node].count = 0;
-    recurse(l, first, mid - first); recurse(l + 1, mid, first + count - mid);
+    recurse(l, first, mid - first, depth + 1); recurse(l + 1, mid, first + count - mid, depth + 1);
   }
 };
 }  // namespace
@@ -351,9 +382,12 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   if (sc->use_bvh) {
     BvhBuilder b(boxes);
     b.build();
-    if ((rc = upload(eng, sc->owned, b.nodes.data(), b.nodes.size(), &sc->d.bvh))) { odw_scene_destroy(sc); return rc; }
+    sc->bvh_host = b.wide();
+    const BvhNode2* dev = nullptr;
+    if ((rc = upload(eng, sc->owned, sc->bvh_host.data(), sc->bvh_host.size(), &dev))) { odw_scene_destroy(sc); return rc; }
+    sc->bvh_dev = const_cast<BvhNode2*>(dev); sc->d.bvh = dev; sc->bvh_margin = 0.0f;
     if ((rc = upload(eng, sc->owned, b.prims.data(), b.prims.size(), &sc->d.bvh_prims))) { odw_scene_destroy(sc); return rc; }
-    sc->d.n_bvh_nodes = (int)b.nodes.size();
+    sc->d.n_bvh_nodes = (int)sc->bvh_host.size();
     sc->smem = 0;
   } else {
     sc->smem = std::max<size_t>(16, faces.size()*sizeof(DFace) + shells.size()*sizeof(DShell));
@@ -510,6 +544,22 @@ static void set_cull_margin(TraceParams& p, const odw_scene* sc, double origin_b
   p.origin_bound = (float)origin_bound;
 }
 
+// The BVH boxes on the device carry the culling margin of the launch; re-widen them when it changes (tolerance,
+// ray length or source changed).  Stream-ordered: earlier launches on the engine stream finish before the copy runs.
+static int ensure_bvh_margin(odw_scene* sc, float margin) {
+  if (!sc->use_bvh || sc->bvh_margin == margin) return ODW_OK;
+  sc->bvh_staging = sc->bvh_host;
+  for (BvhNode2& w : sc->bvh_staging)
+    for (int a = 0; a < 3; ++a) {
+      if (w.count[0] >= 0) { w.lo0[a] = std::nextafter(w.lo0[a] - margin, -INFINITY); w.hi0[a] = std::nextafter(w.hi0[a] + margin, INFINITY); }
+      if (w.count[1] >= 0) { w.lo1[a] = std::nextafter(w.lo1[a] - margin, -INFINITY); w.hi1[a] = std::nextafter(w.hi1[a] + margin, INFINITY); }
+    }
+  CU(cudaMemcpyAsync(sc->bvh_dev, sc->bvh_staging.data(), sc->bvh_staging.size()*sizeof(BvhNode2), cudaMemcpyHostToDevice, sc->eng->stream));
+  CU(cudaStreamSynchronize(sc->eng->stream));      // the staging vector is pageable and reused
+  sc->bvh_margin = margin;
+  return ODW_OK;
+}
+
 static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
   for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
 }
@@ -581,6 +631,7 @@ extern "C" int odw_trace_mc(odw_scene* sc, odw_source* src, const odw_trace_cfg*
   p.wavelength = src->d.wavelength;
   set_ignore(p, src->ignored.data(), (int)src->ignored.size());
   set_cull_margin(p, sc, src->origin_bound);
+  if ((rc = ensure_bvh_margin(sc, p.cull_margin))) { odw_result_destroy(*out); *out = nullptr; return rc; }
   rc = run_trace(eng, sc, *out, p, true);
   if (rc && rc != ODW_EOVERFLOW) { odw_result_destroy(*out); *out = nullptr; }
   return rc;
@@ -615,6 +666,7 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
     p[b].wavelength = src->d.wavelength;
     set_ignore(p[b], src->ignored.data(), (int)src->ignored.size());
     set_cull_margin(p[b], sc, src->origin_bound);
+    if ((rc = ensure_bvh_margin(sc, p[b].cull_margin))) { cleanup(); return rc; }
   }
   const uint64_t n_chunks = (n_rays + chunk - 1)/chunk;
   odw_counts total; memset(&total, 0, sizeof total);
@@ -724,6 +776,7 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   for (uint64_t i = 0; i < 3*n_rays; ++i) origin_bound = std::max(origin_bound, std::fabs(origins[i]));
   if (!std::isfinite(origin_bound)) return bail(fail(ODW_EINVAL, "odw_trace_rays: non-finite ray origin"));
   set_cull_margin(p, sc, origin_bound);
+  if ((rc = ensure_bvh_margin(sc, p.cull_margin))) return bail(rc);
   rc = run_trace(eng, sc, r, p, false);
   if (rc && rc != ODW_EOVERFLOW) return bail(rc);
   return rc;

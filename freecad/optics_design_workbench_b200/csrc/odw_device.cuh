@@ -48,10 +48,19 @@ struct DBinning {
   unsigned long long offset;                         // into the concatenated bins array
 };
 
-struct BvhNode {                   // 32 B: one 256-bit load fetches a node
+struct BvhNode {                   // builder node (host only)
   float lo[3], hi[3];
   int32_t left;                    // inner: index of left child (right = left+1); leaf: first primitive
   int32_t count;                   // 0 = inner node, >0 = number of primitives in the leaf
+};
+
+// Device node: an inner node carries the fp32 boxes of BOTH children (64 B = four 128-bit loads), so one fetch
+// decides both children and their near/far order.  child: inner -> node index, leaf -> first entry of bvh_prims;
+// count: 0 = inner, > 0 = leaf size, < 0 = no child.  Boxes are stored rounded outward and already widened by the
+// launch's culling margin (odw_api.cu ensure_bvh_margin).
+struct BvhNode2 {
+  float lo0[3], hi0[3], lo1[3], hi1[3];
+  int32_t child[2], count[2];
 };
 
 struct DScene {
@@ -59,7 +68,7 @@ struct DScene {
   const DShell* shells;
   const odw_trimseg* segs;
   const DGroup* groups;
-  const BvhNode* bvh;              // nullptr: shells + faces staged in shared memory
+  const BvhNode2* bvh;             // nullptr: shells + faces staged in shared memory
   const int32_t* bvh_prims;        // face indices in leaf order
   int32_t n_faces, n_shells, n_segs, n_groups, n_seq_steps, n_bvh_nodes;
 };

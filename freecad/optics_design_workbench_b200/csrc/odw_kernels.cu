@@ -8,7 +8,7 @@
 // no divergence between lanes of a warp); large scenes walk a BVH with a per-thread short stack.
 #include <cooperative_groups.h>
 #ifndef ODW_BLOCK_SYNC
-#define ODW_BLOCK_SYNC 1
+#define ODW_BLOCK_SYNC 0        // 1: re-converge the whole CTA once per bounce (measured slower since the fp32 culls shrank the loop)
 #endif
 #define ODW_DEVICE_CODE
 #include "odw_device.cuh"
@@ -173,37 +173,72 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
   t_out = h.tA; return h.fA;
 }
 
-// same rule, faces reached through a BVH over face boxes (replaces the shell/face BoundBox culls of ray.py:345-404)
+// same rule, faces reached through a BVH over face boxes (replaces the shell/face BoundBox culls of ray.py:345-404).
+// Conservative fp32 slab tests on boxes widened by the culling margin; near child first, the far child is pushed with
+// its entry distance and dropped at pop time if a closer hit has been accepted meanwhile.
+#define ODW_BVH_STACK 64
 __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const double* s, const double* dn,
                                                 int medium, int seq_index, double max_len, double& t_out) {
   const double tol = p.tol;
-  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = max_len + tol; h.fA = -1; h.fB = -1;
-  const BvhNode* __restrict__ nodes = p.scene.bvh;
-  double inv[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) inv[i] = 1.0/dn[i];
-  int stack[48]; int sp = 0;
-  stack[sp++] = 0;
-  while (sp > 0) {
-    int ni = stack[--sp];
-    // one 32-byte node = two 128-bit loads
-    const float4* np4 = reinterpret_cast<const float4*>(nodes + ni);
-    float4 a = __ldg(np4), b = __ldg(np4 + 1);
-    double lo[3] = { a.x, a.y, a.z }, hi[3] = { a.w, b.x, b.y };
-    int left = __float_as_int(b.z), count = __float_as_int(b.w);
-    double t0 = -tol, t1 = fmin(max_len + tol, h.tA + 2*tol);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double ta = (lo[i] - tol - s[i])*inv[i], tb = (hi[i] + tol - s[i])*inv[i];
-      t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+  const double tmax = max_len + tol;
+  NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = tmax; h.fA = -1; h.fB = -1;
+  const BvhNode2* __restrict__ nodes = p.scene.bvh;
+  const float sx = (float)s[0], sy = (float)s[1], sz = (float)s[2];
+  const float ix = __frcp_rn((float)dn[0]), iy = __frcp_rn((float)dn[1]), iz = __frcp_rn((float)dn[2]);
+  float limf = (float)tmax*1.000002f;
+  int stack_node[ODW_BVH_STACK]; float stack_t[ODW_BVH_STACK]; int sp = 0;
+  int node = 0;
+  for (;;) {
+    const float4* q = reinterpret_cast<const float4*>(nodes + node);
+    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const int4 d = __ldg(reinterpret_cast<const int4*>(q + 3));
+    // child 0: lo = (a.x, a.y, a.z), hi = (a.w, b.x, b.y);  child 1: lo = (b.z, b.w, c.x), hi = (c.y, c.z, c.w)
+    float ta = (a.x - sx)*ix, tb = (a.w - sx)*ix;
+    float n0 = fminf(ta, tb), f0 = fmaxf(ta, tb);
+    ta = (a.y - sy)*iy; tb = (b.x - sy)*iy;
+    n0 = fmaxf(n0, fminf(ta, tb)); f0 = fminf(f0, fmaxf(ta, tb));
+    ta = (a.z - sz)*iz; tb = (b.y - sz)*iz;
+    n0 = fmaxf(n0, fminf(ta, tb)); f0 = fminf(f0, fmaxf(ta, tb));
+    ta = (b.z - sx)*ix; tb = (c.y - sx)*ix;
+    float n1 = fminf(ta, tb), f1 = fmaxf(ta, tb);
+    ta = (b.w - sy)*iy; tb = (c.z - sy)*iy;
+    n1 = fmaxf(n1, fminf(ta, tb)); f1 = fminf(f1, fmaxf(ta, tb));
+    ta = (c.x - sz)*iz; tb = (c.w - sz)*iz;
+    n1 = fmaxf(n1, fminf(ta, tb)); f1 = fminf(f1, fmaxf(ta, tb));
+    bool hit0 = d.z >= 0 && n0 <= f0 && f0 >= 0.0f && n0 <= limf;
+    bool hit1 = d.w >= 0 && n1 <= f1 && f1 >= 0.0f && n1 <= limf;
+    if (hit0 && d.z > 0) {                                             // leaf: exact fp64 tests
+      for (int k = 0; k < d.z; ++k) {
+        const int fi = __ldg(p.scene.bvh_prims + d.x + k);
+        test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
+      }
+      limf = (float)h.lim*1.000002f;
+      hit0 = false;
+      hit1 = hit1 && n1 <= limf;
     }
-    if (t0 > t1) continue;
-    if (count == 0) {
-      if (sp < 46) { stack[sp++] = left; stack[sp++] = left + 1; }
-    } else {
-      for (int k = 0; k < count; ++k)
-        { int fi = __ldg(p.scene.bvh_prims + left + k); test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, max_len + tol, h); }
+    if (hit1 && d.w > 0) {
+      for (int k = 0; k < d.w; ++k) {
+        const int fi = __ldg(p.scene.bvh_prims + d.y + k);
+        test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
+      }
+      limf = (float)h.lim*1.000002f;
+      hit1 = false;
+      hit0 = hit0 && n0 <= limf;
     }
+    if (hit0 && hit1) {
+      const bool first0 = n0 <= n1;
+      if (sp < ODW_BVH_STACK) { stack_node[sp] = first0 ? d.y : d.x; stack_t[sp] = first0 ? n1 : n0; ++sp; }
+      node = first0 ? d.x : d.y;
+      continue;
+    }
+    if (hit0) { node = d.x; continue; }
+    if (hit1) { node = d.y; continue; }
+    bool found = false;
+    while (sp > 0) {
+      --sp;
+      if (stack_t[sp] <= limf) { node = stack_node[sp]; found = true; break; }
+    }
+    if (!found) break;
   }
   if (h.fA < 0) return -1;
   if (h.fB >= 0 && h.tB < h.tA + 2*tol) { t_out = h.tB; return h.fB; }
@@ -256,7 +291,7 @@ __device__ __noinline__ RayInit init_ray_mc(const TraceParams& p, unsigned long 
 }
 
 #ifndef ODW_MIN_BLOCKS
-#define ODW_MIN_BLOCKS 2
+#define ODW_MIN_BLOCKS 3          // 3 CTAs x 8 warps per SM (80 registers): the kernel is latency-bound, 24 warps beat 16 despite spills
 #endif
 #ifndef ODW_THREADS
 #define ODW_THREADS 256          // threads per CTA of the trace kernel
