@@ -1,0 +1,135 @@
+'''
+The call site the engine replaces: GenericSourceProxy.runSimulationIteration
+(reference freecad_elements/generic_source.py:51-146).
+
+The reference generates N ray objects, walks each through Ray.traceRay and hands every hit to
+obj.Proxy.onRayHit -> store.addRayHit.  Here one engine call traces the whole batch on the GPU and the
+hits come back as arrays, grouped per optical group and appended to the store in one go
+(optical_group.py:206-209 -> results_store.py:641-648 semantics: only groups with RecordHits).
+
+Same name, same keyword arguments, same side effects on `store` (hits, totalTracedRays).  `draw=True`
+(GUI ray drawing through Part.makeLine, :102-138) has no meaning without FreeCAD and raises.
+'''
+
+import numpy as np
+
+from . import point_source
+from ..simulation import results_store
+
+
+class GenericSourceProxy:
+  '''
+  One instance per light source, bound to a SimulationContext (simulation/simulation_loop.py), which plays
+  the role of the reference's module-level singletons (simulatingDocument(), find.activeSimulationSettings()).
+  '''
+  def __init__(self, context, source_index):
+    self.context = context
+    self.index = source_index
+
+  @property
+  def record(self):
+    return self.context.sim.source_records[self.index]
+
+  # -- ray generation (PointSourceProxy._generateRays) --------------------------------------------
+  def _generateRays(self, obj, mode, **kwargs):
+    if mode == 'fans':
+      return point_source.generate_fan_rays(obj, obj['gpM'], max_fan_count=kwargs.get('maxFanCount', np.inf),
+                                            max_rays_per_fan=kwargs.get('maxRaysPerFan', np.inf))
+    raise ValueError(f'unexpected ray placement mode {mode} for host-side ray generation')
+
+  # -- the iteration --------------------------------------------------------------------------------
+  def runSimulationIteration(self, obj=None, *, mode, draw=False, store=False, returnInitialConditions=False,
+                             useInitialConditions=None, iterations=1, **kwargs):
+    '''
+    mode 'true'  : `iterations` Monte-Carlo iterations of RaysPerIteration*RaysPerIterationScale rays each in ONE
+                   engine call (odw_trace_mc), drawn on the device from the Philox stream (seed, source id) at
+                   the context's next free global ray indices; in a multi-GPU run this rank traces its shard.
+    mode 'fans'  : the deterministic fan list (or `useInitialConditions`, a RayBatch) through odw_trace_rays.
+    Returns the engine counters of this call (the reference returns None), or the RayBatch if
+    returnInitialConditions.
+    '''
+    ctx = self.context
+    obj = obj if obj is not None else self.record
+    if draw:
+      raise NotImplementedError('draw=True builds FreeCAD Part objects; keep the reference path for displayed rays')
+    if obj.get('proxy', 'PointSourceProxy') != 'PointSourceProxy':
+      raise NotImplementedError(f"light source kind {obj.get('proxy')} is not handled by the engine yet")
+    if mode in ('pseudo', 'singlepseudo'):
+      raise NotImplementedError("pseudo-random mode (drawPseudo) is not implemented on the engine yet")
+
+    if useInitialConditions is not None or mode in ('fans', 'multicorefans'):
+      batch = useInitialConditions if useInitialConditions is not None else self._generateRays(obj, mode='fans', **kwargs)
+      if returnInitialConditions:
+        return batch
+      return self._trace_explicit(obj, batch, store)
+    if mode not in ('true', 'singletrue'):
+      raise ValueError(f'unexpected ray placement mode {mode}')
+    if returnInitialConditions:
+      raise NotImplementedError('Monte-Carlo rays are drawn on the device; use DeviceSource.sample for their initial conditions')
+    return self._trace_monte_carlo(obj, int(iterations), store)
+
+  # -- engine calls -----------------------------------------------------------------------------------
+  def _store_hits(self, obj, hits, store, metadata_of):
+    'append the hit arrays to the store, one entry per optical group (file per (source, object))'
+    scene = self.context.sim.scene
+    group = hits['group']
+    keys = self.context.sim.settings.get('store_hit_keys', [])
+    for gi in np.unique(group):
+      sel = np.nonzero(group == gi)[0]
+      md = metadata_of(hits['ray_index'][sel], keys) if keys else {}
+      store.addRayHits(results_store.named((obj['name'], obj['label'])),
+                       results_store.named((scene.group_names[gi], scene.group_labels[gi])),
+                       hits['points'][sel], hits['directions'][sel], hits['powers'][sel], hits['is_entering'][sel], md)
+
+  def _trace_explicit(self, obj, batch, store):
+    ctx = self.context
+    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])))
+    with ctx.device_scene.trace_rays(cfg, batch.origins, batch.directions, batch.powers, ignored=obj.get('ignored', ())) as res:
+      counts = res.counts
+      hits = res.hits(sort=True) if store else None
+    if store:
+      def metadata_of(ray_index, keys):
+        idx = ray_index.astype(np.int64)
+        md = {}
+        for k in keys:
+          name = k[0].lower()+k[1:]                       # StoreHitInitPoint -> initPoint
+          if name == 'initPoint': md[name] = batch.origins[idx]
+          elif name == 'initDirection': md[name] = batch.directions[idx]
+          elif name == 'initPower': md[name] = batch.powers[idx]
+          elif name == 'initWavelength': md[name] = np.full(len(idx), batch.wavelength)
+          elif name in batch.metadata: md[name] = batch.metadata[name][idx]
+        return md
+      self._store_hits(obj, hits, store, metadata_of)
+      store.incrementRayCount(len(batch))
+    return counts
+
+  def _trace_monte_carlo(self, obj, iterations, store):
+    ctx = self.context
+    n_iter_rays = point_source.rays_per_iteration(obj, ctx.sim.settings)
+    n_total = n_iter_rays*iterations
+    first, n = ctx.claim_rays(self.index, n_total)        # this rank's shard of the next n_total global ray indices
+    dsrc = ctx.device_source(self.index)
+    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, 2*n))
+    with ctx.device_scene.trace_mc(dsrc, cfg, ctx.seed, first, n) as res:
+      counts = res.counts
+      hits = res.hits(sort=True) if store else None
+      if res.overflow:
+        raise RuntimeError(f'hit buffer overflow: {counts}')
+    if store:
+      def metadata_of(ray_index, keys):
+        s = dsrc.sample(ctx.seed, first, n)               # same Philox stream -> the rays' initial conditions
+        idx = (ray_index-np.uint64(first)).astype(np.int64)
+        finite = np.isfinite(float(obj['FocalLength']))
+        md = {}
+        for k in keys:
+          name = k[0].lower()+k[1:]
+          if name == 'initPoint': md[name] = s['origins'][idx]
+          elif name == 'initDirection': md[name] = s['directions'][idx]
+          elif name == 'initPower': md[name] = np.ones(len(idx))
+          elif name == 'initWavelength': md[name] = np.full(len(idx), float(obj['Wavelength']))
+          elif name == 'initPhi': md[name] = s['phi'][idx]
+          elif name == 'initTheta': md[name] = s['first'][idx] if finite else np.full(len(idx), np.nan)
+        return md
+      self._store_hits(obj, hits, store, metadata_of)
+      store.incrementRayCount(n)
+    return counts

@@ -1,0 +1,74 @@
+'''
+TEST DOUBLE: an object with the surface of engine.Engine whose tracing is done by the CPU oracle.
+It lets the host-side logic (runSimulationIteration, the hit writer, the sharded simulation loop) run in
+the `not gpu` suite.  The product never imports this; product code gets the CUDA engine.
+'''
+import numpy as np
+
+from oracle import Oracle
+
+
+class _Result:
+  def __init__(self, r):
+    self._r = r
+    self.overflow = False
+    self.kernel_ms = 0.0
+
+  def __enter__(self):
+    return self
+
+  def __exit__(self, *a):
+    pass
+
+  def close(self):
+    pass
+
+  @property
+  def counts(self):
+    return self._r['counts']
+
+  def hits(self, sort=True, into=None):
+    return self._r['hits']
+
+  def histogram(self, index=0):
+    return self._r['histograms'][index]
+
+
+class _Scene:
+  def __init__(self, orc, scene):
+    self.orc, self.scene = orc, scene
+
+  def trace_mc(self, source, cfg, seed, first_ray, n_rays):
+    return _Result(self.orc.trace_mc(self.scene, source.args, cfg, seed, first_ray, n_rays,
+                                     hit_capacity=max(16, int(cfg.cfg.hit_capacity) or 4*n_rays), threads=0))
+
+  def trace_rays(self, cfg, origins, directions, powers=None, ignored=()):
+    return _Result(self.orc.trace_rays(self.scene, cfg, origins, directions, powers, ignored=ignored, threads=0))
+
+  def close(self):
+    pass
+
+
+class _Source:
+  def __init__(self, orc, args):
+    self.orc, self.args = orc, args
+
+  def sample(self, seed, first_ray, n):
+    return self.orc.sample_mc(self.args, seed, first_ray, n)
+
+  def close(self):
+    pass
+
+
+class OracleEngine:
+  def __init__(self):
+    self.orc = Oracle()
+
+  def scene(self, scene):
+    return _Scene(self.orc, scene)
+
+  def source(self, source_args):
+    return _Source(self.orc, source_args)
+
+  def close(self):
+    pass

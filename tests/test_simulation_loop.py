@@ -1,0 +1,157 @@
+'''
+Host logic around the engine on the CPU: runSimulation / runSimulationIteration / the hit writer, with the
+oracle-backed test double standing in for the GPU engine (tests/oracle_engine.py).  The assertions follow the
+reference's own integration tests where they exist (test/21-simulation-modes/run-simulations.py:42-64: a run
+ends on EndAfterHits=1e3 with > 999 hits, on EndAfterRays=1e3 with > 100 hits).
+'''
+import glob
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from freecad.optics_design_workbench_b200.simulation import simulation_loop, results_store
+from freecad.optics_design_workbench_b200.simulation.setup import prepare
+
+from conftest import SCENES
+from oracle_engine import OracleEngine
+
+
+def load_hits(run_folder, pattern='**'):
+  'what RawFolder._load does (reference jupyter_utils/freecad_document.py:1491-1504), restated with numpy only'
+  result = {}
+  for path in sorted(glob.glob(f'{run_folder}/{pattern}/*-hits.pkl', recursive=True)):
+    with open(path, 'rb') as f:
+      data = pickle.load(f)
+    for k, v in data.items():
+      if k not in result:
+        result[k] = v
+      elif isinstance(v, str):
+        if isinstance(result[k], str) and result[k] != v:
+          result[k] = [result[k], v]
+        elif not isinstance(result[k], str) and v not in result[k]:
+          result[k] = list(result[k])+[v]
+      else:
+        result[k] = np.concatenate([result[k], v], axis=0)
+  return result
+
+
+@pytest.fixture()
+def engine():
+  return OracleEngine()
+
+
+def test_run_ends_after_rays_like_reference_test_21(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'minimal.npz'))
+  run = simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=str(tmp_path/'minimal.OpticsDesign'),
+                                      settings=dict(EndAfterRays=1e3), maxBatchRays=300)
+  hits = load_hits(run)
+  assert len(hits['points']) > 100                     # reference assertion
+  # a single reference worker stops at the first ray count strictly above the limit: 11 iterations of 100 rays
+  assert len(hits['points']) == 1100
+  assert hits['points'].shape == (1100, 3) and hits['directions'].shape == (1100, 3)
+  assert hits['powers'].dtype == np.float64 and hits['isEntering'].dtype.kind == 'i'
+  assert hits['source'] == 'OpticalPointSource' and hits['obj'] == 'OpticalAbsorberGroup'
+  np.testing.assert_allclose(hits['points'][:, 2], 15.0, atol=1e-9)      # entry face of the absorber box
+  assert np.all(hits['isEntering'] == 1) and np.all(hits['powers'] == 1.0)
+
+
+def test_run_ends_after_hits_like_reference_test_21(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  run = simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=str(tmp_path/'x.OpticsDesign'),
+                                      settings=dict(EndAfterHits=1e3, EndAfterRays=np.inf), maxBatchRays=400)
+  hits = load_hits(run)
+  assert len(hits['points']) > 999
+
+
+def test_result_tree_layout(tmp_path, engine):
+  base = str(tmp_path/'lensesAndMirrors.OpticsDesign')
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  run = simulation_loop.runSimulation(sim, 'singletrue', engine=engine, basePath=base)
+  assert run == f'{base}/raw/simulation-run-000000'
+  assert os.path.isdir(f'{base}/notebooks') and os.path.isfile(f'{base}/README.md')
+  uid = [f for f in os.listdir(run) if f.startswith('uid-')]
+  assert len(uid) == 1 and re.fullmatch(r'uid-[0-9a-f-]{36}', uid[0])       # RawFolder requires exactly one
+  with open(f'{run}/global-info.pkl', 'rb') as f:
+    info = pickle.load(f)
+  assert set(info) == {'activeSimulationSettings', 'lightSources', 'opticalObjects'}
+  assert info['lightSources'][0]['placementPathsAndMatrices'][0]['gpM'].shape == (4, 4)
+  files = glob.glob(f'{run}/source-*/object-*/*-hits.pkl')
+  assert files, os.listdir(run)
+  for p in files:
+    rel = os.path.relpath(p, run).split(os.sep)
+    assert rel[0] == 'source-'+sim.source_records[0]['label'] and rel[1].startswith('object-')   # Labels, not Names
+    assert re.fullmatch(r'\d+-pid\d+-thread\d+-hits\.pkl', rel[2])
+    d = pickle.load(open(p, 'rb'))
+    assert list(d)[:6] == ['source', 'obj', 'points', 'directions', 'powers', 'isEntering']
+    assert d['source'] == sim.source_records[0]['name'] and d['obj'] in sim.scene.group_names        # Names inside the file
+  assert not os.path.exists(f'{run}/progress')         # removed by cleanup like the reference
+  # a second run gets the next index
+  run2 = simulation_loop.runSimulation(sim, 'singletrue', engine=engine, basePath=base)
+  assert run2.endswith('simulation-run-000001')
+
+
+def test_fans_mode_with_store_hit_metadata(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  sim.settings['store_hit_keys'] = ['InitPoint', 'InitDirection', 'InitPower', 'InitWavelength', 'InitPhi', 'InitTheta',
+                                    'RayIndex', 'FanIndex', 'TotalFanCount', 'TotalRaysInFan']
+  run = simulation_loop.runSimulation(sim, 'fans', engine=engine, basePath=str(tmp_path/'f.OpticsDesign'))
+  hits = load_hits(run)
+  n = len(hits['powers'])
+  assert n == 40                                       # 2 fans x 20 rays, every ray ends on the absorber
+  for k in results_store.HIT_METADATA_KEYS:
+    assert k in hits and len(hits[k]) == n, k
+  assert hits['initPoint'].shape == (n, 3) and hits['initDirection'].shape == (n, 3)
+  assert set(hits['fanIndex']) == {0, 1} and np.all(hits['totalFanCount'] == 2) and np.all(hits['totalRaysInFan'] == 20)
+  assert sorted(hits['rayIndex'][hits['fanIndex'] == 0]) == list(range(-9, 11)) or sorted(hits['rayIndex'][hits['fanIndex'] == 0]) == list(range(-10, 10))
+  np.testing.assert_allclose(hits['initWavelength'], 500.0)
+
+
+def test_monte_carlo_metadata_comes_from_the_same_philox_stream(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'minimal.npz'))
+  sim.settings['store_hit_keys'] = ['InitTheta', 'InitPhi', 'InitDirection']
+  run = simulation_loop.runSimulation(sim, 'singletrue', engine=engine, basePath=str(tmp_path/'m.OpticsDesign'))
+  hits = load_hits(run)
+  # minimal scene known answer: hit = (15 tan(theta) sin(phi), -15 tan(theta) cos(phi), 15)
+  th, ph = hits['initTheta'], hits['initPhi']
+  want = np.stack([15*np.tan(th)*np.sin(ph), -15*np.tan(th)*np.cos(ph), np.full(len(th), 15.0)], axis=1)
+  np.testing.assert_allclose(hits['points'], want, atol=1e-9)
+  np.testing.assert_allclose(hits['directions'], hits['initDirection'], atol=1e-12)
+
+
+def test_progress_files_and_master_summary(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'minimal.npz'))
+  run = simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=str(tmp_path/'p.OpticsDesign'),
+                                      settings=dict(EndAfterRays=500), maxBatchRays=200, keepProgressFiles=True)
+  masters = sorted(glob.glob(f'{run}/progress/master-*'))
+  assert masters
+  last = pickle.load(open(masters[-1], 'rb'))
+  assert set(last) == {'simulationType', 'totalIterations', 'totalTracedRays', 'totalRecordedHits', 'totalRecordedRays',
+                       'endAfterIterations', 'endAfterRays', 'endAfterHits'}
+  assert last['totalTracedRays'] == 600 and last['totalIterations'] == 6 and last['endAfterRays'] == 500
+
+
+def test_writer_pads_missing_metadata_with_nan(tmp_path):
+  st = results_store.SimulationResults('true', str(tmp_path/'w.OpticsDesign'))
+  src, obj = ('S', 'S label'), ('G', 'G label')
+  st.addRayHits(src, obj, np.zeros((2, 3)), np.ones((2, 3)), [1, 1], [1, 0], dict(initTheta=[0.1, 0.2]))
+  st.addRayHits(src, obj, np.zeros((1, 3)), np.ones((1, 3)), [0.5], [1])
+  st.flush()
+  d = pickle.load(open(st.writtenFiles[0], 'rb'))
+  assert 'source-S label/object-G label' in st.writtenFiles[0]
+  assert d['source'] == 'S' and d['obj'] == 'G' and len(d['powers']) == 3
+  assert np.isnan(d['initTheta'][2]) and d['initTheta'][0] == 0.1
+  assert st.totalRecordedHits == 3
+
+
+def test_unknown_action_and_missing_end_criterion(tmp_path, engine):
+  sim = prepare(os.path.join(SCENES, 'minimal.npz'))
+  with pytest.raises(ValueError):
+    simulation_loop.runSimulation(sim, 'stop', engine=engine, basePath=str(tmp_path/'a'))
+  with pytest.raises(ValueError):
+    simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=str(tmp_path/'b'),
+                                  settings=dict(EndAfterRays=np.inf, EndAfterHits=np.inf, EndAfterIterations=np.inf))
+  with pytest.raises(NotImplementedError):
+    simulation_loop.runSimulation(sim, 'pseudo', engine=engine, basePath=str(tmp_path/'c'), settings=dict(EndAfterRays=10))
