@@ -155,3 +155,31 @@ def test_unknown_action_and_missing_end_criterion(tmp_path, engine):
                                   settings=dict(EndAfterRays=np.inf, EndAfterHits=np.inf, EndAfterIterations=np.inf))
   with pytest.raises(NotImplementedError):
     simulation_loop.runSimulation(sim, 'pseudo', engine=engine, basePath=str(tmp_path/'c'), settings=dict(EndAfterRays=10))
+
+
+@pytest.mark.reference
+def test_engine_bridge_with_reference_side_objects(tmp_path, engine):
+  '''
+  The stub of INTEGRATION.md: FreeCAD-side objects (here stand-ins with the attributes the bridge reads) drive the
+  engine from the saved benchmark project, and the hits land in the reference store's run folder.
+  '''
+  import shutil
+  import types
+  from freecad.optics_design_workbench_b200 import engine_bridge
+  fcstd = str(tmp_path/'minimal.FCStd')
+  shutil.copy('/root/reference/benchmark/minimal.FCStd', fcstd)
+  engine_bridge.set_engine_factory(lambda: engine)
+  try:
+    assert engine_bridge.available()
+    obj = types.SimpleNamespace(Name='OpticalPointSource', Document=types.SimpleNamespace(FileName=fcstd))
+    base = results_store.results_folder_path(fcstd)
+    ref_store = types.SimpleNamespace(basePath=base, simulationRunFolder='raw/simulation-run-000000', simulationType='true',
+                                      totalTracedRays=0, totalRecordedHits=0, flushEverySeconds=5)
+    for _ in range(3):
+      engine_bridge.run_iteration(None, obj, mode='true', store=ref_store)
+    engine_bridge.flush(ref_store)
+    assert ref_store.totalTracedRays == 300 and ref_store.totalRecordedHits == 300
+    hits = load_hits(f'{base}/raw/simulation-run-000000')
+    assert len(hits['points']) == 300 and hits['obj'] == 'OpticalAbsorberGroup'
+  finally:
+    engine_bridge.set_engine_factory(None)
