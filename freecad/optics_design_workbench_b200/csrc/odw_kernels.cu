@@ -15,6 +15,10 @@
 
 namespace cg = cooperative_groups;
 
+// per-CTA event counters in shared memory (flushed to the global Counters once per CTA): keeping them in registers
+// cost five registers per lane for values touched once per ray
+enum { CNT_SEGMENTS = 0, CNT_HITS, CNT_DROPPED, CNT_ESCAPED, CNT_DEPTH, CNT_N };
+
 // outward unit normal: short paths for plane / sphere / cylinder, general otherwise
 __device__ __forceinline__ void outward_normal(const DFace& f, const double* P, double* n) {
   if (f.kind == ODW_SURF_PLANE) {
@@ -249,7 +253,7 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
 // warp-aggregated append (one atomic per converged group of lanes) + optional detector binning
 __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long long ray, int bounce, int group, int face_id,
                                            const double* P, const double* dir, double power, bool entering,
-                                           unsigned int& n_hits, unsigned int& n_dropped) {
+                                           unsigned int* s_cnt) {
   for (int b = 0; b < p.n_binnings; ++b) {
     const DBinning& bn = p.binnings[b];
     if (bn.group != group) continue;
@@ -261,14 +265,13 @@ __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long l
       atomicAdd(p.bins + bn.offset + (size_t)ix*bn.nv + iy, bn.weighted ? power : 1.0);
     }
   }
-  ++n_hits;
-  if (!p.store_hits) return;
+  if (!p.store_hits) { atomicAdd(&s_cnt[CNT_HITS], 1u); return; }
   cg::coalesced_group g = cg::coalesced_threads();
   unsigned long long base = 0;
   if (g.thread_rank() == 0) base = atomicAdd(&p.counters->hits, (unsigned long long)g.size());
   base = g.shfl(base, 0);
   unsigned long long slot = base + g.thread_rank();
-  if (slot >= p.hits.capacity) { ++n_dropped; return; }
+  if (slot >= p.hits.capacity) { atomicAdd(&s_cnt[CNT_DROPPED], 1u); return; }
   double* hp = p.hits.points + 3*slot; hp[0] = P[0]; hp[1] = P[1]; hp[2] = P[2];
   double* hd = p.hits.dirs + 3*slot;   hd[0] = dir[0]; hd[1] = dir[1]; hd[2] = dir[2];
   p.hits.powers[slot] = power;
@@ -301,6 +304,9 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DShell* sshells = reinterpret_cast<DShell*>(smem_raw);
   DFace* sfaces = reinterpret_cast<DFace*>(smem_raw + (size_t)p.scene.n_shells*sizeof(DShell));
+  __shared__ unsigned int s_cnt[CNT_N];
+  if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
+  if (BVH) __syncthreads();
   if (!BVH) {
     // stage the scene (shells, then faces): 16-byte vector copies, coalesced
     const int4* src = reinterpret_cast<const int4*>(p.scene.shells);
@@ -329,7 +335,6 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   unsigned long long t_start = 0, c_start = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start)); c_start = clock64(); }
   const DGroup* __restrict__ groups = p.scene.groups;
-  unsigned int nseg_acc = 0, nhit_acc = 0, ndrop_acc = 0, nesc_acc = 0, ndepth_acc = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
   // Persistent lanes: a lane whose ray has ended fetches its next ray (index + stride) and initialises it; then
   // every lane with a live ray does ONE bounce.  The warp re-converges once per bounce (the __any_sync below),
@@ -337,30 +342,32 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   // differently long the rays of a warp are.  Without this the lanes of a warp drift apart over the ~1e3 rays a
   // lane traces in a 1e8-ray launch and SIMT efficiency collapses.
   unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
-  bool alive = false, first_fetch = true;
-  double point[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, power = 0;
-  int medium = -1, seq_index = 0, n_isect = 0, nseg = 0;
+  // i = index of the lane's current ray; a lane starts "before" its first ray and steps by the grid size
+  bool alive = false;
+  // direction = dn (unit) times dscale: the reference keeps the un-normalised direction (explicit ray lists need not be
+  // unit, a mirror preserves the length) and reports it with every hit; one scalar instead of a second vector
+  double point[3] = {0, 0, 0}, dn[3] = {0, 0, 1}, dscale = 1, power = 0;
+  int medium = -1, seq_index = 0, n_isect = 0;                        // n_isect = segments of the current ray so far
   for (;;) {
-    if (!alive) {
-      if (!first_fetch) i += stride;
-      first_fetch = false;
-      if (i < p.n_rays) {
+    if (!alive && i < p.n_rays) {
+      {
         if (MC) {
           const RayInit r = init_ray_mc(p, p.first_ray + i);
           point[0] = r.o[0]; point[1] = r.o[1]; point[2] = r.o[2];
-          dir[0] = r.d[0]; dir[1] = r.d[1]; dir[2] = r.d[2];
+          dn[0] = r.d[0]; dn[1] = r.d[1]; dn[2] = r.d[2];
           power = 1.0;
         } else {
           const double* o = p.in_origins + 3*i; const double* d = p.in_dirs + 3*i;
           point[0] = o[0]; point[1] = o[1]; point[2] = o[2];
-          dir[0] = d[0]; dir[1] = d[1]; dir[2] = d[2];
+          dn[0] = d[0]; dn[1] = d[1]; dn[2] = d[2];
           power = p.in_powers ? p.in_powers[i] : 1.0;
         }
-        medium = -1; seq_index = 0; n_isect = 0; nseg = 0;
+        {
+          const double d2 = dot3(dn, dn), li = fast_rsqrt(d2);
+          dn[0] *= li; dn[1] *= li; dn[2] *= li; dscale = d2*li;
+        }
+        medium = -1; seq_index = 0; n_isect = 0;
         alive = true;
-      } else {
-        i = p.n_rays;                      // stay parked (no overflow of i)
-        first_fetch = true;
       }
     }
 #if ODW_BLOCK_SYNC
@@ -372,24 +379,21 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
 #endif
     if (alive) {
       bool done = false;
-      if (n_isect >= p.max_isect) { ++ndepth_acc; done = true; }                // ray.py:96-98
+      if (n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); done = true; }   // ray.py:96-98
       else {
         ++n_isect;
-        const double dli = fast_rsqrt(dot3(dir, dir));
-        double dn[3] = { dir[0]*dli, dir[1]*dli, dir[2]*dli };
         double t;
         int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
                      : find_nearest_smem(sshells, sfaces, p, point, dn, medium, seq_index, p.max_len, t);
         if (fi < 0) {                                                            // ray.py:105-109
           point[0] += dn[0]*p.max_len; point[1] += dn[1]*p.max_len; point[2] += dn[2]*p.max_len;
-          ++nseg; ++nesc_acc;
+          atomicAdd(&s_cnt[CNT_ESCAPED], 1u);
           done = true;
         } else {
           const DFace& f = BVH ? p.scene.faces[fi] : sfaces[fi];
           const int fgroup = f.group;
           const DGroup& g = groups[fgroup];
-          point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];
-          ++nseg;                                                                // ray.py:117
+          point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];           // ray.py:117
           if (medium >= 0) {                                                     // ray.py:120-125 (multiplicative)
             double L = groups[medium].absorption_length;
             if (L == 0) power = 0; else if (isfinite(L)) power *= exp(-t/L);
@@ -398,41 +402,42 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
           outward_normal(f, point, nrm);
           const bool entering = dot3(dn, nrm) < 0;                               // ray.py:473-480
           if (entering) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
-          if (g.record || p.record_all)
-            record_hit(p, p.first_ray + i, n_isect-1, fgroup, f.face_id, point, dir, power, entering, nhit_acc, ndrop_acc);
+          if (g.record || p.record_all) {
+            const double dir[3] = { dn[0]*dscale, dn[1]*dscale, dn[2]*dscale };
+            record_hit(p, p.first_ray + i, n_isect-1, fgroup, f.face_id, point, dir, power, entering, s_cnt);
+          }
+          double o[3] = { dn[0], dn[1], dn[2] };                                 // outgoing direction / dscale_out
+          double oscale = dscale;
           switch (g.type) {
             case ODW_OPT_MIRROR: {                                               // ray.py:146-161
-              double o[3]; mirror_dir(dir, nrm, o);
-              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+              mirror_dir(dn, nrm, o);                                            // d - 2(d.n)n is linear in d: the length carries over
               power *= g.reflectivity; ++seq_index;
               break;
             }
             case ODW_OPT_LENS: {                                                 // ray.py:165-211
               double n1 = medium >= 0 ? groups[medium].n : 1.0, n2 = 1.0;
               if (entering) { medium = fgroup; n2 = g.n; }
-              double o[3];
               bool tir = snell(dn, n1, n2, nrm, o);
-              dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+              oscale = 1.0;                                                      // snellsLaw works on the unit direction
               if (!entering && !tir && medium == fgroup) { medium = -1; ++seq_index; }
               break;
             }
             case ODW_OPT_GRATING: {                                              // ray.py:216-268
-              double o[3];
               if (g.gtype == ODW_GRATING_REFLECTION) {
                 if (entering) {
                   double n = medium >= 0 ? groups[medium].n : 1.0;
                   const Vec3 q = line_grating(dn[0], dn[1], dn[2], n, n, nrm[0], nrm[1], nrm[2], &g, p.wavelength, false);
-                  dir[0] = q.x; dir[1] = q.y; dir[2] = q.z; ++seq_index;
+                  o[0] = q.x; o[1] = q.y; o[2] = q.z; oscale = 1.0; ++seq_index;
                 }
               } else if (entering) {
                 if (medium >= 0) { power = 0; break; }                           // the reference raises ValueError here
                 medium = fgroup;
                 const Vec3 q = line_grating(dn[0], dn[1], dn[2], 1.0, g.n, nrm[0], nrm[1], nrm[2], &g, p.wavelength, true);
-                dir[0] = q.x; dir[1] = q.y; dir[2] = q.z;
+                o[0] = q.x; o[1] = q.y; o[2] = q.z; oscale = 1.0;
               } else {
                 double n1 = medium >= 0 ? groups[medium].n : 1.0;
                 bool tir = snell(dn, n1, 1.0, nrm, o);
-                dir[0] = o[0]; dir[1] = o[1]; dir[2] = o[2];
+                oscale = 1.0;
                 if (!tir) { medium = -1; ++seq_index; }
               }
               break;
@@ -441,16 +446,23 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
             default: ++seq_index; break;                                         // Vacuum, ray.py:276-277
           }
           if (power < p.power_tol) done = true;                                  // ray.py:280
+          else {
+            // next segment: unit direction and the length the reference would carry along
+            const double o2 = dot3(o, o), li = fast_rsqrt(o2);
+            dn[0] = o[0]*li; dn[1] = o[1]*li; dn[2] = o[2]*li; dscale = oscale*(o2*li);
+          }
         }
       }
       if (done) {
-        nseg_acc += nseg;
+        // every find_nearest call yields exactly one segment (a hit or the escape segment), so segments == n_isect
+        atomicAdd(&s_cnt[CNT_SEGMENTS], (unsigned int)n_isect);
         if (!MC) {
-          if (p.out_nseg) p.out_nseg[i] = nseg;
+          if (p.out_nseg) p.out_nseg[i] = n_isect;
           if (p.out_final_point) { double* q = p.out_final_point + 3*i; q[0] = point[0]; q[1] = point[1]; q[2] = point[2]; }
           if (p.out_final_power) p.out_final_power[i] = power;
         }
         alive = false;
+        i += stride;
       }
     }
   }
@@ -458,18 +470,13 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
     unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
     p.counters->dbg_cycles = clock64() - c_start; p.counters->dbg_ns = t_end - t_start;
   }
-  // per-warp reduction of the counters, one atomic per warp and counter
-  nseg_acc = __reduce_add_sync(0xffffffffu, nseg_acc);
-  nhit_acc = __reduce_add_sync(0xffffffffu, nhit_acc);
-  ndrop_acc = __reduce_add_sync(0xffffffffu, ndrop_acc);
-  nesc_acc = __reduce_add_sync(0xffffffffu, nesc_acc);
-  ndepth_acc = __reduce_add_sync(0xffffffffu, ndepth_acc);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&p.counters->segments, (unsigned long long)nseg_acc);
-    if (!p.store_hits) atomicAdd(&p.counters->hits, (unsigned long long)nhit_acc);
-    if (ndrop_acc) atomicAdd(&p.counters->hits_dropped, (unsigned long long)ndrop_acc);
-    if (nesc_acc) atomicAdd(&p.counters->escaped, (unsigned long long)nesc_acc);
-    if (ndepth_acc) atomicAdd(&p.counters->depth_terminated, (unsigned long long)ndepth_acc);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&p.counters->segments, (unsigned long long)s_cnt[CNT_SEGMENTS]);
+    if (!p.store_hits) atomicAdd(&p.counters->hits, (unsigned long long)s_cnt[CNT_HITS]);
+    if (s_cnt[CNT_DROPPED]) atomicAdd(&p.counters->hits_dropped, (unsigned long long)s_cnt[CNT_DROPPED]);
+    if (s_cnt[CNT_ESCAPED]) atomicAdd(&p.counters->escaped, (unsigned long long)s_cnt[CNT_ESCAPED]);
+    if (s_cnt[CNT_DEPTH]) atomicAdd(&p.counters->depth_terminated, (unsigned long long)s_cnt[CNT_DEPTH]);
   }
 }
 
