@@ -28,7 +28,9 @@ class SourceDesc(C.Structure):
               ('focal_length', C.c_double), ('wavelength', C.c_double),
               ('max_ray_length_scale', C.c_double), ('max_intersections_scale', C.c_double),
               ('gpM', C.c_double*16),
-              ('phi_cdf', C.c_void_p), ('first_cdf', C.c_void_p), ('ignored_groups', C.c_void_p)]
+              ('phi_cdf', C.c_void_p), ('first_cdf', C.c_void_p), ('ignored_groups', C.c_void_p),
+              ('n_emit', C.c_int32), ('n_emit_segs', C.c_int32),
+              ('emit_faces', C.c_void_p), ('emit_segs', C.c_void_p), ('emit_cdf', C.c_void_p), ('dist_tol', C.c_double)]
 
 
 class Binning(C.Structure):
@@ -78,7 +80,8 @@ class SceneArgs:
 
 class SourceArgs:
   def __init__(self, tables, *, kind, source_id, gpM, focal_length=0.0, wavelength=500.0, ignored=(),
-               max_ray_length_scale=1.0, max_intersections_scale=1.0):
+               max_ray_length_scale=1.0, max_intersections_scale=1.0, emit_faces=None, emit_segs=None,
+               emit_cdf=None, dist_tol=1e-6):
     self.phi_cdf = np.ascontiguousarray(tables.phi_cdf, dtype=np.float64)
     self.first_cdf = np.ascontiguousarray(tables.first_cdf, dtype=np.float64)
     self.ignored = np.ascontiguousarray(list(ignored), dtype=np.int32)
@@ -96,6 +99,13 @@ class SourceArgs:
       d.gpM[i] = m[i]
     d.phi_cdf, d.first_cdf = _ptr(self.phi_cdf), _ptr(self.first_cdf)
     d.ignored_groups = _ptr(self.ignored)
+    if emit_faces is not None:                      # surface source (ODW_SRC_SURFACE)
+      self.emit_faces = np.ascontiguousarray(emit_faces)
+      self.emit_segs = np.ascontiguousarray(emit_segs)
+      self.emit_cdf = np.ascontiguousarray(emit_cdf, dtype=np.float64)
+      d.n_emit, d.n_emit_segs = len(self.emit_faces), len(self.emit_segs)
+      d.emit_faces, d.emit_segs, d.emit_cdf = _ptr(self.emit_faces), _ptr(self.emit_segs), _ptr(self.emit_cdf)
+      d.dist_tol = float(dist_tol)
     self.desc = d
     self.tables = tables
 

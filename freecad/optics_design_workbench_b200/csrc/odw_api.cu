@@ -280,6 +280,42 @@ struct BvhBuilder {
 };
 }  // namespace
 
+// odw_face -> the record the kernels read.  fast_paths: precompute the inline-test constants of the trace kernel
+// (emitting faces of a surface source are only evaluated / trim-tested, never intersected: no fast paths there).
+static void fill_dface(const odw_face& f, const odw_trimseg* segs, bool fast_paths, DFace& d) {
+    memset(&d, 0, sizeof d);
+    for (int k = 0; k < 3; ++k) { d.o[k] = f.origin[k]; d.x[k] = f.xdir[k]; d.y[k] = f.ydir[k]; d.z[k] = f.zdir[k];
+                                  d.bmin[k] = f.aabb_min[k]; d.bmax[k] = f.aabb_max[k];
+                                  }
+    d.p0 = f.p0; d.p1 = f.p1;
+    d.umin = f.uv_min[0]; d.umax = f.uv_max[0]; d.vmin = f.uv_min[1]; d.vmax = f.uv_max[1];
+    d.kind = f.kind; d.trim = f.trim_kind; d.nsign = f.nsign; d.group = f.group;
+    d.seg_first = f.seg_first; d.seg_count = f.seg_count; d.face_id = f.face_id;
+    d.flags = (f.kind != ODW_SURF_PLANE && std::fabs((f.uv_max[0] - f.uv_min[0]) - ODW_TWO_PI) < 1e-9) ? DFACE_FULL_U : 0;
+    {
+      auto dot = [](const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; };
+      const bool full_u = (d.flags & DFACE_FULL_U) != 0;
+      if (fast_paths) {
+      if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_UVBOX) {
+        d.flags |= DFACE_FAST; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
+      } else if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_LOOPS && f.seg_count == 1 &&
+                 segs[f.seg_first].kind == ODW_SEG_ARC && segs[f.seg_first].a[4] >= ODW_TWO_PI - 1e-12) {
+        // a disc: the single trim loop is one full circle (centre a[0], a[1], radius a[2])
+        const odw_trimseg& c = segs[f.seg_first];
+        d.flags |= DFACE_FAST | DFACE_DISC; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
+        d.umin = c.a[0]; d.vmin = c.a[1]; d.umax = c.a[2]; d.vmax = c.a[2];
+      } else if (f.kind == ODW_SURF_SPHERE && (f.trim_kind == ODW_TRIM_NONE || (f.trim_kind == ODW_TRIM_UVBOX && full_u))) {
+        d.flags |= DFACE_FAST;
+        const bool whole = f.trim_kind == ODW_TRIM_NONE;
+        d.c0 = whole ? -1e300 : f.p0*std::sin(f.uv_min[1]);
+        d.c1 = whole ?  1e300 : f.p0*std::sin(f.uv_max[1]);
+      } else if (f.kind == ODW_SURF_CYLINDER && f.trim_kind == ODW_TRIM_UVBOX && full_u) {
+        d.flags |= DFACE_FAST; d.c0 = f.uv_min[1]; d.c1 = f.uv_max[1];
+      }
+      }
+    }
+}
+
 extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_scene** out) {
   if (!eng || !sd || !out) return fail(ODW_EINVAL, "odw_scene_create: NULL argument");
   *out = nullptr;
@@ -296,35 +332,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_segs))
       return fail(ODW_EINVAL, "face " + std::to_string(i) + ": trim segment range out of bounds");
     DFace& d = faces[(size_t)i];
-    memset(&d, 0, sizeof d);
-    for (int k = 0; k < 3; ++k) { d.o[k] = f.origin[k]; d.x[k] = f.xdir[k]; d.y[k] = f.ydir[k]; d.z[k] = f.zdir[k];
-                                  d.bmin[k] = f.aabb_min[k]; d.bmax[k] = f.aabb_max[k];
-                                  boxes[(size_t)i].lo[k] = f.aabb_min[k]; boxes[(size_t)i].hi[k] = f.aabb_max[k]; }
-    d.p0 = f.p0; d.p1 = f.p1;
-    d.umin = f.uv_min[0]; d.umax = f.uv_max[0]; d.vmin = f.uv_min[1]; d.vmax = f.uv_max[1];
-    d.kind = f.kind; d.trim = f.trim_kind; d.nsign = f.nsign; d.group = f.group;
-    d.seg_first = f.seg_first; d.seg_count = f.seg_count; d.face_id = f.face_id;
-    d.flags = (f.kind != ODW_SURF_PLANE && std::fabs((f.uv_max[0] - f.uv_min[0]) - ODW_TWO_PI) < 1e-9) ? DFACE_FULL_U : 0;
-    {
-      auto dot = [](const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; };
-      const bool full_u = (d.flags & DFACE_FULL_U) != 0;
-      if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_UVBOX) {
-        d.flags |= DFACE_FAST; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
-      } else if (f.kind == ODW_SURF_PLANE && f.trim_kind == ODW_TRIM_LOOPS && f.seg_count == 1 &&
-                 sd->segs[f.seg_first].kind == ODW_SEG_ARC && sd->segs[f.seg_first].a[4] >= ODW_TWO_PI - 1e-12) {
-        // a disc: the single trim loop is one full circle (centre a[0], a[1], radius a[2])
-        const odw_trimseg& c = sd->segs[f.seg_first];
-        d.flags |= DFACE_FAST | DFACE_DISC; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
-        d.umin = c.a[0]; d.vmin = c.a[1]; d.umax = c.a[2]; d.vmax = c.a[2];
-      } else if (f.kind == ODW_SURF_SPHERE && (f.trim_kind == ODW_TRIM_NONE || (f.trim_kind == ODW_TRIM_UVBOX && full_u))) {
-        d.flags |= DFACE_FAST;
-        const bool whole = f.trim_kind == ODW_TRIM_NONE;
-        d.c0 = whole ? -1e300 : f.p0*std::sin(f.uv_min[1]);
-        d.c1 = whole ?  1e300 : f.p0*std::sin(f.uv_max[1]);
-      } else if (f.kind == ODW_SURF_CYLINDER && f.trim_kind == ODW_TRIM_UVBOX && full_u) {
-        d.flags |= DFACE_FAST; d.c0 = f.uv_min[1]; d.c1 = f.uv_max[1];
-      }
-    }
+    fill_dface(f, sd->segs, true, d);
+    for (int k = 0; k < 3; ++k) { boxes[(size_t)i].lo[k] = f.aabb_min[k]; boxes[(size_t)i].hi[k] = f.aabb_max[k]; }
     for (int s = 0; s < sd->n_seq_steps; ++s)
       for (int k = sd->seq_offsets[s]; k < sd->seq_offsets[s+1]; ++k)
         if (sd->seq_groups[k] == f.group) d.seqmask[s >> 6] |= 1ull << (s & 63);
@@ -414,9 +423,53 @@ static std::vector<uint32_t> build_guide(const double* cdf, int n) {
   return g;
 }
 
+extern "C" void odw_source_destroy(odw_source* s);
+
+// ODW_SRC_SURFACE (reference freecad_elements/surface_source.py): emitting faces, area CDF and the theta table
+static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw_source** out) {
+  if (sd->n_emit <= 0 || !sd->emit_faces || !sd->emit_cdf) return fail(ODW_EINVAL, "surface source without emitting faces");
+  if (sd->n_first < 2 || !sd->first_cdf) return fail(ODW_EINVAL, "surface source: missing theta CDF");
+  if (!(sd->first_cdf[0] == 0.0) || !(std::fabs(sd->first_cdf[sd->n_first-1] - 1.0) < 1e-12)) return fail(ODW_EINVAL, "surface source: theta CDF must run from 0 to 1");
+  if (!(std::fabs(sd->emit_cdf[sd->n_emit-1] - 1.0) < 1e-12)) return fail(ODW_EINVAL, "surface source: emit_cdf must end at 1");
+  for (int i = 0; i < sd->n_emit; ++i) {
+    const odw_face& f = sd->emit_faces[i];
+    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_TORUS) return fail(ODW_EINVAL, "surface source: unknown surface kind of an emitting face");
+    if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_emit_segs || !sd->emit_segs))
+      return fail(ODW_EINVAL, "surface source: trim segment range of an emitting face out of bounds");
+    if (i && sd->emit_cdf[i] < sd->emit_cdf[i-1]) return fail(ODW_EINVAL, "surface source: emit_cdf must be non-decreasing");
+  }
+  CU(cudaSetDevice(eng->device));
+  odw_source* s = new odw_source();
+  s->eng = eng;
+  std::vector<DFace> faces((size_t)sd->n_emit);
+  double bound = 0;
+  for (int i = 0; i < sd->n_emit; ++i) {
+    fill_dface(sd->emit_faces[i], sd->emit_segs, false, faces[(size_t)i]);
+    for (int k = 0; k < 3; ++k) bound = std::max(bound, std::max(std::fabs(sd->emit_faces[i].aabb_min[k]), std::fabs(sd->emit_faces[i].aabb_max[k])));
+  }
+  int rc;
+  if ((rc = upload(eng, s->owned, faces.data(), faces.size(), &s->d.emit_faces))) { odw_source_destroy(s); return rc; }
+  if ((rc = upload(eng, s->owned, sd->emit_segs, (size_t)sd->n_emit_segs, &s->d.emit_segs))) { odw_source_destroy(s); return rc; }
+  if ((rc = upload(eng, s->owned, sd->emit_cdf, (size_t)sd->n_emit, &s->d.emit_cdf))) { odw_source_destroy(s); return rc; }
+  if ((rc = upload(eng, s->owned, sd->first_cdf, (size_t)sd->n_first, &s->d.first_cdf))) { odw_source_destroy(s); return rc; }
+  std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first);
+  if ((rc = upload(eng, s->owned, fg.data(), fg.size(), &s->d.first_guide))) { odw_source_destroy(s); return rc; }
+  s->d.first_lo = sd->first_lo; s->d.first_hi = sd->first_hi; s->d.phi_lo = 0; s->d.phi_hi = ODW_TWO_PI;
+  s->d.wavelength = sd->wavelength;
+  s->d.kind = sd->kind; s->d.source_id = sd->source_id; s->d.n_first = sd->n_first; s->d.n_phi = 0; s->d.n_rows = 1;
+  s->d.n_emit = sd->n_emit; s->d.dist_tol = sd->dist_tol > 0 ? sd->dist_tol : 1e-6;
+  s->origin_bound = bound;
+  s->max_ray_length_scale = sd->max_ray_length_scale > 0 ? sd->max_ray_length_scale : 1.0;
+  s->max_intersections_scale = sd->max_intersections_scale > 0 ? sd->max_intersections_scale : 1.0;
+  if (sd->n_ignored > 0 && sd->ignored_groups) s->ignored.assign(sd->ignored_groups, sd->ignored_groups + sd->n_ignored);
+  *out = s;
+  return ODW_OK;
+}
+
 extern "C" int odw_source_create(odw_engine* eng, const odw_source_desc* sd, odw_source** out) {
   if (!eng || !sd || !out) return fail(ODW_EINVAL, "odw_source_create: NULL argument");
   *out = nullptr;
+  if (sd->kind == ODW_SRC_SURFACE) return surface_source_create(eng, sd, out);
   if (sd->kind != ODW_SRC_POINT_SPHERICAL && sd->kind != ODW_SRC_POINT_COLLIMATED) return fail(ODW_EUNSUPPORTED, "unknown source kind");
   if (sd->n_first < 2 || sd->n_phi < 2 || !sd->phi_cdf || !sd->first_cdf) return fail(ODW_EINVAL, "odw_source_create: missing CDF tables");
   if (sd->n_rows != 1 && sd->n_rows != sd->n_phi - 1) return fail(ODW_EINVAL, "odw_source_create: n_rows must be 1 or n_phi-1");

@@ -80,7 +80,12 @@ struct DSource {
   const uint32_t* first_guide;     // [n_rows][GUIDE+1]
   double first_lo, first_hi, phi_lo, phi_hi, focal, wavelength;
   double M[12];                    // rows 0..2 of gpM
-  int32_t kind, source_id, n_first, n_phi, n_rows, pad;
+  int32_t kind, source_id, n_first, n_phi, n_rows, n_emit;
+  // surface sources (ODW_SRC_SURFACE): emitting faces in the world frame, their trim loops, cumulative area weights
+  const DFace* emit_faces;
+  const odw_trimseg* emit_segs;
+  const double* emit_cdf;
+  double dist_tol;
 };
 #define ODW_GUIDE 4096
 
@@ -471,6 +476,69 @@ __device__ __forceinline__ void outward_normal_general(const DFace& f, const dou
   }
   double s = (double)f.nsign/sqrt(dot3(g, g));
   n[0] = g[0]*s; n[1] = g[1]*s; n[2] = g[2]*s;
+}
+
+// ---- surface source (reference freecad_elements/surface_source.py:85-111,390-410,522-555) ----------------
+// point and first derivatives of the parametrisation (OCC's, see odw_face in include/odw.h)
+__device__ __forceinline__ void surface_eval(const DFace& f, double u, double v, double* P, double* du, double* dv) {
+  double su, cu; sincos(u, &su, &cu);
+  double rad[3], tang[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { rad[i] = cu*f.x[i] + su*f.y[i]; tang[i] = -su*f.x[i] + cu*f.y[i]; }
+  switch (f.kind) {
+    case ODW_SURF_PLANE:
+      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + u*f.x[i] + v*f.y[i]; du[i] = f.x[i]; dv[i] = f.y[i]; }
+      break;
+    case ODW_SURF_CYLINDER:
+      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + f.p0*rad[i] + v*f.z[i]; du[i] = f.p0*tang[i]; dv[i] = f.z[i]; }
+      break;
+    case ODW_SURF_CONE: {
+      double sa, ca; sincos(f.p1, &sa, &ca);
+      const double r = f.p0 + v*sa;
+      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + r*rad[i] + v*ca*f.z[i]; du[i] = r*tang[i]; dv[i] = sa*rad[i] + ca*f.z[i]; }
+      break;
+    }
+    case ODW_SURF_SPHERE: {
+      double sv, cv; sincos(v, &sv, &cv);
+      const double R = f.p0;
+      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + R*cv*rad[i] + R*sv*f.z[i]; du[i] = R*cv*tang[i]; dv[i] = -R*sv*rad[i] + R*cv*f.z[i]; }
+      break;
+    }
+    default: {
+      double sv, cv; sincos(v, &sv, &cv);
+      const double R = f.p0, r = f.p1;
+      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + (R + r*cv)*rad[i] + r*sv*f.z[i]; du[i] = (R + r*cv)*tang[i]; dv[i] = -r*sv*rad[i] + r*cv*f.z[i]; }
+    }
+  }
+}
+
+// (u, v) distributed by area inside the face's parameter window; false = draw rejected (cone, torus)
+__device__ __forceinline__ bool surface_draw_uv(const DFace& f, double w0, double w1, double w2, double& u, double& v) {
+  double u0 = f.umin, u1 = f.umax, v0 = f.vmin, v1 = f.vmax;
+  if (f.trim == ODW_TRIM_NONE) {
+    u0 = 0; u1 = ODW_TWO_PI;
+    if (f.kind == ODW_SURF_SPHERE) { v0 = -ODW_TWO_PI/4; v1 = ODW_TWO_PI/4; }
+    if (f.kind == ODW_SURF_TORUS) { v0 = 0; v1 = ODW_TWO_PI; }
+  }
+  u = u0 + w0*(u1 - u0);
+  switch (f.kind) {
+    case ODW_SURF_SPHERE: {
+      const double s0 = sin(v0), s1 = sin(v1);
+      v = asin(fmin(1.0, fmax(-1.0, s0 + w1*(s1 - s0))));
+      return true;
+    }
+    case ODW_SURF_CONE: {
+      const double sa = sin(f.p1), r0 = fabs(f.p0 + v0*sa), r1 = fabs(f.p0 + v1*sa);
+      v = v0 + w1*(v1 - v0);
+      return w2*fmax(r0, r1) < fabs(f.p0 + v*sa);
+    }
+    case ODW_SURF_TORUS:
+      v = v0 + w1*(v1 - v0);
+      return w2*(f.p0 + f.p1) < f.p0 + f.p1*cos(v);
+    default:
+      v = v0 + w1*(v1 - v0);
+      return true;
+  }
 }
 
 // ---- Ray.mirror / snellsLaw / lineGrating (ray.py:482-539) ---------------------------------

@@ -293,6 +293,51 @@ __device__ __noinline__ RayInit init_ray_mc(const TraceParams& p, unsigned long 
   return r;
 }
 
+// One Monte-Carlo ray of a surface source (SurfaceSourceProxy._generateRays 'true', surface_source.py:522-555): face by
+// area weight, area-uniform point redrawn until it lies on the trimmed face, theta from the tabulated density, phi uniform,
+// d = cos(theta) n + sin(theta) (cos(phi) (t x n) + sin(phi) t).  Philox purposes: 0 -> (face, theta), 1 -> (phi, -),
+// 2+k -> (u, v) of try k, 0x100+k -> acceptance uniform of try k.
+#define ODW_SURFACE_MAX_TRIES 64
+__device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long long seed, unsigned long long ray,
+                                                 double* theta_out, double* phi_out) {
+  double a0, a1, b0, b1;
+  philox_uniform2(seed, (uint32_t)s.source_id, ray, 0u, a0, a1);
+  philox_uniform2(seed, (uint32_t)s.source_id, ray, 1u, b0, b1);
+  int k = 0;
+  while (k < s.n_emit-1 && !(a0 < __ldg(s.emit_cdf + k))) ++k;
+  const DFace& f = s.emit_faces[k];
+  double P[3] = {0, 0, 0}, du[3] = {1, 0, 0}, dv[3] = {0, 1, 0};
+  for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {
+    double w0, w1, w2, w3, u, v;
+    philox_uniform2(seed, (uint32_t)s.source_id, ray, 2u + tr, w0, w1);
+    philox_uniform2(seed, (uint32_t)s.source_id, ray, 0x100u + tr, w2, w3);
+    const bool ok = surface_draw_uv(f, w0, w1, w2, u, v);
+    surface_eval(f, u, v, P, du, dv);
+    if (!ok) continue;
+    if (on_trimmed_face(f, s.emit_segs, P, s.dist_tol)) break;                  // surface_source.py:399-408
+  }
+  const double theta = interp_cdf(a1, s.first_cdf, s.first_guide, s.n_first, s.first_lo, s.first_hi);
+  const double phi = b0*ODW_TWO_PI;                                              // surface_source.py:544
+  double n[3];
+  outward_normal(f, P, n);
+  const double lu = sqrt(dot3(du, du)), lv = sqrt(dot3(dv, dv));
+  const double* t = (lu > 10*s.dist_tol || lu >= lv) ? du : dv;                  // surface_source.py:549
+  const double tl = sqrt(dot3(t, t));
+  const double th[3] = { t[0]/tl, t[1]/tl, t[2]/tl };
+  const double txn[3] = { th[1]*n[2]-th[2]*n[1], th[2]*n[0]-th[0]*n[2], th[0]*n[1]-th[1]*n[0] };
+  double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phi, &sp, &cp);
+  RayInit r;
+  double d[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[i] = ct*n[i] + st*(cp*txn[i] + sp*th[i]);
+  const double dl = sqrt(dot3(d, d));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { r.o[i] = P[i]; r.d[i] = d[i]/dl; }
+  if (theta_out) *theta_out = theta;
+  if (phi_out) *phi_out = phi;
+  return r;
+}
+
 #ifndef ODW_MIN_BLOCKS
 #define ODW_MIN_BLOCKS 3          // 3 CTAs x 8 warps per SM (80 registers): the kernel is latency-bound, 24 warps beat 16 despite spills
 #endif
@@ -352,7 +397,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
     if (!alive && i < p.n_rays) {
       {
         if (MC) {
-          const RayInit r = init_ray_mc(p, p.first_ray + i);
+          const RayInit r = p.src.kind == ODW_SRC_SURFACE ? init_ray_surface(p.src, p.seed, p.first_ray + i, nullptr, nullptr)
+                                                           : init_ray_mc(p, p.first_ray + i);
           point[0] = r.o[0]; point[1] = r.o[1]; point[2] = r.o[2];
           dn[0] = r.d[0]; dn[1] = r.d[1]; dn[2] = r.d[2];
           power = 1.0;
@@ -364,7 +410,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
         }
         {
           const double d2 = dot3(dn, dn), li = fast_rsqrt(d2);
-          dn[0] *= li; dn[1] *= li; dn[2] *= li; dscale = d2*li;
+          dn[0] *= li; dn[1] *= li; dn[2] *= li;
+          if (!MC) dscale = d2*li;            // Monte-Carlo rays start (and stay, to rounding) unit: no length to carry
         }
         medium = -1; seq_index = 0; n_isect = 0;
         alive = true;
@@ -403,11 +450,12 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
           const bool entering = dot3(dn, nrm) < 0;                               // ray.py:473-480
           if (entering) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
           if (g.record || p.record_all) {
-            const double dir[3] = { dn[0]*dscale, dn[1]*dscale, dn[2]*dscale };
+            const double ds = MC ? 1.0 : dscale;
+            const double dir[3] = { dn[0]*ds, dn[1]*ds, dn[2]*ds };
             record_hit(p, p.first_ray + i, n_isect-1, fgroup, f.face_id, point, dir, power, entering, s_cnt);
           }
           double o[3] = { dn[0], dn[1], dn[2] };                                 // outgoing direction / dscale_out
-          double oscale = dscale;
+          double oscale = MC ? 1.0 : dscale;
           switch (g.type) {
             case ODW_OPT_MIRROR: {                                               // ray.py:146-161
               mirror_dir(dn, nrm, o);                                            // d - 2(d.n)n is linear in d: the length carries over
@@ -449,7 +497,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
           else {
             // next segment: unit direction and the length the reference would carry along
             const double o2 = dot3(o, o), li = fast_rsqrt(o2);
-            dn[0] = o[0]*li; dn[1] = o[1]*li; dn[2] = o[2]*li; dscale = oscale*(o2*li);
+            dn[0] = o[0]*li; dn[1] = o[1]*li; dn[2] = o[2]*li;
+            if (!MC) dscale = oscale*(o2*li);
           }
         }
       }
@@ -487,9 +536,14 @@ __global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long 
   const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {
     double u0, u1, first, phi, o[3], d[3];
-    philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, u0, u1);
-    sample_source(src, u0, u1, first, phi);
-    make_ray(src, first, phi, o, d);
+    if (src.kind == ODW_SRC_SURFACE) {
+      const RayInit r = init_ray_surface(src, seed, first_ray + i, &first, &phi);
+      for (int k = 0; k < 3; ++k) { o[k] = r.o[k]; d[k] = r.d[k]; }
+    } else {
+      philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, u0, u1);
+      sample_source(src, u0, u1, first, phi);
+      make_ray(src, first, phi, o, d);
+    }
     if (first_out) first_out[i] = first;
     if (phi_out) phi_out[i] = phi;
     if (origins) { origins[3*i] = o[0]; origins[3*i+1] = o[1]; origins[3*i+2] = o[2]; }

@@ -165,6 +165,18 @@ def point_source_tables(rec):
   return build_tables(expr, var, dom, phi_dom, float(res), float(rec.get('PhiResolutionNumericMode', '1e2')))
 
 
+def surface_source_tables(rec):
+  '''
+  Surface source record -> SamplerTables whose single conditional row is the theta CDF.  The reference builds a
+  ScalarRandomVariable from the power density as it stands — no sin(theta) area factor (surface_source.py:530 with
+  point_source.py:277-321, scalarRandomVar=True; a surface source has no FocalLength, so the finite-focal-length branch
+  with f = 1 applies).  phi is uniform in [0, 2 pi) (surface_source.py:544) and needs no table.
+  '''
+  expr, var = point_source_density(rec['PowerDensity'], 1.0, scalar=True)
+  dom = parse_domain(rec.get('ThetaDomain', '0, pi/2'), (0, np.pi/2))
+  return build_tables(expr, var, dom, (0.0, 2*np.pi), float(rec.get('ThetaResolutionNumericMode', '1e5')), 3)
+
+
 # ------------------------------------------------------------------------------------------
 # deterministic fan grid
 

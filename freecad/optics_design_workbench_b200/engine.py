@@ -230,7 +230,7 @@ class Engine:
   'one engine per GPU (one process per GPU in multi-GPU runs)'
   def __init__(self, device_id=0):
     L = load_library()
-    if L.odw_abi_version() != 1:
+    if L.odw_abi_version() != 2:
       raise EngineError(-1, 'ABI version mismatch between engine.py and libodw_b200.so')
     h = C.c_void_p()
     _check(L.odw_engine_create(int(device_id), C.byref(h)))

@@ -52,8 +52,11 @@ class GenericSourceProxy:
     obj = obj if obj is not None else self.record
     if draw:
       raise NotImplementedError('draw=True builds FreeCAD Part objects; keep the reference path for displayed rays')
-    if obj.get('proxy', 'PointSourceProxy') != 'PointSourceProxy':
-      raise NotImplementedError(f"light source kind {obj.get('proxy')} is not handled by the engine yet")
+    kind = obj.get('proxy', 'PointSourceProxy')
+    if kind not in ('PointSourceProxy', 'SurfaceSourceProxy'):
+      raise NotImplementedError(f"light source kind {kind} is not handled by the engine yet")
+    if kind == 'SurfaceSourceProxy' and (mode in ('fans', 'multicorefans') and useInitialConditions is None):
+      raise NotImplementedError('fan mode of surface sources (_makeSurfaceGrid, surface_source.py:122-267) is not on the engine yet')
     if mode in ('pseudo', 'singlepseudo'):
       raise NotImplementedError("pseudo-random mode (drawPseudo) is not implemented on the engine yet")
 
@@ -119,7 +122,7 @@ class GenericSourceProxy:
       def metadata_of(ray_index, keys):
         s = dsrc.sample(ctx.seed, first, n)               # same Philox stream -> the rays' initial conditions
         idx = (ray_index-np.uint64(first)).astype(np.int64)
-        finite = np.isfinite(float(obj['FocalLength']))
+        finite = np.isfinite(float(obj.get('FocalLength', 0)))
         md = {}
         for k in keys:
           name = k[0].lower()+k[1:]

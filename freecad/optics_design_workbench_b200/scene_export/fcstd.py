@@ -405,15 +405,49 @@ def source_records(doc):
     gp = doc.global_placements(s, ignore_links=True)
     rec = dict(name=s.Name, label=s.Label, proxy=s.proxy_class, source_id=i, gpM=gp[0][0],
                ignored=[group_index[n] for n in (s.get('IgnoredOpticalElements') or []) if n in group_index])
+    if s.proxy_class == 'SurfaceSourceProxy':
+      try:
+        rec['emit'], rec['emit_error'] = surface_source_faces(doc, s), None
+      except Exception as e:          # e.g. B-spline emitters: need the tessellation path (not built yet)
+        rec['emit'], rec['emit_error'] = None, f'{type(e).__name__}: {e}' 
     for k, default in (('PowerDensity', 'exp(-theta^2/0.01)'), ('Wavelength', 500.0), ('FocalLength', '0'),
                        ('ThetaDomain', '0, pi/4'), ('PhiDomain', '0, 2*pi'), ('RadiusDomain', '0, 10'),
                        ('ThetaResolutionNumericMode', '1e5'), ('RadiusResolutionNumericMode', '1e5'),
                        ('PhiResolutionNumericMode', '1e2'), ('Fans', 2), ('FanPhi0', '0'), ('RaysPerFan', 20),
                        ('FanModePowerSpan', 0.9), ('RaysPerIterationScale', 1.0), ('MaxIntersectionsScale', 1.0),
-                       ('MaxRayLengthScale', 1.0), ('RecordRays', False)):
+                       ('MaxRayLengthScale', 1.0), ('RecordRays', False), ('FanModeRayCount', 100)):
       rec[k] = s.get(k, default)
     out.append(rec)
   return out
+
+
+def surface_source_faces(doc, source):
+  '''
+  Emitting faces of a surface source (surface_source.py:437-458): every (part, [FaceN...]) entry of ActiveSurfaces,
+  once per placement of the part; an empty face list = all faces of the part.  World transform of a face =
+  gpM * pMi * Shape = (global placement of the part) * (shape without the part's own placement).
+  '''
+  from ..freecad_elements import surface_source
+  wanted = {}
+  for part_name, sub in source.get('ActiveSurfaces') or []:
+    wanted.setdefault(part_name, [])
+    if sub:
+      wanted[part_name].append(sub)
+  selections = []
+  for part_name, subs in wanted.items():
+    part = doc.objects.get(part_name)
+    if part is None:
+      continue
+    for gpM, _path in doc.global_placements(part):
+      instances = doc.shape_instances(part, with_placement=False)
+      all_faces = [(fi, m) for faces, m in instances for fi in faces]       # Shape.Faces order
+      if subs:
+        picked = [all_faces[int(sname[4:])-1] for sname in subs if sname.startswith('Face') and 0 < int(sname[4:]) <= len(all_faces)]
+      else:
+        picked = all_faces
+      for fi, m in picked:
+        selections.append(([fi], gpM @ m))
+  return surface_source.emitting_faces_from_instances(selections)
 
 
 def load_fcstd(path):

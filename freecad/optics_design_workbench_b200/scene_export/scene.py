@@ -16,7 +16,7 @@ SEG_LINE, SEG_ARC = 1, 2
 OPT_MIRROR, OPT_LENS, OPT_GRATING, OPT_ABSORBER, OPT_VACUUM = 0, 1, 2, 3, 4
 OPTICAL_TYPES = ('Mirror', 'Lens', 'Grating', 'Absorber', 'Vacuum')
 GRATING_TYPES = ('Reflection', 'Transmission')
-SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED = 0, 1
+SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED, SRC_SURFACE = 0, 1, 2
 
 _KIND_ID = dict(plane=SURF_PLANE, cylinder=SURF_CYLINDER, cone=SURF_CONE, sphere=SURF_SPHERE,
                 torus=SURF_TORUS)

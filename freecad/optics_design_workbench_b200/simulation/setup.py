@@ -11,9 +11,9 @@ import json
 import numpy as np
 
 from .. import _abi
-from ..distributions import point_source_tables
+from ..distributions import point_source_tables, surface_source_tables
 from ..scene_export import fcstd
-from ..scene_export.scene import Scene, SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED
+from ..scene_export.scene import Scene, SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED, SRC_SURFACE
 
 
 class PreparedSimulation:
@@ -43,8 +43,11 @@ class PreparedSimulation:
     scene = Scene(z['faces'], z['segs'], z['shells'], z['groups'], meta['group_names'], meta['group_labels'],
                   z['seq_offsets'], z['seq_groups'])
     records = meta['source_records']
-    for r in records:
+    for i, r in enumerate(records):
       r['gpM'] = np.array(r['gpM'], dtype=np.float64)
+      if f'emit_faces_{i}' in z.files:
+        from ..freecad_elements.surface_source import EmittingFaces
+        r['emit'] = EmittingFaces(z[f'emit_faces_{i}'], z[f'emit_segs_{i}'])
     settings = meta['settings']
     for k in ('EndAfterRays', 'EndAfterHits', 'EndAfterIterations'):
       if settings.get(k) is None:
@@ -62,10 +65,14 @@ class PreparedSimulation:
       return v
     meta = dict(group_names=self.scene.group_names, group_labels=self.scene.group_labels,
                 settings={k: clean(v) for k, v in self.settings.items()},
-                source_records=[{k: clean(v) for k, v in r.items()} for r in self.source_records])
+                source_records=[{k: clean(v) for k, v in r.items() if k != 'emit'} for r in self.source_records])
+    extra = {}
+    for i, r in enumerate(self.source_records):
+      if r.get('emit') is not None:
+        extra[f'emit_faces_{i}'], extra[f'emit_segs_{i}'] = r['emit'].faces, r['emit'].segs
     np.savez_compressed(path, faces=self.scene.faces, segs=self.scene.segs, shells=self.scene.shells,
                         groups=self.scene.groups, seq_offsets=self.scene.seq_offsets,
-                        seq_groups=self.scene.seq_groups, meta=np.array(json.dumps(meta)))
+                        seq_groups=self.scene.seq_groups, meta=np.array(json.dumps(meta)), **extra)
 
   # -- engine inputs
   def cfg(self, **overrides):
@@ -82,6 +89,19 @@ class PreparedSimulation:
     'SourceArgs (tables + odw_source_desc) of light source `index`; tables are built once'
     if index not in self._source_args:
       rec = self.source_records[index]
+      if rec['proxy'] == 'SurfaceSourceProxy':
+        emit = rec.get('emit')
+        if emit is None or not len(emit.faces):
+          raise NotImplementedError(f"surface source {rec['name']}: no emitting faces the engine can sample "
+                                    f"({rec.get('emit_error') or 'ActiveSurfaces empty'})")
+        tables = surface_source_tables(rec)
+        self._source_args[index] = _abi.SourceArgs(
+          tables, kind=SRC_SURFACE, source_id=rec['source_id'], gpM=np.eye(4), wavelength=float(rec['Wavelength']),
+          ignored=rec['ignored'], max_ray_length_scale=float(rec['MaxRayLengthScale']),
+          max_intersections_scale=float(rec['MaxIntersectionsScale']),
+          emit_faces=emit.faces, emit_segs=emit.segs, emit_cdf=emit.cdf,
+          dist_tol=max(float(self.settings['DistanceTolerance']), 1e-9))        # surface_source.py:113-119
+        return self._source_args[index]
       if rec['proxy'] != 'PointSourceProxy':
         raise NotImplementedError(f"source kind {rec['proxy']} has no device sampler yet")
       tables = point_source_tables(rec)

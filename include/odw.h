@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ODW_ABI_VERSION 1
+#define ODW_ABI_VERSION 2
 
 /* error codes */
 #define ODW_OK           0
@@ -74,6 +74,7 @@ extern "C" {
 /* source kinds */
 #define ODW_SRC_POINT_SPHERICAL  0   /* finite focal length: (theta, phi) sampling, point_source.py:424-435 */
 #define ODW_SRC_POINT_COLLIMATED 1   /* FocalLength = inf:   (r, phi) sampling,     point_source.py:438-446 */
+#define ODW_SRC_SURFACE          2   /* SurfaceSourceProxy: emission from faces,    surface_source.py:418-555 */
 
 /* One face instance in WORLD coordinates (placements/links/arrays already applied by the scene export:
  * M = gpM * pMi of ray.py:338-339 folded into origin/xdir/ydir/zdir).
@@ -169,6 +170,23 @@ typedef struct odw_source_desc {
   const double* phi_cdf;         /* [n_phi]  normalised to cdf[n_phi-1] == 1 */
   const double* first_cdf;       /* [n_rows][n_first] each row normalised */
   const int32_t* ignored_groups; /* [n_ignored] */
+  /* ---- surface sources only (kind == ODW_SRC_SURFACE; reference freecad_elements/surface_source.py:418-555) ----
+   * Per ray: pick an emitting face with probability proportional to its area (:465-466,536-537), draw a point
+   * uniformly by area inside the face's (u,v) window and redraw until it lies on the trimmed face within dist_tol
+   * (:390-410), draw theta from first_cdf (one row, edges linspace(first_lo, first_hi, n_first); NO sin(theta)
+   * factor, :530) and phi uniform in [0, 2pi) (:544), then
+   *   d = cos(theta) n + sin(theta) (cos(phi) (t x n) + sin(phi) t)        [= R(n,phi) R(t,theta) n, :85-111]
+   * with n the outward face normal and t the unit u-tangent (the longer of the u/v tangents when |dP/du| <= 10 dist_tol).
+   * phi_cdf, n_phi, n_rows, focal_length and gpM are ignored (the faces are given in WORLD coordinates: gpM*pMi of the
+   * emitting part already applied).  The reference tabulates the area element on an adaptively refined (u,v) grid
+   * (:269-387); the engine samples the area measure of the elementary surfaces in closed form instead — the same
+   * distribution without the table's discretisation error. */
+  int32_t n_emit;                /* emitting face instances */
+  int32_t n_emit_segs;
+  const odw_face* emit_faces;    /* [n_emit], world frame; group/shell fields unused */
+  const odw_trimseg* emit_segs;  /* [n_emit_segs] trim loops of the emitting faces */
+  const double* emit_cdf;        /* [n_emit] cumulative area weights, emit_cdf[n_emit-1] == 1 */
+  double dist_tol;               /* on-face tolerance, max(DistanceTolerance, 1e-9) (:113-119) */
 } odw_source_desc;
 
 /* Detector binning (new capability; semantics = numpy.histogram2d over plane-projected hit points as in

@@ -156,13 +156,14 @@ int oracle_sample_uniforms(const odw_source_desc* s, const double* u_phi, const 
   return 0;
 }
 
+static void source_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t ray, double* first, double* phi,
+                            double* origin, double* dir);
+
 int oracle_sample_mc(const odw_source_desc* s, uint64_t seed, uint64_t first_ray, uint64_t n,
                      double* first, double* phi, double* origins, double* dirs) {
   for (uint64_t i = 0; i < n; ++i) {
-    double u[2], f, p, o[3], d[3];
-    oracle_philox(seed, (uint32_t)s->source_id, first_ray + i, 0, u);
-    sample_from_uniforms(s, u[0], u[1], &f, &p);
-    make_ray(s, f, p, o, d);
+    double f, p, o[3], d[3];
+    source_make_ray(s, seed, first_ray + i, &f, &p, o, d);
     if (first) first[i] = f;
     if (phi) phi[i] = p;
     if (origins) memcpy(origins + 3*i, o, sizeof o);
@@ -422,6 +423,138 @@ static int trim_contains(const odw_face* f, const odw_trimseg* segs, double* uv,
     }
   }
   return crossings & 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* surface source: freecad_elements/surface_source.py:418-555 (_generateRays 'true'), :390-410
+ * (_drawRandomPositionOnFace), :85-111 (_makeRay).  The reference draws (u,v) from a tabulated area element
+ * (:269-387); here the area measure of the elementary surfaces is sampled in closed form (see include/odw.h). */
+
+/* point and first derivatives of the parametrisation (OCC's, see odw_face in odw.h) */
+static void surface_eval(const odw_face* f, double u, double v, double* P, double* du, double* dv) {
+  double cu = cos(u), su = sin(u);
+  double rad[3], tan_[3];
+  for (int i = 0; i < 3; ++i) { rad[i] = cu*f->xdir[i] + su*f->ydir[i]; tan_[i] = -su*f->xdir[i] + cu*f->ydir[i]; }
+  switch (f->kind) {
+    case ODW_SURF_PLANE:
+      for (int i = 0; i < 3; ++i) { P[i] = f->origin[i] + u*f->xdir[i] + v*f->ydir[i]; du[i] = f->xdir[i]; dv[i] = f->ydir[i]; }
+      break;
+    case ODW_SURF_CYLINDER:
+      for (int i = 0; i < 3; ++i) { P[i] = f->origin[i] + f->p0*rad[i] + v*f->zdir[i]; du[i] = f->p0*tan_[i]; dv[i] = f->zdir[i]; }
+      break;
+    case ODW_SURF_CONE: {
+      double sa = sin(f->p1), ca = cos(f->p1), r = f->p0 + v*sa;
+      for (int i = 0; i < 3; ++i) { P[i] = f->origin[i] + r*rad[i] + v*ca*f->zdir[i]; du[i] = r*tan_[i]; dv[i] = sa*rad[i] + ca*f->zdir[i]; }
+      break;
+    }
+    case ODW_SURF_SPHERE: {
+      double cv = cos(v), sv = sin(v), R = f->p0;
+      for (int i = 0; i < 3; ++i) { P[i] = f->origin[i] + R*cv*rad[i] + R*sv*f->zdir[i]; du[i] = R*cv*tan_[i]; dv[i] = -R*sv*rad[i] + R*cv*f->zdir[i]; }
+      break;
+    }
+    default: {   /* torus */
+      double cv = cos(v), sv = sin(v), R = f->p0, r = f->p1;
+      for (int i = 0; i < 3; ++i) { P[i] = f->origin[i] + (R + r*cv)*rad[i] + r*sv*f->zdir[i]; du[i] = (R + r*cv)*tan_[i]; dv[i] = -r*sv*rad[i] + r*cv*f->zdir[i]; }
+    }
+  }
+}
+
+/* (u,v) distributed by area inside the face's parameter window; returns 0 when the draw is rejected (cone, torus) */
+static int surface_draw_uv(const odw_face* f, double w0, double w1, double w2, double* u, double* v) {
+  double u0 = f->uv_min[0], u1 = f->uv_max[0], v0 = f->uv_min[1], v1 = f->uv_max[1];
+  if (f->trim_kind == ODW_TRIM_NONE) {
+    u0 = 0; u1 = TWO_PI;
+    if (f->kind == ODW_SURF_SPHERE) { v0 = -TWO_PI/4; v1 = TWO_PI/4; }
+    if (f->kind == ODW_SURF_TORUS) { v0 = 0; v1 = TWO_PI; }
+  }
+  *u = u0 + w0*(u1 - u0);
+  switch (f->kind) {
+    case ODW_SURF_SPHERE: {
+      double s0 = sin(v0), s1 = sin(v1), sv = s0 + w1*(s1 - s0);
+      if (sv > 1) sv = 1; if (sv < -1) sv = -1;
+      *v = asin(sv);
+      return 1;
+    }
+    case ODW_SURF_CONE: {
+      double sa = sin(f->p1), r0 = fabs(f->p0 + v0*sa), r1 = fabs(f->p0 + v1*sa);
+      double rmax = r0 > r1 ? r0 : r1;
+      *v = v0 + w1*(v1 - v0);
+      return w2*rmax < fabs(f->p0 + (*v)*sa);
+    }
+    case ODW_SURF_TORUS:
+      *v = v0 + w1*(v1 - v0);
+      return w2*(f->p0 + f->p1) < f->p0 + f->p1*cos(*v);
+    default:
+      *v = v0 + w1*(v1 - v0);
+      return 1;
+  }
+}
+
+#define ODW_SURFACE_MAX_TRIES 64
+static void surface_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t ray, double* theta_out, double* phi_out,
+                             double* origin, double* dir) {
+  double a[2], b[2];
+  oracle_philox(seed, (uint32_t)s->source_id, ray, 0, a);       /* a[0]: face, a[1]: theta */
+  oracle_philox(seed, (uint32_t)s->source_id, ray, 1, b);       /* b[0]: phi */
+  int k = 0;
+  while (k < s->n_emit-1 && !(a[0] < s->emit_cdf[k])) ++k;
+  const odw_face* f = &s->emit_faces[k];
+  double P[3], du[3], dv[3], u = 0, v = 0;
+  for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {
+    double w[2], w2[2];
+    oracle_philox(seed, (uint32_t)s->source_id, ray, 2 + tr, w);
+    oracle_philox(seed, (uint32_t)s->source_id, ray, 0x100 + tr, w2);
+    int ok = surface_draw_uv(f, w[0], w[1], w2[0], &u, &v);
+    surface_eval(f, u, v, P, du, dv);
+    if (!ok) continue;
+    double uv[2], n_tmp[3];
+    surface_uv_normal(f, P, uv, n_tmp);
+    if (trim_contains(f, s->emit_segs, uv, s->dist_tol)) break;   /* :399-408 keep rolling until the point is on the face */
+  }
+  double theta = interp_cdf(a[1], s->first_cdf, s->n_first, s->first_lo, s->first_hi);
+  double phi = b[0]*TWO_PI;                                        /* :544 */
+  double uv[2], n[3];
+  surface_uv_normal(f, P, uv, n);
+  /* :549 faceTangent = du if du.Length > 10 distTol else the longer of du, dv */
+  double lu = len3(du), lv = len3(dv);
+  const double* t = (lu > 10*s->dist_tol || lu >= lv) ? du : dv;
+  double tl = len3(t), th[3] = { t[0]/tl, t[1]/tl, t[2]/tl }, txn[3];
+  cross3(th, n, txn);
+  double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+  double d[3];
+  for (int i = 0; i < 3; ++i) d[i] = ct*n[i] + st*(cp*txn[i] + sp*th[i]);
+  double dl = len3(d);
+  for (int i = 0; i < 3; ++i) { origin[i] = P[i]; dir[i] = d[i]/dl; }
+  if (theta_out) *theta_out = theta;
+  if (phi_out) *phi_out = phi;
+}
+
+/* one Monte-Carlo ray of any source kind: the Philox stream (seed, source_id) at counter `ray` */
+static void source_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t ray, double* first, double* phi,
+                            double* origin, double* dir) {
+  if (s->kind == ODW_SRC_SURFACE) { surface_make_ray(s, seed, ray, first, phi, origin, dir); return; }
+  double u[2], f, p;
+  oracle_philox(seed, (uint32_t)s->source_id, ray, 0, u);
+  sample_from_uniforms(s, u[0], u[1], &f, &p);
+  make_ray(s, f, p, origin, dir);
+  if (first) *first = f;
+  if (phi) *phi = p;
+}
+
+int oracle_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(odw_face);
+    case 1: return (int)sizeof(odw_trimseg);
+    case 2: return (int)sizeof(odw_shell);
+    case 3: return (int)sizeof(odw_group);
+    case 4: return (int)sizeof(odw_scene_desc);
+    case 5: return (int)sizeof(odw_source_desc);
+    case 6: return (int)sizeof(odw_binning);
+    case 7: return (int)sizeof(odw_trace_cfg);
+    case 8: return (int)sizeof(odw_counts);
+    case 9: return (int)sizeof(odw_hits_view);
+  }
+  return -1;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -817,11 +950,9 @@ int oracle_trace_mc(const odw_scene_desc* sc, const odw_source_desc* src, const 
 #pragma omp for schedule(dynamic, 256)
 #endif
     for (int64_t i = 0; i < (int64_t)n; ++i) {
-      double u[2], f, p, o[3], d[3];
+      double o[3], d[3];
       uint64_t ray = first_ray + (uint64_t)i;
-      oracle_philox(seed, (uint32_t)src->source_id, ray, 0, u);
-      sample_from_uniforms(src, u[0], u[1], &f, &p);
-      make_ray(src, f, p, o, d);
+      source_make_ray(src, seed, ray, NULL, NULL, o, d);
       trace_one(sc, cfg, o, d, 1.0, src->wavelength, max_len, max_isect, src->ignored_groups, src->n_ignored,
                 ray, &sk, shell_c, face_c, &st, NULL, NULL, NULL);
     }

@@ -15,6 +15,12 @@ SCENES = {
   'lensesAndMirrors': 'benchmark/lensesAndMirrors.FCStd',
   'lensesAndMirrorsSequential': 'benchmark/lensesAndMirrorsSequential.FCStd',
   'hugeArray': 'benchmark/hugeArray.FCStd',
+  # reference test/21-simulation-modes: surface source (Box001.Face5, cos(theta)**2) -> sphere lens -> absorber box, sequential mode
+  'surfaceSourceTest21': 'test/21-simulation-modes/main.FCStd',
+  # reference test/50-old-tests: transmission/reflection grating and a Gaussian beam on a box detector
+  'grating': 'test/50-old-tests/grating.FCStd',
+  'gaussian': 'test/50-old-tests/gaussian.FCStd',
+  'gettingStarted': 'examples/1-getting-started/GettingStarted.FCStd',
 }
 
 def main():

@@ -28,19 +28,24 @@ def test_library_exports_every_declared_symbol():
   for n in names:
     assert hasattr(lib, n), f'{n} declared in include/odw.h but not exported by libodw_b200.so'
   assert set(names) == set(engine.EXPORTS)
-  assert lib.odw_abi_version() == 1
+  assert lib.odw_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
-  'numpy dtypes / ctypes structs mirror the C structs (sizes the kernels rely on)'
-  assert sc.FACE_DTYPE.itemsize == 224 and sc.SEG_DTYPE.itemsize == 48
-  assert sc.SHELL_DTYPE.itemsize == 64 and sc.GROUP_DTYPE.itemsize == 80
-  assert C.sizeof(_abi.SceneDesc) == 24+6*8
-  assert C.sizeof(_abi.Counts) == 64
-  assert C.sizeof(_abi.HitsView) == 72
-  assert C.sizeof(_abi.Binning) == 16+9*8+4*8
-  assert C.sizeof(_abi.SourceDesc) == 24+8*8+16*8+3*8
-  assert C.sizeof(_abi.TraceCfg) == 3*8+6*4+8+8
+  'numpy dtypes / ctypes structs mirror the C structs: sizes as the C compiler sees include/odw.h (via the oracle build)'
+  import ctypes
+  from oracle import Oracle
+  lib = Oracle().lib
+  lib.oracle_sizeof.restype = ctypes.c_int
+  csize = lambda which: lib.oracle_sizeof(which)
+  assert sc.FACE_DTYPE.itemsize == csize(0) == 224 and sc.SEG_DTYPE.itemsize == csize(1) == 48
+  assert sc.SHELL_DTYPE.itemsize == csize(2) == 64 and sc.GROUP_DTYPE.itemsize == csize(3) == 80
+  assert C.sizeof(_abi.SceneDesc) == csize(4)
+  assert C.sizeof(_abi.SourceDesc) == csize(5)
+  assert C.sizeof(_abi.Binning) == csize(6)
+  assert C.sizeof(_abi.TraceCfg) == csize(7)
+  assert C.sizeof(_abi.Counts) == csize(8) == 64
+  assert C.sizeof(_abi.HitsView) == csize(9) == 72
 
 
 @pytest.mark.skipif(os.environ.get('ODW_EXPECT_GPU') == '1', reason='GPU box')

@@ -108,6 +108,23 @@ def test_monte_carlo_hits_match_oracle(name, gpu_engine, oracle, sims):
     assert abs(gc['segments']-o['counts']['segments']) <= 100*bad
 
 
+@pytest.mark.parametrize('name', ['grating', 'gaussian', 'gettingStarted'])
+def test_reference_test_and_example_scenes_match_oracle(name, gpu_engine, oracle, sims):
+  '''
+  scenes of the reference's own tests / example (test/50-old-tests grating.FCStd, gaussian.FCStd; examples/1-getting-started):
+  gratings (wavelength plumbing, lineGrating), a mirror + plano-convex lens + absorber train
+  '''
+  sim = sims(name)
+  n = 30000
+  cfg = sim.cfg(record_all_hits=True, hit_capacity=12*n)
+  sa = sim.source_args(0)
+  with gpu_engine.scene(sim.scene).trace_mc(gpu_engine.source(sa), cfg, SEED, 0, n) as res:
+    gc, gh = res.counts, res.hits(sort=True)
+  o = oracle.trace_mc(sim.scene, sa, cfg, SEED, 0, n, hit_capacity=12*n, threads=0)
+  assert compare_hits(gh, o['hits'], n) == 0
+  assert gc == o['counts'] and gc['hits'] > n//2
+
+
 @pytest.mark.parametrize('name', ['minimal', 'lensesAndMirrors', 'lensesAndMirrorsSequential'])
 def test_recorded_hits_only(name, gpu_engine, oracle, sims):
   'default RecordHits flags: what the reference would store (absorber hits only)'
