@@ -386,6 +386,10 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   // so the expensive part (find nearest intersection) always runs with all live lanes together, no matter how
   // differently long the rays of a warp are.  Without this the lanes of a warp drift apart over the ~1e3 rays a
   // lane traces in a 1e8-ray launch and SIMT efficiency collapses.
+  // (Measured and rejected for the BVH path, where only ~6 of 32 lanes are active on hugeArray because traversal lengths
+  // differ wildly: alternating "traversal step" / "interaction" phases gated by the number of lanes still traversing.
+  // The interaction + ray-initialisation code then runs once per few traversal steps instead of once per bounce and
+  // costs more than the idle lanes it saves: 7.5e8 vs 9.3e8 segments/s.)
   unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
   // i = index of the lane's current ray; a lane starts "before" its first ray and steps by the grid size
   bool alive = false;
