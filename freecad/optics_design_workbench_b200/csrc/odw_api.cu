@@ -18,6 +18,15 @@ extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long 
                                          double* dirs, int blocks, cudaStream_t st);
 extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem);
 extern "C" int odw_trace_threads(void);
+// wavefront kernels (odw_wavefront.cu)
+extern "C" size_t odw_wf_pool_bytes_per_ray(void);
+extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, cudaStream_t st);
+extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
+                                       unsigned int* fetch_counter, int blocks, cudaStream_t st);
+extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap,
+                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st);
+extern "C" cudaError_t odw_wf_tail(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, int bounce, cudaStream_t st);
+extern "C" int odw_wf_traverse_occupancy(void);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -72,6 +81,7 @@ struct odw_scene {
   DScene d{};
   std::vector<void*> owned;
   bool use_bvh = false;
+  bool wavefront = true;                // BVH scenes: wavefront kernels (odw_wavefront.cu) instead of the register-resident kernel
   size_t smem = 0;
   int n_groups = 0;
   double extent = 0;                    // max |coordinate| over all face boxes
@@ -388,6 +398,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   if ((rc = upload(eng, sc->owned, groups.data(), groups.size(), &sc->d.groups))) { odw_scene_destroy(sc); return rc; }
   sc->d.n_faces = sd->n_faces; sc->d.n_segs = sd->n_segs; sc->d.n_groups = sd->n_groups; sc->d.n_seq_steps = sd->n_seq_steps;
   sc->use_bvh = sd->n_faces > SMEM_FACE_LIMIT;
+  if (const char* w = getenv("ODW_BVH")) { if (atoi(w) == 1 && sd->n_faces > 0) sc->use_bvh = true; }   // developer/test knob: BVH path for small scenes too
+  if (const char* w = getenv("ODW_WAVEFRONT")) sc->wavefront = atoi(w) != 0;
   if (sc->use_bvh) {
     BvhBuilder b(boxes);
     b.build();
@@ -617,6 +629,44 @@ static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
   for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
 }
 
+// One wave of the wavefront formulation (BVH scenes, see odw_wavefront.cu): generate, then per bounce traverse + interact
+// with the survivor count read back after every bounce (it sizes the next launches and ends the loop); once fewer than
+// `tail` rays are left they finish in one launch.
+static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, uint64_t* launches) {
+  const unsigned int n0 = (unsigned int)q.n_rays;
+  if (n0 == 0) return ODW_OK;
+  const size_t cap = n0;
+  void *pool_a = nullptr, *pool_b = nullptr, *hits = nullptr; unsigned int* ctr = nullptr;
+  int rc;
+  auto cleanup = [&]() { eng->release(pool_a); eng->release(pool_b); eng->release(hits); eng->release(ctr); };
+  if ((rc = eng->alloc(&pool_a, cap*odw_wf_pool_bytes_per_ray())) || (rc = eng->alloc(&pool_b, cap*odw_wf_pool_bytes_per_ray())) ||
+      (rc = eng->alloc(&hits, cap*16)) || (rc = eng->alloc((void**)&ctr, 16))) { cleanup(); return rc; }
+  unsigned int tail = 8192;
+  if (const char* w = getenv("ODW_WAVEFRONT_TAIL")) { long long v = atoll(w); if (v >= 0) tail = (unsigned int)v; }
+  const int blocks = eng->sm_count*std::max(1, odw_wf_traverse_occupancy());
+  cudaStream_t st = eng->stream;
+  unsigned int* host_n = reinterpret_cast<unsigned int*>(&eng->pinned_counters[0]);     // page-locked scratch
+  cudaError_t e = odw_wf_generate(&q, mc, pool_a, cap, n0, st);
+  if (launches) ++*launches;
+  unsigned int n = q.max_isect > 0 ? n0 : 0;
+  void *cur = pool_a, *nxt = pool_b;
+  for (int bounce = 0; e == cudaSuccess && n > 0; ++bounce) {
+    if (n <= tail) { e = odw_wf_tail(&q, mc, cur, cap, n, bounce, st); if (launches) ++*launches; break; }
+    if ((e = cudaMemsetAsync(ctr, 0, 16, st)) != cudaSuccess) break;                    // ctr[0] = survivors, ctr[1] = fetch counter
+    if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, blocks, st)) != cudaSuccess) break;
+    if ((e = odw_wf_interact(&q, mc, cur, hits, nxt, cap, n, ctr, bounce, st)) != cudaSuccess) break;
+    if (launches) *launches += 2;
+    if ((e = cudaMemcpyAsync(host_n, ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+    n = *host_n;
+    std::swap(cur, nxt);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);                                  // the pools go back to the allocator
+  cleanup();
+  if (e != cudaSuccess) return fail(ODW_ECUDA, std::string("wavefront trace: ") + cudaGetErrorString(e));
+  return ODW_OK;
+}
+
 // Issues the trace of p.n_rays rays as back-to-back launches on the engine stream (no synchronisation).
 static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams& p, bool mc, uint64_t* launches) {
   int per_sm = odw_trace_occupancy(mc, sc->use_bvh, sc->smem);
@@ -628,8 +678,9 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   // instruction working set no longer fits the shared instruction cache levels and the kernel slows down by ~35 %
   // (measured on B200, lensesAndMirrors: 1e8 rays in one launch 146 ms, in 48 launches of 2^21 rays 106 ms).  Launches are
   // asynchronous on one stream, so there is no host gap between them.
-  uint64_t wave = sc->use_bvh ? (1ull << 24) : (1ull << 21);   // BVH scenes have long per-launch tails (uneven ray depth)
+  uint64_t wave = sc->use_bvh ? (1ull << 24) : (1ull << 21);   // BVH scenes: big waves amortise the per-bounce host round trip
   if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
+  wave = std::min<uint64_t>(wave, 1ull << 31);
   for (uint64_t off = 0; off < p.n_rays; off += wave) {
     TraceParams q = p;
     q.n_rays = std::min<uint64_t>(wave, p.n_rays - off);
@@ -640,6 +691,11 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
       if (p.out_nseg) q.out_nseg = p.out_nseg + off;
       if (p.out_final_point) q.out_final_point = p.out_final_point + 3*off;
       if (p.out_final_power) q.out_final_power = p.out_final_power + off;
+    }
+    if (sc->use_bvh && sc->wavefront) {
+      int rc = run_wavefront_wave(eng, q, mc, launches);
+      if (rc) return rc;
+      continue;
     }
     const uint64_t tpb = (uint64_t)odw_trace_threads();
     uint64_t want_w = (q.n_rays + tpb - 1)/tpb;

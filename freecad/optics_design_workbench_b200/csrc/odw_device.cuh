@@ -118,7 +118,8 @@ struct TraceParams {
   float origin_bound;                // max |coordinate| of any ray origin of this launch (host-side bound)
 };
 
-#ifdef ODW_DEVICE_CODE   // device functions: only the kernel translation unit defines this
+#ifdef ODW_DEVICE_CODE   // device functions: only the kernel translation units define this
+namespace {              // internal linkage: two translation units (odw_kernels.cu, odw_wavefront.cu) include these definitions
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
 __device__ __forceinline__ double dot3(double ax, double ay, double az, const double* b) { return ax*b[0]+ay*b[1]+az*b[2]; }
@@ -587,4 +588,5 @@ __device__ __noinline__ Vec3 line_grating(double rx, double ry, double rz, doubl
   Vec3 r; r.x = out[0]; r.y = out[1]; r.z = out[2];
   return r;
 }
+}  // namespace
 #endif  // ODW_DEVICE_CODE

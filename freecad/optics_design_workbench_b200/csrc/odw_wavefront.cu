@@ -1,0 +1,321 @@
+// odw_wavefront.cu — wavefront trace kernels for scenes that need the BVH (hundreds of faces and more).
+//
+// Why a second formulation: in the register-resident kernel (odw_kernels.cu) a warp does one bounce per iteration and
+// waits for its slowest lane.  With a BVH the traversal lengths of the 32 rays of a warp differ wildly (a ray that misses
+// everything visits a handful of nodes, one threading a lattice of spheres hundreds): on benchmark/hugeArray.FCStd only
+// 4 of 32 lanes were active on average (profiles/r01_v7_trace_hugeArray_raw.json).  Here the bounce loop of
+// Ray.traceRay (reference freecad_elements/ray.py:91-281) is cut at findNearestIntersection:
+//
+//   wf_generate   rays of the wave -> ray pool in HBM (SoA of 16-byte columns: coalesced 128-bit loads / stores)
+//   per bounce:
+//     wf_traverse   persistent warps; a lane whose traversal ended stores (t, face) and immediately takes the next ray
+//                   of the pool (warp-aggregated atomic on the fetch counter), so every lane always traverses
+//     wf_interact   one lane per ray: hit -> normal / Snell / mirror / grating / absorber, hit append, survivors are
+//                   compacted into the other pool (warp ballot + one atomic per warp)
+//   wf_tail       the last few thousand survivors of a wave finish in one launch (one lane per ray, whole bounce loop)
+//
+// HBM traffic per segment is the wavefront figure of SURVEY.md §8d (ray state read + written once per bounce).
+#include "odw_trace.cuh"
+
+// ---- ray pool ------------------------------------------------------------------------------
+struct WfPool {
+  double2* a0;       // (ox, oy)
+  double2* a1;       // (oz, dx)
+  double2* a2;       // (dy, dz)          d = unit direction
+  double2* a3;       // (power, dscale)
+  ulonglong2* a4;    // (ray number inside the launch, medium | seq_index << 32)
+};
+
+struct WfRay {
+  double point[3], dn[3], power, dscale;
+  unsigned long long i;
+  int medium, seq_index;
+};
+
+__device__ __forceinline__ void pool_store(const WfPool& pl, unsigned int slot, const double* point, const double* dn,
+                                           double power, double dscale, unsigned long long i, int medium, int seq_index) {
+  pl.a0[slot] = make_double2(point[0], point[1]);
+  pl.a1[slot] = make_double2(point[2], dn[0]);
+  pl.a2[slot] = make_double2(dn[1], dn[2]);
+  pl.a3[slot] = make_double2(power, dscale);
+  pl.a4[slot] = make_ulonglong2(i, (unsigned long long)(unsigned int)medium | ((unsigned long long)(unsigned int)seq_index << 32));
+}
+
+// ---- resumable BVH traversal, "while-while" form --------------------------------------------------------------
+// Same rule as find_nearest_bvh (odw_trace.cuh), split so that the lanes of a warp spend their time in the same code:
+// `cur` is the lane's next work item: an inner node (>= 0), a leaf (<= -2, first primitive and count packed) or
+// TRAV_DONE.  The kernel first lets every lane descend through inner nodes (cheap fp32 box tests) until each holds a
+// leaf or is done, then all lanes holding a leaf run the exact fp64 face tests together.  Testing a leaf the moment it
+// is found (as find_nearest_bvh does) left 7 of 32 lanes active: every lane sat in a different part of the step.
+#define TRAV_DONE (-1)
+struct BvhTrav {
+  NearestHit h;
+  float sx, sy, sz, ix, iy, iz, limf;
+  int cur, sp;
+  int stack_ref[ODW_BVH_STACK];
+  float stack_t[ODW_BVH_STACK];
+};
+
+__device__ __forceinline__ int leaf_ref(int first, int count) { return -2 - ((first << 4) | count); }
+
+__device__ __forceinline__ void bvh_begin(BvhTrav& tr, const TraceParams& p, const double* s, const double* dn) {
+  const double tmax = p.max_len + p.tol;
+  tr.h.tA = 1e300; tr.h.tB = 1e300; tr.h.lim = tmax; tr.h.fA = -1; tr.h.fB = -1;
+  tr.sx = (float)s[0]; tr.sy = (float)s[1]; tr.sz = (float)s[2];
+  tr.ix = __frcp_rn((float)dn[0]); tr.iy = __frcp_rn((float)dn[1]); tr.iz = __frcp_rn((float)dn[2]);
+  tr.limf = (float)tmax*1.000002f;
+  tr.cur = 0; tr.sp = 0;
+}
+
+// next stacked item that can still matter
+__device__ __forceinline__ int bvh_pop(BvhTrav& tr) {
+  while (tr.sp > 0) {
+    --tr.sp;
+    if (tr.stack_t[tr.sp] <= tr.limf) return tr.stack_ref[tr.sp];
+  }
+  return TRAV_DONE;
+}
+
+// cur is an inner node: test both children, go to the nearer one, stack the other
+__device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const TraceParams& p) {
+  const float sx = tr.sx, sy = tr.sy, sz = tr.sz, ix = tr.ix, iy = tr.iy, iz = tr.iz;
+  const float4* q = reinterpret_cast<const float4*>(p.scene.bvh + tr.cur);
+  const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  const int4 d = __ldg(reinterpret_cast<const int4*>(q + 3));
+  // child 0: lo = (a.x, a.y, a.z), hi = (a.w, b.x, b.y);  child 1: lo = (b.z, b.w, c.x), hi = (c.y, c.z, c.w)
+  float ta = (a.x - sx)*ix, tb = (a.w - sx)*ix;
+  float n0 = fminf(ta, tb), f0 = fmaxf(ta, tb);
+  ta = (a.y - sy)*iy; tb = (b.x - sy)*iy;
+  n0 = fmaxf(n0, fminf(ta, tb)); f0 = fminf(f0, fmaxf(ta, tb));
+  ta = (a.z - sz)*iz; tb = (b.y - sz)*iz;
+  n0 = fmaxf(n0, fminf(ta, tb)); f0 = fminf(f0, fmaxf(ta, tb));
+  ta = (b.z - sx)*ix; tb = (c.y - sx)*ix;
+  float n1 = fminf(ta, tb), f1 = fmaxf(ta, tb);
+  ta = (b.w - sy)*iy; tb = (c.z - sy)*iy;
+  n1 = fmaxf(n1, fminf(ta, tb)); f1 = fminf(f1, fmaxf(ta, tb));
+  ta = (c.x - sz)*iz; tb = (c.w - sz)*iz;
+  n1 = fmaxf(n1, fminf(ta, tb)); f1 = fminf(f1, fmaxf(ta, tb));
+  const bool hit0 = d.z >= 0 && n0 <= f0 && f0 >= 0.0f && n0 <= tr.limf;
+  const bool hit1 = d.w >= 0 && n1 <= f1 && f1 >= 0.0f && n1 <= tr.limf;
+  const int r0 = d.z > 0 ? leaf_ref(d.x, d.z) : d.x, r1 = d.w > 0 ? leaf_ref(d.y, d.w) : d.y;
+  if (hit0 && hit1) {
+    const bool first0 = n0 <= n1;
+    if (tr.sp < ODW_BVH_STACK) { tr.stack_ref[tr.sp] = first0 ? r1 : r0; tr.stack_t[tr.sp] = first0 ? n1 : n0; ++tr.sp; }
+    tr.cur = first0 ? r0 : r1;
+  } else if (hit0) tr.cur = r0;
+  else if (hit1) tr.cur = r1;
+  else tr.cur = bvh_pop(tr);
+}
+
+// cur is a leaf: exact fp64 tests of its faces
+__device__ __forceinline__ void bvh_leaf_step(BvhTrav& tr, const TraceParams& p, const double* s, const double* dn, int medium, int seq_index) {
+  const int packed = -2 - tr.cur, first = packed >> 4, count = packed & 15;
+  const double tmax = p.max_len + p.tol;
+  for (int k = 0; k < count; ++k) {
+    const int fi = __ldg(p.scene.bvh_prims + first + k);
+    test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, tr.h);
+  }
+  tr.limf = (float)tr.h.lim*1.000002f;
+  tr.cur = bvh_pop(tr);
+}
+
+__device__ __forceinline__ void flush_counters(const TraceParams& p, const unsigned int* s_cnt) {
+  if (s_cnt[CNT_SEGMENTS]) atomicAdd(&p.counters->segments, (unsigned long long)s_cnt[CNT_SEGMENTS]);
+  if (!p.store_hits && s_cnt[CNT_HITS]) atomicAdd(&p.counters->hits, (unsigned long long)s_cnt[CNT_HITS]);
+  if (s_cnt[CNT_DROPPED]) atomicAdd(&p.counters->hits_dropped, (unsigned long long)s_cnt[CNT_DROPPED]);
+  if (s_cnt[CNT_ESCAPED]) atomicAdd(&p.counters->escaped, (unsigned long long)s_cnt[CNT_ESCAPED]);
+  if (s_cnt[CNT_DEPTH]) atomicAdd(&p.counters->depth_terminated, (unsigned long long)s_cnt[CNT_DEPTH]);
+}
+
+// ---- kernels -------------------------------------------------------------------------------
+// rays [0, n) of the launch -> pool slots [0, n)
+template <bool MC>
+__global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ TraceParams p, WfPool pool, unsigned int n) {
+  __shared__ unsigned int s_cnt[CNT_N];
+  if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
+  if (idx < n) {
+    double point[3], dn[3], dscale = 1, power = 0;
+    int medium = -1, seq_index = 0, n_isect = 0;
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+    fetch_ray<MC>(p, idx, r);
+    if (p.max_isect <= 0) {                                                      // ray.py:96-98 before the first segment
+      atomicAdd(&s_cnt[CNT_DEPTH], 1u);
+      finish_ray<MC>(p, idx, r, s_cnt);
+    } else {
+      pool_store(pool, idx, point, dn, power, dscale, idx, medium, seq_index);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flush_counters(p, s_cnt);
+}
+
+// nearest intersection of every ray of the pool: hits[slot] = (t, face index | -1)
+__global__ void __launch_bounds__(256, 3) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
+                                                      unsigned int n, unsigned int* fetch_counter) {
+  const unsigned int lane = threadIdx.x & 31u;
+  bool have = false, exhausted = false;
+  unsigned int slot = 0;
+  double s[3] = {0, 0, 0}, dn[3] = {0, 0, 1};
+  int medium = -1, seq_index = 0;
+  BvhTrav tr;
+  tr.cur = TRAV_DONE; tr.sp = 0;
+  for (;;) {
+    const unsigned int need = __ballot_sync(0xffffffffu, !have);
+    if (need && !exhausted) {
+      // lanes without a ray take the next pool slots: one atomic per warp
+      const int leader = __ffs(need) - 1;
+      unsigned int base = 0;
+      if ((int)lane == leader) base = atomicAdd(fetch_counter, (unsigned int)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (!have) {
+        slot = base + __popc(need & ((1u << lane) - 1u));
+        if (slot < n) {
+          const double2 a0 = pool.a0[slot], a1 = pool.a1[slot], a2 = pool.a2[slot];
+          const ulonglong2 a4 = pool.a4[slot];
+          s[0] = a0.x; s[1] = a0.y; s[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
+          medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
+          bvh_begin(tr, p, s, dn);
+          have = true;
+        }
+      }
+      exhausted = base + (unsigned int)__popc(need) >= n;
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    // descend: every lane walks inner nodes until it holds a leaf or has finished
+    while (__any_sync(0xffffffffu, have && tr.cur >= 0)) {
+      if (have && tr.cur >= 0) bvh_inner_step(tr, p);
+    }
+    // leaves: exact face tests, all lanes that hold one together
+    if (have && tr.cur < TRAV_DONE) bvh_leaf_step(tr, p, s, dn, medium, seq_index);
+    if (have && tr.cur == TRAV_DONE) {
+      const double tol = p.tol;
+      double t = 0; int fi = -1;
+      if (tr.h.fA >= 0) {                                                        // final choice, ray.py:438-452
+        if (tr.h.fB >= 0 && tr.h.tB < tr.h.tA + 2*tol) { t = tr.h.tB; fi = tr.h.fB; } else { t = tr.h.tA; fi = tr.h.fA; }
+      }
+      hits[slot] = make_double2(t, __longlong_as_double((long long)fi));
+      have = false;
+    }
+  }
+}
+
+// surface interaction of every ray of pool_in with its hit; survivors are appended to pool_out
+template <bool MC>
+__global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ TraceParams p, WfPool pool_in, const double2* __restrict__ hits,
+                                                   WfPool pool_out, unsigned int n, unsigned int* n_next, int bounce) {
+  __shared__ unsigned int s_cnt[CNT_N];
+  if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
+  bool survive = false;
+  double point[3], dn[3], dscale = 1, power = 0;
+  int medium = -1, seq_index = 0, n_isect = bounce + 1;          // every ray of this wave has done `bounce` segments before
+  unsigned long long i = 0;
+  if (idx < n) {
+    const double2 a0 = pool_in.a0[idx], a1 = pool_in.a1[idx], a2 = pool_in.a2[idx], a3 = pool_in.a3[idx];
+    const ulonglong2 a4 = pool_in.a4[idx];
+    const double2 h = hits[idx];
+    point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
+    power = a3.x; dscale = a3.y; i = a4.x;
+    medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+    bool done = interact<MC>(p, p.scene.faces, p.scene.groups, (int)__double_as_longlong(h.y), h.x, i, r, s_cnt);
+    if (!done && n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); done = true; }   // ray.py:96-98
+    if (done) finish_ray<MC>(p, i, r, s_cnt);
+    survive = !done;
+  }
+  // compaction: one atomic per warp (warp ballot + prefix count)
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int alive = __ballot_sync(0xffffffffu, survive);
+  if (alive) {
+    const int leader = __ffs(alive) - 1;
+    unsigned int base = 0;
+    if ((int)lane == leader) base = atomicAdd(n_next, (unsigned int)__popc(alive));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (survive) pool_store(pool_out, base + __popc(alive & ((1u << lane) - 1u)), point, dn, power, dscale, i, medium, seq_index);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flush_counters(p, s_cnt);
+}
+
+// the last survivors of a wave: one lane per ray runs the rest of its bounce loop
+template <bool MC>
+__global__ void __launch_bounds__(256) wf_tail(const __grid_constant__ TraceParams p, WfPool pool, unsigned int n, int bounce) {
+  __shared__ unsigned int s_cnt[CNT_N];
+  if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
+  if (idx < n) {
+    double point[3], dn[3], dscale, power;
+    int medium, seq_index, n_isect = bounce;
+    const double2 a0 = pool.a0[idx], a1 = pool.a1[idx], a2 = pool.a2[idx], a3 = pool.a3[idx];
+    const ulonglong2 a4 = pool.a4[idx];
+    point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
+    power = a3.x; dscale = a3.y;
+    const unsigned long long i = a4.x;
+    medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+    for (;;) {
+      if (n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); break; }
+      ++n_isect;
+      double t;
+      const int fi = find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t);
+      if (interact<MC>(p, p.scene.faces, p.scene.groups, fi, t, i, r, s_cnt)) break;
+    }
+    finish_ray<MC>(p, i, r, s_cnt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) flush_counters(p, s_cnt);
+}
+
+// ---- launch helpers used by odw_api.cu ---------------------------------------------------------
+extern "C" size_t odw_wf_pool_bytes_per_ray(void) { return 4*sizeof(double2) + sizeof(ulonglong2); }
+
+static WfPool make_pool(void* base, size_t cap) {
+  WfPool pl;
+  char* b = static_cast<char*>(base);
+  pl.a0 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
+  pl.a1 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
+  pl.a2 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
+  pl.a3 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
+  pl.a4 = reinterpret_cast<ulonglong2*>(b);
+  return pl;
+}
+
+extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, cudaStream_t st) {
+  const WfPool pl = make_pool(pool, cap);
+  const unsigned int blocks = (n + 255u)/256u;
+  if (mc) wf_generate<true><<<blocks, 256, 0, st>>>(*p, pl, n); else wf_generate<false><<<blocks, 256, 0, st>>>(*p, pl, n);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
+                                       unsigned int* fetch_counter, int blocks, cudaStream_t st) {
+  const unsigned int want = (n + 255u)/256u;
+  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap,
+                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st) {
+  const unsigned int blocks = (n + 255u)/256u;
+  const WfPool pi = make_pool(pool_in, cap), po = make_pool(pool_out, cap);
+  if (mc) wf_interact<true><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
+  else wf_interact<false><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
+  return cudaGetLastError();
+}
+
+extern "C" cudaError_t odw_wf_tail(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, int bounce, cudaStream_t st) {
+  const unsigned int blocks = (n + 255u)/256u;
+  if (mc) wf_tail<true><<<blocks, 256, 0, st>>>(*p, make_pool(pool, cap), n, bounce);
+  else wf_tail<false><<<blocks, 256, 0, st>>>(*p, make_pool(pool, cap), n, bounce);
+  return cudaGetLastError();
+}
+
+extern "C" int odw_wf_traverse_occupancy(void) {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_traverse, 256, 0);
+  return nb;
+}

@@ -37,7 +37,7 @@ def build_library(force=False):
   'compile csrc/*.cu for sm_100a in-tree (nvcc cross-compiles without a GPU)'
   import subprocess
   srcdir = os.path.join(_HERE, 'csrc')
-  deps = [os.path.join(srcdir, f) for f in ('odw_kernels.cu', 'odw_api.cu', 'odw_device.cuh')]
+  deps = [os.path.join(srcdir, f) for f in ('odw_kernels.cu', 'odw_wavefront.cu', 'odw_api.cu', 'odw_device.cuh', 'odw_trace.cuh')]
   deps.append(os.path.join(_HERE, '..', '..', 'include', 'odw.h'))
   stale = not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
   if force or stale:

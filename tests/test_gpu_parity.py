@@ -335,3 +335,37 @@ def test_full_size_properties(gpu_engine, sims):
   assert np.unique(h['ray_index']).size == c['hits']  # one recorded hit per ray at most
   # beam centre and symmetric spread on the detector (on-axis answer of SURVEY.md Appendix B)
   assert abs(h['points'][on_box, 0].mean()+68.857864) < 1e-3 and abs(h['points'][on_box, 1].mean()) < 1e-3
+
+
+@pytest.mark.parametrize('tail', ['0', '100000000'])
+def test_wavefront_kernels_equal_register_resident_kernel(gpu_engine, oracle, sims, monkeypatch, tail):
+  '''
+  The two formulations of the trace (odw_kernels.cu: one lane owns a ray for life; odw_wavefront.cu: generate /
+  traverse / interact per bounce through a ray pool in HBM) must produce the same hits.  ODW_BVH=1 sends a small scene
+  down the BVH path; tail = 0: every bounce through traverse + interact, tail = huge: everything in the tail kernel.
+  '''
+  sim = sims('lensesAndMirrors')
+  sa = sim.source_args(0)
+  n = 40000
+  cfg = sim.cfg(record_all_hits=True, hit_capacity=10*n)
+  with gpu_engine.scene(sim.scene).trace_mc(gpu_engine.source(sa), cfg, SEED, 5000, n) as res:
+    c0, h0 = res.counts, res.hits(sort=True)
+  monkeypatch.setenv('ODW_BVH', '1')
+  monkeypatch.setenv('ODW_WAVEFRONT', '1')
+  monkeypatch.setenv('ODW_WAVEFRONT_TAIL', tail)
+  ds = gpu_engine.scene(sim.scene)                       # the knobs are read when the scene is created / traced
+  with ds.trace_mc(gpu_engine.source(sa), cfg, SEED, 5000, n) as res:
+    c1, h1 = res.counts, res.hits(sort=True)
+  o_, d_ = explicit_fan(n=5000, spread=0.05)
+  d_ = d_*np.linspace(0.5, 2.0, len(d_))[:, None]
+  cfg2 = sim.cfg(record_all_hits=True, hit_capacity=20*len(d_))
+  with ds.trace_rays(cfg2, o_, d_) as res:
+    c3, h3, s3 = res.counts, res.hits(sort=True), res.ray_summary()
+  monkeypatch.delenv('ODW_BVH'); monkeypatch.delenv('ODW_WAVEFRONT'); monkeypatch.delenv('ODW_WAVEFRONT_TAIL')
+  for k in ('rays', 'segments', 'hits', 'escaped', 'depth_terminated'):
+    assert c0[k] == c1[k], k
+  assert compare_hits(h1, h0, n, base=5000) == 0
+  o = oracle.trace_rays(sim.scene, cfg2, o_, d_, hit_capacity=20*len(d_))
+  assert compare_hits(h3, o['hits'], len(d_)) == 0
+  assert np.array_equal(s3['n_segments'], o['n_segments'])
+  assert np.abs(s3['final_points']-o['final_points']).max() < 1e-6
