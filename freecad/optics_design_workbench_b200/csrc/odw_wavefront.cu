@@ -152,7 +152,10 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 }
 
 // nearest intersection of every ray of the pool: hits[slot] = (t, face index | -1)
-__global__ void __launch_bounds__(256, 3) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
+#ifndef ODW_WF_BLOCKS
+#define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
+#endif
+__global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
                                                       unsigned int n, unsigned int* fetch_counter) {
   const unsigned int lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;
