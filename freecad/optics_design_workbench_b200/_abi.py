@@ -18,7 +18,14 @@ class SceneDesc(C.Structure):
   _fields_ = [('n_faces', C.c_int32), ('n_segs', C.c_int32), ('n_shells', C.c_int32), ('n_groups', C.c_int32),
               ('n_seq_steps', C.c_int32), ('n_seq_entries', C.c_int32),
               ('faces', C.c_void_p), ('segs', C.c_void_p), ('shells', C.c_void_p), ('groups', C.c_void_p),
-              ('seq_offsets', C.c_void_p), ('seq_groups', C.c_void_p)]
+              ('seq_offsets', C.c_void_p), ('seq_groups', C.c_void_p),
+              ('n_scatters', C.c_int32), ('pad0', C.c_int32), ('scatters', C.c_void_p), ('group_scatter', C.c_void_p)]
+
+
+class Scatter(C.Structure):
+  _fields_ = [('n_first', C.c_int32), ('n_phi', C.c_int32), ('n_rows', C.c_int32), ('pad', C.c_int32),
+              ('first_lo', C.c_double), ('first_hi', C.c_double), ('phi_lo', C.c_double), ('phi_hi', C.c_double),
+              ('phi_cdf', C.c_void_p), ('first_cdf', C.c_void_p)]
 
 
 class SourceDesc(C.Structure):
@@ -43,7 +50,7 @@ class TraceCfg(C.Structure):
   _fields_ = [('max_ray_length', C.c_double), ('dist_tol', C.c_double), ('power_tol', C.c_double),
               ('max_intersections', C.c_int32), ('sequential', C.c_int32), ('record_all_hits', C.c_int32),
               ('store_hits', C.c_int32), ('n_binnings', C.c_int32), ('bounces_per_wave', C.c_int32),
-              ('hit_capacity', C.c_uint64), ('binnings', C.c_void_p)]
+              ('hit_capacity', C.c_uint64), ('binnings', C.c_void_p), ('scatter_seed', C.c_uint64)]
 
 
 class Counts(C.Structure):
@@ -75,6 +82,16 @@ class SceneArgs:
     d.faces, d.segs = _ptr(scene.faces), _ptr(scene.segs)
     d.shells, d.groups = _ptr(scene.shells), _ptr(scene.groups)
     d.seq_offsets, d.seq_groups = _ptr(scene.seq_offsets), _ptr(scene.seq_groups)
+    tables = list(getattr(scene, 'scatters', []) or [])
+    if tables:
+      self.scatters = (Scatter*len(tables))()
+      for sct, t in zip(self.scatters, tables):
+        sct.n_first, sct.n_phi, sct.n_rows = t.first_cdf.shape[1], t.phi_cdf.shape[0], t.first_cdf.shape[0]
+        sct.first_lo, sct.first_hi = t.first_domain
+        sct.phi_lo, sct.phi_hi = t.phi_domain
+        sct.phi_cdf, sct.first_cdf = _ptr(t.phi_cdf), _ptr(t.first_cdf)
+      self.group_scatter = np.ascontiguousarray(scene.group_scatter, dtype=np.int32).reshape(len(scene.groups), 2)
+      d.n_scatters, d.scatters, d.group_scatter = len(tables), C.addressof(self.scatters), _ptr(self.group_scatter)
     self.desc = d
 
 
@@ -113,7 +130,7 @@ class SourceArgs:
 class CfgArgs:
   def __init__(self, *, max_ray_length=1000.0, dist_tol=1e-6, power_tol=1e-6, max_intersections=100,
                sequential=False, record_all_hits=False, store_hits=True, binnings=(), bounces_per_wave=0,
-               hit_capacity=0):
+               hit_capacity=0, scatter_seed=0):
     self.binnings = (Binning*max(1, len(binnings)))()
     for i, b in enumerate(binnings):
       bb = self.binnings[i]
@@ -134,6 +151,7 @@ class CfgArgs:
     c.bounces_per_wave = int(bounces_per_wave)
     c.hit_capacity = int(hit_capacity)
     c.binnings = C.addressof(self.binnings) if len(binnings) else None
+    c.scatter_seed = int(scatter_seed)
     self.cfg = c
 
 

@@ -290,6 +290,8 @@ struct BvhBuilder {
 };
 }  // namespace
 
+static std::vector<uint32_t> build_guide(const double* cdf, int n);
+
 // odw_face -> the record the kernels read.  fast_paths: precompute the inline-test constants of the trace kernel
 // (emitting faces of a surface source are only evaluated / trim-tested, never intersected: no fast paths there).
 static void fill_dface(const odw_face& f, const odw_trimseg* segs, bool fast_paths, DFace& d) {
@@ -387,6 +389,16 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     d.lpm = g.grating_lines_per_mm; d.order = g.grating_order;
     for (int k = 0; k < 3; ++k) d.gdir[k] = g.grating_orientation[k];
     d.type = g.optical_type; d.record = g.record_hits; d.gtype = g.grating_type; d.pad = 0;
+    d.scat_main = d.scat_modify = -1; d.pad1 = d.pad2 = 0;
+    if (sd->n_scatters > 0 && sd->group_scatter && (g.optical_type == ODW_OPT_MIRROR || g.optical_type == ODW_OPT_LENS)) {
+      d.scat_main = sd->group_scatter[2*i]; d.scat_modify = sd->group_scatter[2*i+1];
+      if (d.scat_main >= sd->n_scatters || d.scat_modify >= sd->n_scatters) return fail(ODW_EINVAL, "group " + std::to_string(i) + ": scatter index out of range");
+    }
+  }
+  for (int i = 0; i < sd->n_scatters; ++i) {
+    const odw_scatter& t = sd->scatters[i];
+    if (t.n_first < 2 || t.n_phi < 2 || !t.phi_cdf || !t.first_cdf || (t.n_rows != 1 && t.n_rows != t.n_phi - 1))
+      return fail(ODW_EINVAL, "scatter " + std::to_string(i) + ": malformed tables");
   }
   odw_scene* sc = new odw_scene();
   sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
@@ -396,6 +408,21 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   sc->d.n_shells = (int)shells.size();
   if ((rc = upload(eng, sc->owned, sd->segs, (size_t)sd->n_segs, &sc->d.segs))) { odw_scene_destroy(sc); return rc; }
   if ((rc = upload(eng, sc->owned, groups.data(), groups.size(), &sc->d.groups))) { odw_scene_destroy(sc); return rc; }
+  if (sd->n_scatters > 0) {
+    std::vector<DScatter> scat((size_t)sd->n_scatters);
+    for (int i = 0; i < sd->n_scatters; ++i) {
+      const odw_scatter& t = sd->scatters[i]; DScatter& d = scat[(size_t)i];
+      if ((rc = upload(eng, sc->owned, t.phi_cdf, (size_t)t.n_phi, &d.phi_cdf))) { odw_scene_destroy(sc); return rc; }
+      if ((rc = upload(eng, sc->owned, t.first_cdf, (size_t)t.n_rows*t.n_first, &d.first_cdf))) { odw_scene_destroy(sc); return rc; }
+      std::vector<uint32_t> pg = build_guide(t.phi_cdf, t.n_phi), fg;
+      for (int r = 0; r < t.n_rows; ++r) { std::vector<uint32_t> g = build_guide(t.first_cdf + (size_t)r*t.n_first, t.n_first); fg.insert(fg.end(), g.begin(), g.end()); }
+      if ((rc = upload(eng, sc->owned, pg.data(), pg.size(), &d.phi_guide))) { odw_scene_destroy(sc); return rc; }
+      if ((rc = upload(eng, sc->owned, fg.data(), fg.size(), &d.first_guide))) { odw_scene_destroy(sc); return rc; }
+      d.first_lo = t.first_lo; d.first_hi = t.first_hi; d.phi_lo = t.phi_lo; d.phi_hi = t.phi_hi;
+      d.n_first = t.n_first; d.n_phi = t.n_phi; d.n_rows = t.n_rows; d.pad = 0;
+    }
+    if ((rc = upload(eng, sc->owned, scat.data(), scat.size(), &sc->d.scatters))) { odw_scene_destroy(sc); return rc; }
+  }
   sc->d.n_faces = sd->n_faces; sc->d.n_segs = sd->n_segs; sc->d.n_groups = sd->n_groups; sc->d.n_seq_steps = sd->n_seq_steps;
   sc->use_bvh = sd->n_faces > SMEM_FACE_LIMIT;
   if (const char* w = getenv("ODW_BVH")) { if (atoi(w) == 1 && sd->n_faces > 0) sc->use_bvh = true; }   // developer/test knob: BVH path for small scenes too
@@ -879,6 +906,7 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   p.in_origins = r->d_in_o; p.in_dirs = r->d_in_d; p.in_powers = powers ? r->d_in_p : nullptr;
   p.out_nseg = r->d_nseg; p.out_final_point = r->d_final_point; p.out_final_power = r->d_final_power;
   p.first_ray = 0;
+  p.seed = cfg->scatter_seed; p.src.source_id = 0;       // Philox stream of the stochastic-surface draws of an explicit list
   p.wavelength = 500.0;
   set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0);
   double origin_bound = 0;

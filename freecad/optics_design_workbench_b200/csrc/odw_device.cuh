@@ -39,6 +39,17 @@ struct DShell {                    // 64 B
 struct DGroup {
   double n, reflectivity, absorption_length, lpm, order, gdir[3];
   int32_t type, record, gtype, pad;
+  int32_t scat_main, scat_modify, pad1, pad2;   // stochastic surface model: indices into DScene::scatters, -1 = ideal
+};
+
+// tabulated (theta, phi) density of a stochastic surface model; field names as in DSource so that the samplers are shared
+struct DScatter {
+  const double* phi_cdf;
+  const double* first_cdf;
+  const uint32_t* phi_guide;
+  const uint32_t* first_guide;
+  double first_lo, first_hi, phi_lo, phi_hi;
+  int32_t n_first, n_phi, n_rows, pad;
 };
 
 struct DBinning {
@@ -68,6 +79,7 @@ struct DScene {
   const DShell* shells;
   const odw_trimseg* segs;
   const DGroup* groups;
+  const DScatter* scatters;        // [n_scatters] stochastic surface models (nullptr: all surfaces ideal)
   const BvhNode2* bvh;             // nullptr: shells + faces staged in shared memory
   const int32_t* bvh_prims;        // face indices in leaf order
   int32_t n_faces, n_shells, n_segs, n_groups, n_seq_steps, n_bvh_nodes;
@@ -208,7 +220,8 @@ __device__ __forceinline__ int nearest_row(double phi, double lo, double hi, int
   return best;
 }
 
-__device__ __forceinline__ void sample_source(const DSource& s, double u_phi, double u_first, double& first, double& phi) {
+template <class Table>   // DSource or DScatter
+__device__ __forceinline__ void sample_source(const Table& s, double u_phi, double u_first, double& first, double& phi) {
   phi = interp_cdf(u_phi, s.phi_cdf, s.phi_guide, s.n_phi, s.phi_lo, s.phi_hi);
   int row = 0;
   if (s.n_rows > 1) row = nearest_row(phi, s.phi_lo, s.phi_hi, s.n_phi);
@@ -540,6 +553,22 @@ __device__ __forceinline__ bool surface_draw_uv(const DFace& f, double w0, doubl
       v = v0 + w1*(v1 - v0);
       return true;
   }
+}
+
+// ---- stochastic surface model (optical_group.py:279-323) -------------------------------------
+// Rotation(n, phi) * Rotation(n x d_in, theta) * n = cos(theta) n^ + sin(theta) (cos(phi) (a x n^) + sin(phi) a), a = unit(n x d_in),
+// scaled to |n|; a vanishing axis rotates nothing
+__device__ __forceinline__ void scatter_direction(const double* n, const double* d_in, double theta, double phi, double* out) {
+  const double nl = sqrt(dot3(n, n));
+  const double nh[3] = { n[0]/nl, n[1]/nl, n[2]/nl };
+  double a[3] = { nh[1]*d_in[2]-nh[2]*d_in[1], nh[2]*d_in[0]-nh[0]*d_in[2], nh[0]*d_in[1]-nh[1]*d_in[0] };
+  const double al = sqrt(dot3(a, a));
+  if (!(al > 1e-300)) { out[0] = n[0]; out[1] = n[1]; out[2] = n[2]; return; }
+  a[0] /= al; a[1] /= al; a[2] /= al;
+  const double axn[3] = { a[1]*nh[2]-a[2]*nh[1], a[2]*nh[0]-a[0]*nh[2], a[0]*nh[1]-a[1]*nh[0] };
+  double st, ct, sp, cp; sincos(theta, &st, &ct); sincos(phi, &sp, &cp);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out[i] = nl*(ct*nh[i] + st*(cp*axn[i] + sp*a[i]));
 }
 
 // ---- Ray.mirror / snellsLaw / lineGrating (ray.py:482-539) ---------------------------------

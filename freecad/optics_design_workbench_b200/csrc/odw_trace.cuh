@@ -380,6 +380,30 @@ __device__ __forceinline__ void finish_ray(const TraceParams& p, unsigned long l
   }
 }
 
+// applyStochasticRayCorrections (optical_group.py:279-323) of a Mirror / Lens hit: `o` holds the ideal outgoing direction
+// on entry.  Out of line: surfaces are ideal in every benchmark scene, the bounce loop should not carry this code.
+__device__ __noinline__ Vec3 apply_scatter(const DScatter* scatters, int main_i, int mod_i, unsigned long long seed, uint32_t source_id,
+                                           unsigned long long ray, int bounce, double dx, double dy, double dz,
+                                           double nx, double ny, double nz, double ox, double oy, double oz) {
+  const double d_in[3] = { dx, dy, dz }, nrm[3] = { nx, ny, nz };
+  double o[3] = { ox, oy, oz };
+  if (main_i >= 0) {
+    double u0, u1, th, ph;
+    philox_uniform2(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce, u0, u1);
+    sample_source(scatters[main_i], u0, u1, th, ph);
+    scatter_direction(nrm, d_in, th, ph, o);
+  }
+  if (mod_i >= 0) {
+    double u0, u1, th, ph;
+    const double cur[3] = { o[0], o[1], o[2] };
+    philox_uniform2(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce + 1u, u0, u1);
+    sample_source(scatters[mod_i], u0, u1, th, ph);
+    scatter_direction(cur, d_in, th, ph, o);
+  }
+  Vec3 r; r.x = o[0]; r.y = o[1]; r.z = o[2];
+  return r;
+}
+
 // Everything Ray.traceRay does after findNearestIntersection returned (ray.py:105-281): escape segment, or move to the
 // hit, absorption in the traversed medium, normal, onRayHit, the OpticalType rule.  true = the ray has ended.
 template <bool MC>
@@ -413,6 +437,11 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
   switch (g.type) {
     case ODW_OPT_MIRROR: {                                                       // ray.py:146-161
       mirror_dir(dn, nrm, o);                                                    // d - 2(d.n)n is linear in d: the length carries over
+      if (p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {        // ray.py:151-155 (uniform test first: no scene table, no loads)
+        const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
+                                     r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
+        o[0] = q.x; o[1] = q.y; o[2] = q.z; oscale = 1.0;
+      }
       r.power *= g.reflectivity; ++r.seq_index;
       break;
     }
@@ -421,6 +450,11 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
       if (entering) { r.medium = fgroup; n2 = g.n; }
       bool tir = snell(dn, n1, n2, nrm, o);
       oscale = 1.0;                                                              // snellsLaw works on the unit direction
+      if (p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {        // ray.py:197-201
+        const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
+                                     r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
+        o[0] = q.x; o[1] = q.y; o[2] = q.z;
+      }
       if (!entering && !tir && r.medium == fgroup) { r.medium = -1; ++r.seq_index; }
       break;
     }

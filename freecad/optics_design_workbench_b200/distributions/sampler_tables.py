@@ -177,6 +177,36 @@ def surface_source_tables(rec):
   return build_tables(expr, var, dom, (0.0, 2*np.pi), float(rec.get('ThetaResolutionNumericMode', '1e5')), 3)
 
 
+def scatter_tables(density, theta_domain, phi_domain, resolution=None):
+  '''
+  Stochastic surface model of an optical group (reference freecad_elements/optical_group.py:212-269): the density string
+  in (theta, phi) as it stands (no sin(theta) factor, :219-223) -> SamplerTables, or None when the density is empty or
+  reduces to "no change".  Resolution: the reference's default for a 2-variable sampler, 5 + int(1e6**(1/2)) = 1005
+  (random_number_generator.py:323-334).
+
+  Handled specially: `DiracDelta(theta)` (optionally times DiracDelta(phi) or a function of phi) pins theta to 0, for
+  which both rotations of applyStochasticRayCorrections are the identity (:311-320) -> None.
+  Refused: densities that depend on the incident / specular angles (theta_in, phi_in, theta_refl, phi_refl), which the
+  reference re-compiles per hit (:307) — they cannot be tabulated once — and other DiracDelta terms.
+  '''
+  if density is None or not str(density).strip():
+    return None
+  expr = sy.sympify(str(density))
+  names = {str(x) for x in expr.free_symbols}
+  per_hit = names & {'theta_in', 'phi_in', 'theta_refl', 'phi_refl'}
+  if per_hit:
+    raise NotImplementedError(f'stochastic surface density {density!r} depends on {sorted(per_hit)}: needs per-hit tables')
+  if expr.has(sy.DiracDelta):
+    theta = sy.Symbol('theta')
+    pinned = [d for d in expr.atoms(sy.DiracDelta) if d.args[0] == theta]
+    if pinned:
+      return None
+    raise NotImplementedError(f'stochastic surface density {density!r}: only DiracDelta(theta) (no change) is supported')
+  res = 5+int(1e6**0.5) if resolution is None else resolution
+  return build_tables(expr, 'theta', parse_domain(theta_domain, (-np.pi/2, np.pi/2)),
+                      parse_domain(phi_domain, (0, 2*np.pi)), res, res)
+
+
 # ------------------------------------------------------------------------------------------
 # deterministic fan grid
 

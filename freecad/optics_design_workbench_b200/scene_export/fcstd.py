@@ -378,7 +378,12 @@ def build_scene(doc):
       grating_type=g.get('GratingType', 'Reflection') if g.get('GratingType') in ('Reflection', 'Transmission') else 'Reflection',
       grating_lines_per_mm=float(g.get('GratingLinesPerMillimeter', 1000.0)),
       grating_order=float(g.get('GratingDiffractionOrder', 1.0)),
-      grating_orientation=orient if orient is not None else (0, 0, 1))
+      grating_orientation=orient if orient is not None else (0, 0, 1),
+      scatter_density=(g.get('ReflectedProbabilityDensity', '') if otype == 'Mirror'
+                       else g.get('RefractedProbabilityDensity', '') if otype == 'Lens' else ''),
+      power_theta_domain=g.get('PowerThetaDomain', '-pi/2, pi/2'), power_phi_domain=g.get('PowerPhiDomain', '0, 2*pi'),
+      modify_density=g.get('RayModificationProbabilityDensity', ''),
+      modify_theta_domain=g.get('ModifyThetaDomain', '-pi/2, pi/2'), modify_phi_domain=g.get('ModifyPhiDomain', '0, 2*pi'))
     index[g.Name] = gi
     for gpM, _path in doc.global_placements(g):
       for name in g.get('ElementList', []) or []:

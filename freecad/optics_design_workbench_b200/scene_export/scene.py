@@ -270,7 +270,7 @@ class Scene:
   names needed by the hit writer.
   '''
   def __init__(self, faces, segs, shells, groups, group_names, group_labels,
-               seq_offsets=None, seq_groups=None):
+               seq_offsets=None, seq_groups=None, scatters=None, group_scatter=None):
     self.faces = np.ascontiguousarray(faces, dtype=FACE_DTYPE)
     self.segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
     self.shells = np.ascontiguousarray(shells, dtype=SHELL_DTYPE)
@@ -279,6 +279,10 @@ class Scene:
     self.group_labels = list(group_labels)
     self.seq_offsets = np.ascontiguousarray(seq_offsets if seq_offsets is not None else [0], dtype=np.int32)
     self.seq_groups = np.ascontiguousarray(seq_groups if seq_groups is not None else [], dtype=np.int32)
+    # stochastic surface models: list of distributions.SamplerTables + per group {main, modify} index or -1
+    self.scatters = list(scatters or [])
+    self.group_scatter = (np.ascontiguousarray(group_scatter, dtype=np.int32).reshape(len(self.groups), 2)
+                          if group_scatter is not None else np.full((len(self.groups), 2), -1, dtype=np.int32))
 
   @property
   def n_seq_steps(self):
@@ -298,11 +302,19 @@ class SceneBuilder:
   def __init__(self):
     self.faces, self.segs, self.shells, self.groups = [], [], [], []
     self.group_names, self.group_labels = [], []
+    self.scatters, self.group_scatter = [], []
     self.skipped = []          # (group, reason) for faces that need the tessellation path
 
   def add_group(self, name, label, optical_type, refractive_index=1.0, reflectivity=1.0,
                 absorption_length=np.inf, record_hits=False, grating_type=0,
-                grating_lines_per_mm=1000.0, grating_order=1.0, grating_orientation=(0, 0, 1)):
+                grating_lines_per_mm=1000.0, grating_order=1.0, grating_orientation=(0, 0, 1),
+                scatter_density='', power_theta_domain='-pi/2, pi/2', power_phi_domain='0, 2*pi',
+                modify_density='', modify_theta_domain='-pi/2, pi/2', modify_phi_domain='0, 2*pi',
+                scatter_resolution=None):
+    '''
+    scatter_density = ReflectedProbabilityDensity (Mirror) / RefractedProbabilityDensity (Lens); modify_density =
+    RayModificationProbabilityDensity (optical_group.py:29-96); empty = ideal surface.
+    '''
     g = np.zeros((), dtype=GROUP_DTYPE)
     g['optical_type'] = (OPTICAL_TYPES.index(optical_type) if isinstance(optical_type, str)
                          else optical_type)
@@ -316,6 +328,16 @@ class SceneBuilder:
     self.groups.append(g)
     self.group_names.append(name)
     self.group_labels.append(label)
+    from ..distributions import scatter_tables
+    idx = [-1, -1]
+    if int(g['optical_type']) in (OPT_MIRROR, OPT_LENS):       # applyStochasticRayCorrections is only called for these
+      for k, (dens, td, pd) in enumerate(((scatter_density, power_theta_domain, power_phi_domain),
+                                          (modify_density, modify_theta_domain, modify_phi_domain))):
+        t = scatter_tables(dens, td, pd, scatter_resolution)
+        if t is not None:
+          self.scatters.append(t)
+          idx[k] = len(self.scatters)-1
+    self.group_scatter.append(idx)
     return len(self.groups)-1
 
   def add_shape(self, group, face_instances, transform):
@@ -363,4 +385,5 @@ class SceneBuilder:
     for step in (sequence or []):
       seq_groups.extend(step)
       seq_offsets.append(len(seq_groups))
-    return Scene(faces, segs, shells, groups, self.group_names, self.group_labels, seq_offsets, seq_groups)
+    return Scene(faces, segs, shells, groups, self.group_names, self.group_labels, seq_offsets, seq_groups,
+                 scatters=self.scatters, group_scatter=self.group_scatter if self.group_scatter else None)

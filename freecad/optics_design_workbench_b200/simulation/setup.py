@@ -40,8 +40,14 @@ class PreparedSimulation:
     'scene fixture written by save_fixture (tests/golden/scenes/*.npz): the exported scene, not the FCStd'
     z = np.load(path, allow_pickle=False)
     meta = json.loads(str(z['meta']))
+    scatters = []
+    for i in range(int(meta.get('n_scatters', 0))):
+      from ..distributions import SamplerTables
+      d = meta['scatter_domains'][i]
+      scatters.append(SamplerTables(z[f'scatter_phi_{i}'], z[f'scatter_first_{i}'], d[0], d[1], 'theta'))
     scene = Scene(z['faces'], z['segs'], z['shells'], z['groups'], meta['group_names'], meta['group_labels'],
-                  z['seq_offsets'], z['seq_groups'])
+                  z['seq_offsets'], z['seq_groups'], scatters=scatters,
+                  group_scatter=z['group_scatter'] if 'group_scatter' in z.files else None)
     records = meta['source_records']
     for i, r in enumerate(records):
       r['gpM'] = np.array(r['gpM'], dtype=np.float64)
@@ -67,6 +73,12 @@ class PreparedSimulation:
                 settings={k: clean(v) for k, v in self.settings.items()},
                 source_records=[{k: clean(v) for k, v in r.items() if k != 'emit'} for r in self.source_records])
     extra = {}
+    if self.scene.scatters:
+      meta['n_scatters'] = len(self.scene.scatters)
+      meta['scatter_domains'] = [[list(t.first_domain), list(t.phi_domain)] for t in self.scene.scatters]
+      extra['group_scatter'] = self.scene.group_scatter
+      for i, t in enumerate(self.scene.scatters):
+        extra[f'scatter_phi_{i}'], extra[f'scatter_first_{i}'] = t.phi_cdf, t.first_cdf
     for i, r in enumerate(self.source_records):
       if r.get('emit') is not None:
         extra[f'emit_faces_{i}'], extra[f'emit_segs_{i}'] = r['emit'].faces, r['emit'].segs

@@ -134,6 +134,18 @@ typedef struct odw_group {
   int32_t pad;
 } odw_group;
 
+/* Tabulated (theta, phi) density of an optical group's stochastic surface model (optical_group.py:212-323:
+ * ReflectedProbabilityDensity of a mirror, RefractedProbabilityDensity of a lens, RayModificationProbabilityDensity of
+ * either).  Same table layout and draw as a point source sampler (phi from the marginal, theta from the row of the
+ * nearest phi mid-point); NO sin(theta) factor is added (optical_group.py:219-223).  Only densities that do not depend
+ * on theta_in / phi_in / theta_refl / phi_refl can be tabulated once; the host refuses the others. */
+typedef struct odw_scatter {
+  int32_t n_first, n_phi, n_rows, pad;
+  double first_lo, first_hi, phi_lo, phi_hi;
+  const double* phi_cdf;         /* [n_phi] */
+  const double* first_cdf;       /* [n_rows][n_first] */
+} odw_scatter;
+
 typedef struct odw_scene_desc {
   int32_t n_faces;
   int32_t n_segs;
@@ -147,6 +159,16 @@ typedef struct odw_scene_desc {
   const odw_group*   groups;
   const int32_t*     seq_offsets; /* [n_seq_steps+1] into seq_groups */
   const int32_t*     seq_groups;  /* group indices */
+  /* stochastic surface models (applyStochasticRayCorrections, optical_group.py:279-323); n_scatters = 0: all ideal.
+   * After the ideal mirror / Snell direction of a Mirror or Lens hit:
+   *   main density   (theta, phi) -> d = cos(theta) n + sin(theta) (cos(phi) (a x n) + sin(phi) a),  a = unit(n x d_in)
+   *                  [= Rotation(n, phi) Rotation(n x d_in, theta) n, n = face normal flipped along the propagation]
+   *   modify density (theta, phi) -> the same formula with n replaced by the current outgoing direction
+   * Draws: Philox stream of the ray, purposes 0x10000 + 4*bounce (main) and + 1 (modify). */
+  int32_t n_scatters;
+  int32_t pad0;
+  const odw_scatter* scatters;
+  const int32_t*     group_scatter; /* [n_groups][2] = {main, modify} index into scatters, -1 = ideal; NULL = all ideal */
 } odw_scene_desc;
 
 /* Point source + its tabulated sampler (random_number_generator.py:372-464, Appendix D of SURVEY.md).
@@ -213,6 +235,8 @@ typedef struct odw_trace_cfg {
   int32_t bounces_per_wave;      /* 0 = engine default; rays alive after this many bounces are compacted into the next wave */
   uint64_t hit_capacity;         /* 0 = engine default (n_rays * 2) */
   const odw_binning* binnings;
+  uint64_t scatter_seed;         /* odw_trace_rays only: Philox key of the stochastic-surface draws (ray = row of the list,
+                                    source id 0); odw_trace_mc uses its seed argument and the source's id */
 } odw_trace_cfg;
 
 typedef struct odw_counts {

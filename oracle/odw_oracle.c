@@ -114,6 +114,47 @@ static int nearest_row(double phi, double lo, double hi, int n_edges) {
   return best;
 }
 
+/* stochastic surface model: (theta, phi) from a tabulated density, same draw as the point source sampler */
+static void scatter_sample(const odw_scatter* s, double u_phi, double u_first, double* theta, double* phi) {
+  double ph = interp_cdf(u_phi, s->phi_cdf, s->n_phi, s->phi_lo, s->phi_hi);
+  int row = 0;
+  if (s->n_rows > 1) row = nearest_row(ph, s->phi_lo, s->phi_hi, s->n_phi);
+  *theta = interp_cdf(u_first, s->first_cdf + (size_t)row*(size_t)s->n_first, s->n_first, s->first_lo, s->first_hi);
+  *phi = ph;
+}
+
+/* Rotation(n, phi) * Rotation(n x d_in, theta) * n  (optical_group.py:309-311,318-320):
+ * out = cos(theta) n^ + sin(theta) (cos(phi) (a x n^) + sin(phi) a),  a = unit(n x d_in); a zero axis rotates nothing */
+static void scatter_direction(const double* n, const double* d_in, double theta, double phi, double* out) {
+  double nl = len3(n), nh[3] = { n[0]/nl, n[1]/nl, n[2]/nl }, a[3];
+  cross3(nh, d_in, a);
+  double al = len3(a);
+  if (!(al > 1e-300)) { for (int i = 0; i < 3; ++i) out[i] = nh[i]*nl; return; }
+  for (int i = 0; i < 3; ++i) a[i] /= al;
+  double axn[3]; cross3(a, nh, axn);
+  double st = sin(theta), ct = cos(theta), sp = sin(phi), cp = cos(phi);
+  for (int i = 0; i < 3; ++i) out[i] = nl*(ct*nh[i] + st*(cp*axn[i] + sp*a[i]));
+}
+
+/* applyStochasticRayCorrections (optical_group.py:279-323) for a Mirror / Lens hit; dir_in unit, out = ideal direction on entry */
+static void apply_scatter(const odw_scene_desc* sc, int group, uint64_t seed, uint32_t source_id, uint64_t ray, int bounce,
+                          const double* dir_in, const double* nrm, double* out) {
+  if (!sc->n_scatters || !sc->group_scatter) return;
+  int main_i = sc->group_scatter[2*group], mod_i = sc->group_scatter[2*group+1];
+  if (main_i >= 0) {
+    double u[2], th, ph;
+    oracle_philox(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce, u);
+    scatter_sample(&sc->scatters[main_i], u[0], u[1], &th, &ph);
+    scatter_direction(nrm, dir_in, th, ph, out);
+  }
+  if (mod_i >= 0) {
+    double u[2], th, ph, cur[3] = { out[0], out[1], out[2] };
+    oracle_philox(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce + 1u, u);
+    scatter_sample(&sc->scatters[mod_i], u[0], u[1], &th, &ph);
+    scatter_direction(cur, dir_in, th, ph, out);
+  }
+}
+
 static void sample_from_uniforms(const odw_source_desc* s, double u_phi, double u_first,
                                  double* first, double* phi) {
   /* phi (last variable) is drawn first from its marginal; then theta|r conditional on the nearest phi row */
@@ -778,7 +819,7 @@ typedef struct { uint64_t segments, escaped, depth_terminated; } ray_stats_t;
 
 static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const double* origin, const double* dir0,
                       double power0, double wavelength, double max_len, int max_isect,
-                      const int32_t* ignored, int n_ignored, uint64_t ray_index, const sink_t* sk,
+                      const int32_t* ignored, int n_ignored, uint64_t ray_index, uint64_t seed, uint32_t source_id, const sink_t* sk,
                       cand_t* shell_c, cand_t* face_c, ray_stats_t* st,
                       int32_t* n_segments, double* final_point, double* final_power) {
   double point[3] = { origin[0], origin[1], origin[2] };
@@ -826,7 +867,9 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
     double dnrm[3] = { dir[0]/dl, dir[1]/dl, dir[2]/dl };
     switch (g->optical_type) {
       case ODW_OPT_MIRROR: {                                                /* :146-161 */
-        double o[3]; mirror(dir, nrm, o); memcpy(dir, o, sizeof o);
+        double o[3]; mirror(dir, nrm, o);
+        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, o);   /* :151-155 */
+        memcpy(dir, o, sizeof o);
         power *= g->reflectivity;
         seq_index++;
         break;
@@ -843,6 +886,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
         }
         double o[3];
         int tir = snell(dnrm, n1, n2, nrm, o);
+        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, o);   /* :197-201 */
         memcpy(dir, o, sizeof o);
         if (!entering && !tir && medium == f->group) { medium = -1; seq_index++; }
         break;
@@ -912,7 +956,8 @@ int oracle_trace_rays(const odw_scene_desc* sc, const odw_trace_cfg* cfg,
 #endif
     for (int64_t i = 0; i < (int64_t)n; ++i) {
       trace_one(sc, cfg, origins + 3*i, dirs + 3*i, powers ? powers[i] : 1.0, wavelength,
-                cfg->max_ray_length, cfg->max_intersections, ignored, n_ignored, ray_index_base + (uint64_t)i, &sk,
+                cfg->max_ray_length, cfg->max_intersections, ignored, n_ignored, ray_index_base + (uint64_t)i,
+                cfg->scatter_seed, 0u, &sk,
                 shell_c, face_c, &st,
                 n_segments ? n_segments + i : NULL, final_points ? final_points + 3*i : NULL,
                 final_powers ? final_powers + i : NULL);
@@ -954,7 +999,7 @@ int oracle_trace_mc(const odw_scene_desc* sc, const odw_source_desc* src, const 
       uint64_t ray = first_ray + (uint64_t)i;
       source_make_ray(src, seed, ray, NULL, NULL, o, d);
       trace_one(sc, cfg, o, d, 1.0, src->wavelength, max_len, max_isect, src->ignored_groups, src->n_ignored,
-                ray, &sk, shell_c, face_c, &st, NULL, NULL, NULL);
+                ray, seed, (uint32_t)src->source_id, &sk, shell_c, face_c, &st, NULL, NULL, NULL);
     }
     segs += st.segments; esc += st.escaped; depth += st.depth_terminated;
     free(shell_c); free(face_c);

@@ -20,6 +20,7 @@ SCENES = {
   # reference test/50-old-tests: transmission/reflection grating and a Gaussian beam on a box detector
   'grating': 'test/50-old-tests/grating.FCStd',
   'gaussian': 'test/50-old-tests/gaussian.FCStd',
+  'mirrorDiffuse': 'test/50-old-tests/mirror-diffuse.FCStd',     # Lambert-like diffuse mirror (stochastic surface model)
   'gettingStarted': 'examples/1-getting-started/GettingStarted.FCStd',
 }
 
