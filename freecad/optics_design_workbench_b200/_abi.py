@@ -50,7 +50,7 @@ class TraceCfg(C.Structure):
   _fields_ = [('max_ray_length', C.c_double), ('dist_tol', C.c_double), ('power_tol', C.c_double),
               ('max_intersections', C.c_int32), ('sequential', C.c_int32), ('record_all_hits', C.c_int32),
               ('store_hits', C.c_int32), ('n_binnings', C.c_int32), ('bounces_per_wave', C.c_int32),
-              ('hit_capacity', C.c_uint64), ('binnings', C.c_void_p), ('scatter_seed', C.c_uint64)]
+              ('hit_capacity', C.c_uint64), ('binnings', C.c_void_p), ('wavelength', C.c_double), ('scatter_seed', C.c_uint64)]
 
 
 class Counts(C.Structure):
@@ -130,7 +130,7 @@ class SourceArgs:
 class CfgArgs:
   def __init__(self, *, max_ray_length=1000.0, dist_tol=1e-6, power_tol=1e-6, max_intersections=100,
                sequential=False, record_all_hits=False, store_hits=True, binnings=(), bounces_per_wave=0,
-               hit_capacity=0, scatter_seed=0):
+               hit_capacity=0, scatter_seed=0, wavelength=0.0):
     self.binnings = (Binning*max(1, len(binnings)))()
     for i, b in enumerate(binnings):
       bb = self.binnings[i]
@@ -152,6 +152,7 @@ class CfgArgs:
     c.hit_capacity = int(hit_capacity)
     c.binnings = C.addressof(self.binnings) if len(binnings) else None
     c.scatter_seed = int(scatter_seed)
+    c.wavelength = float(wavelength)
     self.cfg = c
 
 

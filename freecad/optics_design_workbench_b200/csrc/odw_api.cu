@@ -907,7 +907,7 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   p.out_nseg = r->d_nseg; p.out_final_point = r->d_final_point; p.out_final_power = r->d_final_power;
   p.first_ray = 0;
   p.seed = cfg->scatter_seed; p.src.source_id = 0;       // Philox stream of the stochastic-surface draws of an explicit list
-  p.wavelength = 500.0;
+  p.wavelength = cfg->wavelength > 0 ? cfg->wavelength : 500.0;
   set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0);
   double origin_bound = 0;
   for (uint64_t i = 0; i < 3*n_rays; ++i) origin_bound = std::max(origin_bound, std::fabs(origins[i]));

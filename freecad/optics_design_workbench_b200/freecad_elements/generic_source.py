@@ -53,8 +53,10 @@ class GenericSourceProxy:
     if draw:
       raise NotImplementedError('draw=True builds FreeCAD Part objects; keep the reference path for displayed rays')
     kind = obj.get('proxy', 'PointSourceProxy')
-    if kind not in ('PointSourceProxy', 'SurfaceSourceProxy'):
+    if kind not in ('PointSourceProxy', 'SurfaceSourceProxy', 'ReplaySourceProxy'):
       raise NotImplementedError(f"light source kind {kind} is not handled by the engine yet")
+    if kind == 'ReplaySourceProxy':
+      return self._replay_iteration(obj, mode, int(iterations), store, returnInitialConditions)
     if kind == 'SurfaceSourceProxy' and (mode in ('fans', 'multicorefans') and useInitialConditions is None):
       raise NotImplementedError('fan mode of surface sources (_makeSurfaceGrid, surface_source.py:122-267) is not on the engine yet')
     if mode in ('pseudo', 'singlepseudo'):
@@ -71,6 +73,26 @@ class GenericSourceProxy:
       raise NotImplementedError('Monte-Carlo rays are drawn on the device; use DeviceSource.sample for their initial conditions')
     return self._trace_monte_carlo(obj, int(iterations), store)
 
+  # -- replay source (reference freecad_elements/replay_source.py:73-166) --------------------------------
+  def _replay_iteration(self, obj, mode, iterations, store, returnInitialConditions):
+    from . import replay_source
+    if mode in ('fans', 'multicorefans'):
+      return None                                        # :132-135 a replay source places no fans
+    stock = self.context.replay_stock(self.index, lambda: replay_source.load_stock(obj))
+    n_total = point_source.rays_per_iteration(obj, self.context.sim.settings)*iterations
+    first, n = self.context.claim_rays(self.index, n_total)
+    batches = stock.take(first, n)
+    if returnInitialConditions:
+      return batches
+    counts = None
+    for batch in batches:
+      c = self._trace_explicit(obj, batch, store)
+      counts = c if counts is None else {k: counts[k]+c[k] for k in counts}
+    if first+n >= len(stock) and first < len(stock) or not batches:
+      from ..simulation.simulation_loop import SimulationEnded
+      raise SimulationEnded(f'replay light source {obj["name"]} ran out of rays')     # :160-161
+    return counts
+
   # -- engine calls -----------------------------------------------------------------------------------
   def _store_hits(self, obj, hits, store, metadata_of):
     'append the hit arrays to the store, one entry per optical group (file per (source, object))'
@@ -86,7 +108,10 @@ class GenericSourceProxy:
 
   def _trace_explicit(self, obj, batch, store):
     ctx = self.context
-    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])))
+    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])),
+                  wavelength=batch.wavelength, scatter_seed=ctx.seed,
+                  max_ray_length=float(ctx.sim.settings['MaxRayLength'])*float(obj.get('MaxRayLengthScale', 1.0)),
+                  max_intersections=int(float(ctx.sim.settings['MaxIntersections'])*float(obj.get('MaxIntersectionsScale', 1.0))))
     with ctx.device_scene.trace_rays(cfg, batch.origins, batch.directions, batch.powers, ignored=obj.get('ignored', ())) as res:
       counts = res.counts
       hits = res.hits(sort=True) if store else None

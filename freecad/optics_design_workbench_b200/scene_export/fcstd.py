@@ -420,7 +420,7 @@ def source_records(doc):
                        ('ThetaResolutionNumericMode', '1e5'), ('RadiusResolutionNumericMode', '1e5'),
                        ('PhiResolutionNumericMode', '1e2'), ('Fans', 2), ('FanPhi0', '0'), ('RaysPerFan', 20),
                        ('FanModePowerSpan', 0.9), ('RaysPerIterationScale', 1.0), ('MaxIntersectionsScale', 1.0),
-                       ('MaxRayLengthScale', 1.0), ('RecordRays', False), ('FanModeRayCount', 100)):
+                       ('MaxRayLengthScale', 1.0), ('RecordRays', False), ('FanModeRayCount', 100), ('ReplayFromDir', '')):
       rec[k] = s.get(k, default)
     out.append(rec)
   return out

@@ -18,6 +18,10 @@ from . import results_store, sharding
 from .setup import prepare, PreparedSimulation
 from ..freecad_elements.generic_source import GenericSourceProxy
 
+class SimulationEnded(RuntimeError):
+  'control flow like the reference (freecad_elements/common.py:155): a light source ran dry / the run was finished'
+
+
 DEFAULT_SEED = 0x0DDB1A5E
 ACTIONS = ('fans', 'singlepseudo', 'singletrue', 'pseudo', 'true')
 
@@ -34,6 +38,7 @@ class SimulationContext:
     self.device_scene = engine.scene(sim.scene)
     self._device_sources = {}
     self._next_ray = {}                   # per light source: next unused global ray index
+    self._replay = {}                     # per replay source: its stock of rays
 
   def device_source(self, index):
     if index not in self._device_sources:
@@ -49,6 +54,11 @@ class SimulationContext:
     first = self._next_ray.get(source_index, 0)
     self._next_ray[source_index] = first+int(n_global)
     return sharding.shard_range(first, n_global, self.rank, self.world)
+
+  def replay_stock(self, index, loader):
+    if index not in self._replay:
+      self._replay[index] = loader()
+    return self._replay[index]
 
   def close(self):
     for s in self._device_sources.values():
@@ -137,6 +147,12 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
     if not continuous:
       # one iteration (simulation_loop.py:342-411: single shots and fans are not continuous)
       for src in sources:
+        if src.record.get('proxy') == 'ReplaySourceProxy' and mode != 'fans':
+          try:
+            src.runSimulationIteration(mode='true', store=store, iterations=1)
+          except SimulationEnded:
+            pass
+          continue
         if mode == 'fans':
           # fans are a short deterministic list: rank 0 traces them (the reference's multicorefans mailbox,
           # results_store.py:679-738, distributes chunks of the same list; not worth it for <= 1e3 rays)
@@ -146,15 +162,20 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
           src.runSimulationIteration(mode='true', store=store, iterations=1)
       store.incrementIterationCount()
     else:
-      if not any(np.isfinite(v) for v in (store.endAfterIterations, store.endAfterRays, store.endAfterHits)):
+      has_replay = any(r.get('proxy') == 'ReplaySourceProxy' for r in sim.source_records)
+      if not has_replay and not any(np.isfinite(v) for v in (store.endAfterIterations, store.endAfterRays, store.endAfterHits)):
         raise ValueError("continuous simulation without any end criterion (EndAfterRays/Hits/Iterations all 'inf')")
       from ..freecad_elements import point_source
       per_iter = sum(point_source.rays_per_iteration(r, s) for r in sim.source_records)
       batch_rays = min(maxBatchRays, max(per_iter, 1 << 16))
       while True:
         k = _iterations_until_end(store_global(store, world), per_iter, batch_rays)
+        ended = False
         for src in sources:
-          src.runSimulationIteration(mode='true', store=store, iterations=k)
+          try:
+            src.runSimulationIteration(mode='true', store=store, iterations=k)
+          except SimulationEnded:
+            ended = True                                          # a replay source ran out of rays (replay_source.py:160-161)
         store.incrementIterationCount(k)
         store.writeDiskIfNeeded()
         total = sharding.all_reduce_counters(dict(totalTracedRays=store.totalTracedRays,
@@ -164,7 +185,7 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
         store._global = total
         if rank == 0:
           store.dumpMasterProgress(total)
-        if store.isEndReached(total):
+        if store.isEndReached(total) or ended:
           break
         batch_rays = min(maxBatchRays, batch_rays*4)            # grow while only EndAfterHits is pending
   finally:

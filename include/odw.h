@@ -235,6 +235,7 @@ typedef struct odw_trace_cfg {
   int32_t bounces_per_wave;      /* 0 = engine default; rays alive after this many bounces are compacted into the next wave */
   uint64_t hit_capacity;         /* 0 = engine default (n_rays * 2) */
   const odw_binning* binnings;
+  double wavelength;             /* odw_trace_rays only: wavelength (nm) of the listed rays (gratings); 0 = 500.  odw_trace_mc uses the source's */
   uint64_t scatter_seed;         /* odw_trace_rays only: Philox key of the stochastic-surface draws (ray = row of the list,
                                     source id 0); odw_trace_mc uses its seed argument and the source's id */
 } odw_trace_cfg;

@@ -84,9 +84,11 @@ class Oracle:
       off += n
     return out
 
-  def trace_rays(self, scene, cfg, origins, directions, powers=None, wavelength=500.0, ignored=(),
+  def trace_rays(self, scene, cfg, origins, directions, powers=None, wavelength=None, ignored=(),
                  hit_capacity=None, threads=1, ray_index_base=0, sort=True):
     sa = scene if isinstance(scene, _abi.SceneArgs) else _abi.SceneArgs(scene)
+    if wavelength is None:
+      wavelength = cfg.cfg.wavelength if cfg.cfg.wavelength > 0 else 500.0
     o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
     d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
     n = len(o)

@@ -183,3 +183,33 @@ def test_engine_bridge_with_reference_side_objects(tmp_path, engine):
     assert len(hits['points']) == 300 and hits['obj'] == 'OpticalAbsorberGroup'
   finally:
     engine_bridge.set_engine_factory(None)
+
+
+def test_replay_source_re_emits_stored_hits(tmp_path, engine, oracle):
+  '''
+  ReplaySourceProxy (reference freecad_elements/replay_source.py:73-166): hits stored by one simulation are the rays of
+  the next; the run ends when the stock is used up.
+  '''
+  # stage 1: rays of the point source stopped on a Vacuum plane in front of the optics
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  sa = sim.source_args(0)
+  s = oracle.sample_mc(sa, 7, 0, 1000)
+  stage1 = results_store.SimulationResults('true', str(tmp_path/'stage1.OpticsDesign'))
+  pts = s['origins'] + s['directions']*5.0                                  # 5 mm down the beam
+  stage1.addRayHits(('src', 'src'), ('Plane', 'Plane'), pts, s['directions'], np.full(1000, 0.7), np.ones(1000))
+  stage1.flush()
+  # stage 2: a replay source pointing at stage 1's run folder, shifted by its own placement
+  gpM = np.eye(4); gpM[:3, 3] = [0, 0, 0.25]
+  sim2 = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  sim2.source_records = [dict(name='OpticalReplaySource', label='replay', proxy='ReplaySourceProxy', source_id=0, gpM=gpM,
+                              ignored=[], ReplayFromDir=stage1.runFolderPath(), RaysPerIterationScale=1.0,
+                              MaxRayLengthScale=1.0, MaxIntersectionsScale=1.0, Wavelength=500.0)]
+  run = simulation_loop.runSimulation(sim2, 'true', engine=engine, basePath=str(tmp_path/'stage2.OpticsDesign'),
+                                      settings=dict(RaysPerIteration=300), maxBatchRays=300)
+  hits = load_hits(run)
+  want = oracle.trace_rays(sim2.scene, sim2.cfg(wavelength=1.0), pts+[0, 0, 0.25], s['directions'], np.full(1000, 0.7))
+  assert len(hits['points']) == want['counts']['hits'] > 900
+  key = lambda p: np.lexsort(np.round(p, 9).T)
+  np.testing.assert_allclose(hits['points'][key(hits['points'])], want['hits']['points'][key(want['hits']['points'])], atol=1e-9)
+  np.testing.assert_allclose(hits['powers'], 0.7*np.ones(len(hits['powers'])))       # mirrors have Reflectivity 1 here
+  assert hits['source'] == 'OpticalReplaySource'
