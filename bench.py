@@ -299,9 +299,9 @@ def main():
     # dominant kernel = trace_kernel; algorithmic bytes per launch / its mean CUDA-event duration (this rank)
     alg_bytes = segs*BYTES_PER_SEGMENT + hits*BYTES_PER_HIT
     achieved = alg_bytes/(kernel_ms*1e-3)/1e9
-    traffic = ncu_traffic()
+    traffic = ncu_traffic() if args.scene == 'lensesAndMirrors' else None     # the committed ncu capture is of this scene's kernel
     line = dict(
-      metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+      metric=METRIC if args.scene == 'lensesAndMirrors' else METRIC.replace('lensesAndMirrors', args.scene), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
       ms_per_step=elapsed_ms/args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
       dtype='f64', data='synthetic',
       config=dict(workload=f'benchmark/{args.scene}.FCStd, Monte-Carlo (true) mode, {n_rays} rays per GPU per step, '

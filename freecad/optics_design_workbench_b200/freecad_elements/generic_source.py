@@ -137,12 +137,18 @@ class GenericSourceProxy:
     n_total = n_iter_rays*iterations
     first, n = ctx.claim_rays(self.index, n_total)        # this rank's shard of the next n_total global ray indices
     dsrc = ctx.device_source(self.index)
-    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, 2*n))
-    with ctx.device_scene.trace_mc(dsrc, cfg, ctx.seed, first, n) as res:
-      counts = res.counts
-      hits = res.hits(sort=True) if store else None
-      if res.overflow:
-        raise RuntimeError(f'hit buffer overflow: {counts}')
+    capacity = max(1024, 2*n)
+    while True:
+      cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=capacity)
+      with ctx.device_scene.trace_mc(dsrc, cfg, ctx.seed, first, n) as res:
+        counts = res.counts
+        overflow = res.overflow
+        hits = res.hits(sort=True) if (store and not overflow) else None
+      if not overflow:
+        break
+      # more recorded hits than rows (transparent detectors record two hits per pass): the same ray range again with
+      # room for all of them — the Philox stream makes the repeat identical
+      capacity = max(4*capacity, int(counts['hits'])+1024)
     if store:
       def metadata_of(ray_index, keys):
         s = dsrc.sample(ctx.seed, first, n)               # same Philox stream -> the rays' initial conditions
