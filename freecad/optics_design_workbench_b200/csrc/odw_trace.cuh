@@ -299,8 +299,8 @@ __device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long
   double a0, a1, b0, b1;
   philox_uniform2(seed, (uint32_t)s.source_id, ray, 0u, a0, a1);
   philox_uniform2(seed, (uint32_t)s.source_id, ray, 1u, b0, b1);
-  int k = 0;
-  while (k < s.n_emit-1 && !(a0 < __ldg(s.emit_cdf + k))) ++k;
+  int k = 0, hi = s.n_emit-1;                                                    // first face with a0 < emit_cdf[k]
+  while (k < hi) { const int m = (k + hi) >> 1; if (a0 < __ldg(s.emit_cdf + m)) hi = m; else k = m + 1; }
   const DFace& f = s.emit_faces[k];
   double P[3] = {0, 0, 0}, du[3] = {1, 0, 0}, dv[3] = {0, 1, 0};
   for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {

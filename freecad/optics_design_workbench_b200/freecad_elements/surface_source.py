@@ -107,6 +107,9 @@ def face_area(f, segs):
   if trim in (sc.TRIM_NONE, sc.TRIM_UVBOX):
     return (u1-u0)*_v_integral(f, v0, v1)
   mine = segs[int(f['seg_first']):int(f['seg_first'])+int(f['seg_count'])]
+  if int(f['kind']) == sc.SURF_PLANE and len(mine) == 3 and all(int(m['kind']) == sc.SEG_LINE for m in mine):
+    (x0, y0, x1, y1), (_, _, x2, y2) = mine[0]['a'][:4], mine[1]['a'][:4]
+    return 0.5*abs((x1-x0)*(y2-y0)-(x2-x0)*(y1-y0))                        # a triangle
   if (int(f['kind']) == sc.SURF_PLANE and len(mine) == 1 and int(mine[0]['kind']) == sc.SEG_ARC
           and mine[0]['a'][4] >= TWO_PI-1e-12):
     return np.pi*float(mine[0]['a'][2])**2            # a disc
@@ -138,7 +141,13 @@ def emitting_faces_from_instances(selections):
   faces, segs = [], []
   for face_instances, transform in selections:
     for fi in face_instances:
-      faces.append(sc.face_record(fi, transform, 0, 0, len(faces), segs))
+      try:
+        faces.append(sc.face_record(fi, transform, 0, 0, len(faces), segs))
+      except sc.UnsupportedGeometry:
+        # B-spline and other free-form emitters: emit from the triangles of the tessellated face
+        from ..scene_export import tessellate
+        tris, _info = tessellate.triangle_faces(fi, transform, 0, 0, len(faces), segs)
+        faces.extend(tris)
   seg_arr = np.zeros(len(segs), dtype=sc.SEG_DTYPE)
   for i, (kind, a) in enumerate(segs):
     seg_arr[i]['kind'] = kind

@@ -303,7 +303,10 @@ class SceneBuilder:
     self.faces, self.segs, self.shells, self.groups = [], [], [], []
     self.group_names, self.group_labels = [], []
     self.scatters, self.group_scatter = [], []
-    self.skipped = []          # (group, reason) for faces that need the tessellation path
+    self.skipped = []          # (group, reason) for faces that could neither be written in closed form nor meshed
+    self.tessellated = []      # one entry per face that went through the tessellation path (grid, achieved deflection)
+    from .tessellate import DEFAULT_DEFLECTION
+    self.deflection = DEFAULT_DEFLECTION
 
   def add_group(self, name, label, optical_type, refractive_index=1.0, reflectivity=1.0,
                 absorption_length=np.inf, record_hits=False, grating_type=0,
@@ -362,7 +365,15 @@ class SceneBuilder:
         try:
           self.faces.append(face_record(fi, transform, group, shell_index, len(self.faces), self.segs))
         except UnsupportedGeometry as e:
-          self.skipped.append((group, str(e)))
+          # no closed form: tessellate (scene_export/tessellate.py); only what cannot be meshed either is skipped
+          try:
+            from . import tessellate
+            tris, info = tessellate.triangle_faces(fi, transform, group, shell_index, len(self.faces), self.segs,
+                                                   deflection=self.deflection)
+            self.faces.extend(tris)
+            self.tessellated.append(dict(group=group, reason=str(e), **info))
+          except UnsupportedGeometry as e2:
+            self.skipped.append((group, f'{e}; {e2}'))
       count = len(self.faces)-first
       if count == 0:
         continue

@@ -537,8 +537,8 @@ static void surface_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t r
   double a[2], b[2];
   oracle_philox(seed, (uint32_t)s->source_id, ray, 0, a);       /* a[0]: face, a[1]: theta */
   oracle_philox(seed, (uint32_t)s->source_id, ray, 1, b);       /* b[0]: phi */
-  int k = 0;
-  while (k < s->n_emit-1 && !(a[0] < s->emit_cdf[k])) ++k;
+  int k = 0, hi = s->n_emit-1;                                   /* first face with a[0] < emit_cdf[k] (binary search) */
+  while (k < hi) { int m = (k + hi) >> 1; if (a[0] < s->emit_cdf[m]) hi = m; else k = m + 1; }
   const odw_face* f = &s->emit_faces[k];
   double P[3], du[3], dv[3], u = 0, v = 0;
   for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {
