@@ -64,7 +64,7 @@ class Counts(C.Structure):
 class HitsView(C.Structure):
   _fields_ = [('capacity', C.c_uint64), ('points', C.c_void_p), ('directions', C.c_void_p), ('powers', C.c_void_p),
               ('is_entering', C.c_void_p), ('ray_index', C.c_void_p), ('group', C.c_void_p), ('bounce', C.c_void_p),
-              ('face_id', C.c_void_p)]
+              ('face_id', C.c_void_p), ('medium', C.c_void_p)]
 
 
 def _ptr(a):
@@ -168,9 +168,10 @@ class HitArrays:
     self.group = np.empty(capacity, dtype=np.int32)
     self.bounce = np.empty(capacity, dtype=np.int32)
     self.face_id = np.empty(capacity, dtype=np.int32)
+    self.medium = np.empty(capacity, dtype=np.int32)
     v = HitsView()
     v.capacity = capacity
-    for k in ('points', 'directions', 'powers', 'is_entering', 'ray_index', 'group', 'bounce', 'face_id'):
+    for k in ('points', 'directions', 'powers', 'is_entering', 'ray_index', 'group', 'bounce', 'face_id', 'medium'):
       setattr(v, k, getattr(self, k).ctypes.data)
     self.view = v
     self.n = 0
@@ -179,7 +180,7 @@ class HitArrays:
     n = int(n)
     self.n = n
     out = {k: getattr(self, k)[:n] for k in ('points', 'directions', 'powers', 'is_entering', 'ray_index',
-                                             'group', 'bounce', 'face_id')}
+                                             'group', 'bounce', 'face_id', 'medium')}
     if sort and n:
       order = np.lexsort((out['bounce'], out['ray_index']))
       out = {k: v[order] for k, v in out.items()}

@@ -108,7 +108,7 @@ struct odw_result {
   DBinning* dbinnings = nullptr;
   std::vector<DBinning> binnings;
   size_t total_bins = 0;
-  int32_t* d_nseg = nullptr; double* d_final_point = nullptr; double* d_final_power = nullptr;
+  int32_t* d_nseg = nullptr; double* d_final_point = nullptr; double* d_final_power = nullptr; int32_t* d_final_medium = nullptr;
   double* d_in_o = nullptr; double* d_in_d = nullptr; double* d_in_p = nullptr;
   odw_counts counts{};
   uint64_t n_rays = 0;
@@ -567,7 +567,7 @@ extern "C" void odw_result_destroy(odw_result* r) {
   odw_engine* e = r->eng;
   cudaSetDevice(e->device);
   void* ptrs[] = { r->hb.points, r->hb.dirs, r->hb.powers, r->hb.entering, r->hb.ray_index, r->hb.group, r->hb.bounce,
-                   r->hb.face_id, r->dcounters, r->dbins, r->dbinnings, r->d_nseg, r->d_final_point, r->d_final_power,
+                   r->hb.face_id, r->hb.medium, r->dcounters, r->dbins, r->dbinnings, r->d_nseg, r->d_final_point, r->d_final_power, r->d_final_medium,
                    r->d_in_o, r->d_in_d, r->d_in_p };
   for (void* p : ptrs) e->release(p);
   delete r;
@@ -590,6 +590,7 @@ static int prepare_result(odw_engine* eng, const odw_scene* sc, const odw_trace_
     if ((rc = eng->alloc((void**)&r->hb.group, cap*4))) return rc;
     if ((rc = eng->alloc((void**)&r->hb.bounce, cap*4))) return rc;
     if ((rc = eng->alloc((void**)&r->hb.face_id, cap*4))) return rc;
+    if ((rc = eng->alloc((void**)&r->hb.medium, cap*4))) return rc;
   }
   if ((rc = eng->alloc((void**)&r->dcounters, sizeof(Counters)))) return rc;
   CU(cudaMemsetAsync(r->dcounters, 0, sizeof(Counters), eng->stream));
@@ -718,6 +719,7 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
       if (p.out_nseg) q.out_nseg = p.out_nseg + off;
       if (p.out_final_point) q.out_final_point = p.out_final_point + 3*off;
       if (p.out_final_power) q.out_final_power = p.out_final_power + off;
+      if (p.out_final_medium) q.out_final_medium = p.out_final_medium + off;
     }
     if (sc->use_bvh && sc->wavefront) {
       int rc = run_wavefront_wave(eng, q, mc, launches);
@@ -844,6 +846,7 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
       if (host->group)       CU(cudaMemcpyAsync(host->group + stored, hb.group, n*4, cudaMemcpyDeviceToHost, cs));
       if (host->bounce)      CU(cudaMemcpyAsync(host->bounce + stored, hb.bounce, n*4, cudaMemcpyDeviceToHost, cs));
       if (host->face_id)     CU(cudaMemcpyAsync(host->face_id + stored, hb.face_id, n*4, cudaMemcpyDeviceToHost, cs));
+      if (host->medium)      CU(cudaMemcpyAsync(host->medium + stored, hb.medium, n*4, cudaMemcpyDeviceToHost, cs));
     }
     CU(cudaEventRecord(eng->ev_copy[b], cs));
     stored += n;
@@ -898,13 +901,14 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   if ((rc = eng->alloc((void**)&r->d_nseg, n_rays*4))) return bail(rc);
   if ((rc = eng->alloc((void**)&r->d_final_point, n_rays*24))) return bail(rc);
   if ((rc = eng->alloc((void**)&r->d_final_power, n_rays*8))) return bail(rc);
+  if ((rc = eng->alloc((void**)&r->d_final_medium, n_rays*4))) return bail(rc);
   if (n_rays) {
     CU(cudaMemcpyAsync(r->d_in_o, origins, n_rays*24, cudaMemcpyHostToDevice, eng->stream));
     CU(cudaMemcpyAsync(r->d_in_d, directions, n_rays*24, cudaMemcpyHostToDevice, eng->stream));
     if (powers) CU(cudaMemcpyAsync(r->d_in_p, powers, n_rays*8, cudaMemcpyHostToDevice, eng->stream));
   }
   p.in_origins = r->d_in_o; p.in_dirs = r->d_in_d; p.in_powers = powers ? r->d_in_p : nullptr;
-  p.out_nseg = r->d_nseg; p.out_final_point = r->d_final_point; p.out_final_power = r->d_final_power;
+  p.out_nseg = r->d_nseg; p.out_final_point = r->d_final_point; p.out_final_power = r->d_final_power; p.out_final_medium = r->d_final_medium;
   p.first_ray = 0;
   p.seed = cfg->scatter_seed; p.src.source_id = 0;       // Philox stream of the stochastic-surface draws of an explicit list
   p.wavelength = cfg->wavelength > 0 ? cfg->wavelength : 500.0;
@@ -950,6 +954,7 @@ extern "C" int odw_result_hits(const odw_result* r, odw_hits_view* v, int sorted
     if (v->group)       CU(cudaMemcpyAsync(v->group, r->hb.group, n*4, cudaMemcpyDeviceToHost, st));
     if (v->bounce)      CU(cudaMemcpyAsync(v->bounce, r->hb.bounce, n*4, cudaMemcpyDeviceToHost, st));
     if (v->face_id)     CU(cudaMemcpyAsync(v->face_id, r->hb.face_id, n*4, cudaMemcpyDeviceToHost, st));
+    if (v->medium)      CU(cudaMemcpyAsync(v->medium, r->hb.medium, n*4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return ODW_OK;
   }
@@ -980,6 +985,7 @@ extern "C" int odw_result_hits(const odw_result* r, odw_hits_view* v, int sorted
   if ((rc = gather(v->group, r->hb.group, 4))) return rc;
   if ((rc = gather(v->bounce, r->hb.bounce, 4))) return rc;
   if ((rc = gather(v->face_id, r->hb.face_id, 4))) return rc;
+  if ((rc = gather(v->medium, r->hb.medium, 4))) return rc;
   return ODW_OK;
 }
 
@@ -998,6 +1004,14 @@ extern "C" int odw_result_histogram_device(const odw_result* r, int32_t b, void*
   const DBinning& d = r->binnings[(size_t)b];
   *dptr = r->dbins + d.offset;
   if (n_bins) *n_bins = (uint64_t)d.nu*d.nv;
+  return ODW_OK;
+}
+
+extern "C" int odw_result_ray_media(const odw_result* r, int32_t* final_medium) {
+  if (!r || !final_medium) return fail(ODW_EINVAL, "odw_result_ray_media: NULL argument");
+  if (!r->d_final_medium) return fail(ODW_EINVAL, "odw_result_ray_media: only available for odw_trace_rays results");
+  CU(cudaSetDevice(r->eng->device));
+  if (r->n_rays) CU(cudaMemcpy(final_medium, r->d_final_medium, r->n_rays*4, cudaMemcpyDeviceToHost));
   return ODW_OK;
 }
 

@@ -104,7 +104,7 @@ struct DSource {
 struct HitBuffers {
   double* points; double* dirs; double* powers;
   uint8_t* entering; unsigned long long* ray_index;
-  int32_t* group; int32_t* bounce; int32_t* face_id;
+  int32_t* group; int32_t* bounce; int32_t* face_id; int32_t* medium;
   unsigned long long capacity;
 };
 
@@ -121,7 +121,7 @@ struct TraceParams {
   // explicit ray input (nullptr for MC)
   const double* in_origins; const double* in_dirs; const double* in_powers;
   // per-ray summary (explicit lists)
-  int32_t* out_nseg; double* out_final_point; double* out_final_power;
+  int32_t* out_nseg; double* out_final_point; double* out_final_power; int32_t* out_final_medium;
   unsigned long long ignore_mask[4];
   unsigned long long seed, first_ray, n_rays;
   double max_len, tol, power_tol, wavelength;

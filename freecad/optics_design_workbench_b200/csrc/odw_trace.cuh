@@ -248,7 +248,7 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
 // OpticalGroupProxy.onRayHit -> SimulationResults.addRayHit (optical_group.py:206-209, results_store.py:641-648):
 // warp-aggregated append (one atomic per converged group of lanes) + optional detector binning
 __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long long ray, int bounce, int group, int face_id,
-                                           const double* P, const double* dir, double power, bool entering,
+                                           const double* P, const double* dir, double power, bool entering, int medium,
                                            unsigned int* s_cnt) {
   for (int b = 0; b < p.n_binnings; ++b) {
     const DBinning& bn = p.binnings[b];
@@ -276,6 +276,7 @@ __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long l
   p.hits.group[slot] = group;
   p.hits.bounce[slot] = bounce;
   p.hits.face_id[slot] = face_id;
+  p.hits.medium[slot] = medium;
 }
 
 // Philox draw + tabulated inverse CDF + _makeRay: once per ray, kept out of line so the bounce loop stays small
@@ -377,6 +378,7 @@ __device__ __forceinline__ void finish_ray(const TraceParams& p, unsigned long l
     if (p.out_nseg) p.out_nseg[i] = r.n_isect;
     if (p.out_final_point) { double* q = p.out_final_point + 3*i; q[0] = r.point[0]; q[1] = r.point[1]; q[2] = r.point[2]; }
     if (p.out_final_power) p.out_final_power[i] = r.power;
+    if (p.out_final_medium) p.out_final_medium[i] = r.medium;
   }
 }
 
@@ -418,6 +420,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
   const DFace& f = face_table[fi];
   const int fgroup = f.group;
   const DGroup& g = groups[fgroup];
+  const int prev_medium = r.medium;
   point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];                 // ray.py:117
   if (r.medium >= 0) {                                                           // ray.py:120-125 (multiplicative)
     double L = groups[r.medium].absorption_length;
@@ -430,7 +433,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
   if (g.record || p.record_all) {
     const double ds = MC ? 1.0 : r.dscale;
     const double dir[3] = { dn[0]*ds, dn[1]*ds, dn[2]*ds };
-    record_hit(p, p.first_ray + i, r.n_isect-1, fgroup, f.face_id, point, dir, r.power, entering, s_cnt);
+    record_hit(p, p.first_ray + i, r.n_isect-1, fgroup, f.face_id, point, dir, r.power, entering, prev_medium, s_cnt);
   }
   double o[3] = { dn[0], dn[1], dn[2] };                                         // outgoing direction / its length
   double oscale = MC ? 1.0 : r.dscale;

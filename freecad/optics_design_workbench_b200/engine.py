@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get('ODW_LIB') or os.path.join(_HERE, 'libodw_b200.so')   
 EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name', 'odw_engine_stream',
            'odw_scene_create', 'odw_scene_destroy', 'odw_source_create', 'odw_source_destroy',
            'odw_trace_mc', 'odw_trace_mc_host', 'odw_sample_mc', 'odw_trace_rays', 'odw_result_counts', 'odw_result_hits',
-           'odw_result_histogram', 'odw_result_histogram_device', 'odw_result_ray_summary',
+           'odw_result_histogram', 'odw_result_histogram_device', 'odw_result_ray_summary', 'odw_result_ray_media',
            'odw_result_kernel_ms', 'odw_result_destroy']
 
 _lib = None
@@ -74,6 +74,7 @@ def load_library():
   L.odw_result_histogram.argtypes = [vp, i32, vp]
   L.odw_result_histogram_device.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
   L.odw_result_ray_summary.argtypes = [vp, vp, vp, vp]
+  L.odw_result_ray_media.argtypes = [vp, vp]
   L.odw_result_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
   L.odw_result_destroy.argtypes = [vp]; L.odw_result_destroy.restype = None
   _lib = L
@@ -152,7 +153,9 @@ class TraceResult:
     n = self.counts['rays']
     nseg, fp, fpow = np.zeros(n, dtype=np.int32), np.zeros((n, 3)), np.zeros(n)
     _check(load_library().odw_result_ray_summary(self._h, nseg.ctypes.data, fp.ctypes.data, fpow.ctypes.data))
-    return dict(n_segments=nseg, final_points=fp, final_powers=fpow)
+    med = np.zeros(n, dtype=np.int32)
+    _check(load_library().odw_result_ray_media(self._h, med.ctypes.data))
+    return dict(n_segments=nseg, final_points=fp, final_powers=fpow, final_media=med)
 
 
 class DeviceScene:

@@ -66,11 +66,13 @@ class GenericSourceProxy:
       batch = useInitialConditions if useInitialConditions is not None else self._generateRays(obj, mode='fans', **kwargs)
       if returnInitialConditions:
         return batch
-      return self._trace_explicit(obj, batch, store)
+      return self._trace_explicit(obj, batch, store, record_rays=bool(store and obj.get('RecordRays', False)))
     if mode not in ('true', 'singletrue'):
       raise ValueError(f'unexpected ray placement mode {mode}')
     if returnInitialConditions:
       raise NotImplementedError('Monte-Carlo rays are drawn on the device; use DeviceSource.sample for their initial conditions')
+    if store and obj.get('RecordRays', False) and kind == 'PointSourceProxy':
+      return self._trace_monte_carlo_recording_rays(obj, int(iterations), store)
     return self._trace_monte_carlo(obj, int(iterations), store)
 
   # -- replay source (reference freecad_elements/replay_source.py:73-166) --------------------------------
@@ -106,15 +108,51 @@ class GenericSourceProxy:
                        results_store.named((scene.group_names[gi], scene.group_labels[gi])),
                        hits['points'][sel], hits['directions'][sel], hits['powers'][sel], hits['is_entering'][sel], md)
 
-  def _trace_explicit(self, obj, batch, store):
+  def _ray_dicts(self, obj, batch, hits, summary):
+    '''
+    Per-ray polylines in the reference's *-rays.pkl form (SimulationResultsSingleRay.dump, results_store.py:241-257):
+    points = segment start points + the end of the last segment, powers = power at the start of each segment, media =
+    Name of the optical group each segment runs through (None = vacuum).  Needs every intersection recorded.
+    '''
+    scene = self.context.sim.scene
+    names = scene.group_names
+    refl = np.where(scene.groups['optical_type'] == 0, scene.groups['reflectivity'], 1.0)      # Mirror: power *= Reflectivity
+    refl = np.where(scene.groups['optical_type'] == 3, 0.0, refl)                              # Absorber: power = 0
+    order = np.lexsort((hits['bounce'], hits['ray_index']))
+    ray = hits['ray_index'][order].astype(np.int64)
+    starts = np.searchsorted(ray, np.arange(len(batch)+1))
+    out = []
+    for r in range(len(batch)):
+      sel = order[starts[r]:starts[r+1]]
+      n_seg = int(summary['n_segments'][r])
+      pts = [batch.origins[r]] + list(hits['points'][sel])
+      media = [None if m < 0 else names[m] for m in hits['medium'][sel]]
+      powers = [batch.powers[r]] + list(hits['powers'][sel]*refl[hits['group'][sel]])
+      if n_seg > len(sel):                                            # the ray escaped: its last segment has no hit
+        pts.append(summary['final_points'][r])
+        fm = int(summary['final_media'][r])
+        media.append(None if fm < 0 else names[fm])
+      else:
+        powers = powers[:-1]
+      if n_seg:
+        out.append(dict(points=np.array(pts), powers=np.array(powers[:n_seg]), media=media))
+    return out
+
+  def _trace_explicit(self, obj, batch, store, record_rays=False):
     ctx = self.context
-    cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])),
+    cfg = ctx.cfg(obj, store_hits=bool(store), record_all_hits=bool(record_rays),
+                  hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])),
                   wavelength=batch.wavelength, scatter_seed=ctx.seed,
                   max_ray_length=float(ctx.sim.settings['MaxRayLength'])*float(obj.get('MaxRayLengthScale', 1.0)),
                   max_intersections=int(float(ctx.sim.settings['MaxIntersections'])*float(obj.get('MaxIntersectionsScale', 1.0))))
     with ctx.device_scene.trace_rays(cfg, batch.origins, batch.directions, batch.powers, ignored=obj.get('ignored', ())) as res:
       counts = res.counts
       hits = res.hits(sort=True) if store else None
+      summary = res.ray_summary() if (store and record_rays) else None
+    if store and record_rays:
+      store.addRays(results_store.named((obj['name'], obj['label'])), self._ray_dicts(obj, batch, hits, summary))
+      keep = ctx.sim.scene.groups['record_hits'][hits['group']] != 0        # onRayHit only stores RecordHits groups
+      hits = {k: v[keep] for k, v in hits.items()}
     if store:
       def metadata_of(ray_index, keys):
         idx = ray_index.astype(np.int64)
@@ -130,6 +168,19 @@ class GenericSourceProxy:
       self._store_hits(obj, hits, store, metadata_of)
       store.incrementRayCount(len(batch))
     return counts
+
+  def _trace_monte_carlo_recording_rays(self, obj, iterations, store):
+    '''
+    RecordRays (generic_source.py:80-82,96-100): the same Monte-Carlo rays (same Philox stream, odw_sample_mc) as an explicit
+    list, traced with every intersection recorded so that the per-ray polylines can be written next to the hits.
+    '''
+    ctx = self.context
+    first, n = ctx.claim_rays(self.index, point_source.rays_per_iteration(obj, ctx.sim.settings)*iterations)
+    s = ctx.device_source(self.index).sample(ctx.seed, first, n)
+    finite = np.isfinite(float(obj.get('FocalLength', 0)))
+    md = dict(initPhi=s['phi'], initTheta=s['first'] if finite else np.full(n, np.nan))
+    batch = point_source.RayBatch(s['origins'], s['directions'], np.ones(n), float(obj['Wavelength']), md)
+    return self._trace_explicit(obj, batch, store, record_rays=True)
 
   def _trace_monte_carlo(self, obj, iterations, store):
     ctx = self.context

@@ -116,6 +116,8 @@ class SimulationResults:
     self.totalRecordedHits = 0
     self.hits = None           # list of (source, obj, arrays dict)
     self._bufferedHits = 0
+    self.rays = None           # list of (source, [ray dicts])
+    self._bufferedRays = 0
     self._cleanedUp = False
     self._lastFingerprintMs = 0
     self.writtenFiles = []
@@ -184,6 +186,20 @@ class SimulationResults:
     self._bufferedHits += n
     self.writeDiskIfNeeded()
 
+  def addRays(self, source, rays):
+    '''
+    Batch form of addRay / addSegment / rayComplete (results_store.py:236-257,628-639): `rays` = list of dicts
+    dict(points (M+1, 3), powers (M,), media [group Name | None]*M), one per COMPLETE ray of light source `source`.
+    '''
+    self._raiseIfCleanedUp()
+    if not rays:
+      return
+    if self.rays is None:
+      self.rays = []
+    self.rays.append((named(source), list(rays)))
+    self._bufferedRays += len(rays)
+    self.writeDiskIfNeeded()
+
   def addRayHit(self, source, obj, point, direction, power, isEntering, metadata):
     'single-hit form with the reference signature'
     md = {k: np.asarray([v]) for k, v in (metadata or {}).items()}
@@ -193,6 +209,16 @@ class SimulationResults:
     'buffered hits -> one pickle per (source, object) with a fresh fingerprint (results_store.py:369-460)'
     self._raiseIfCleanedUp()
     self._fingerprint(fresh=True)
+    if self.rays is not None:                                   # results_store.py:380-403: one list of ray dicts per source
+      by_file = {}
+      for source, rays in self.rays:
+        by_file.setdefault(self._makeFilename(kind='rays', source=source), []).extend(rays)
+      for fname, dump in by_file.items():
+        with open(fname, 'wb') as f:
+          pickle.dump(dump, f)
+        self.writtenFiles.append(fname)
+      self.totalRecordedRays += self._bufferedRays
+      self.rays, self._bufferedRays = None, 0
     if self.hits is not None:
       groups = {}
       for source, obj, entry in self.hits:
@@ -226,7 +252,7 @@ class SimulationResults:
                 totalIterations=self.totalIterations,
                 totalTracedRays=self.totalTracedRays,
                 totalRecordedHits=self.totalRecordedHits+self._bufferedHits,
-                totalRecordedRays=self.totalRecordedRays)
+                totalRecordedRays=self.totalRecordedRays+self._bufferedRays)
 
   def progressMonitorPath(self):
     return f'{self.runFolderPath()}/progress'

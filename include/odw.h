@@ -262,6 +262,8 @@ typedef struct odw_hits_view {
   int32_t*  group;               /* [n] optical group index */
   int32_t*  bounce;              /* [n] 0-based intersection number along the ray */
   int32_t*  face_id;             /* [n] */
+  int32_t*  medium;              /* [n] optical group the segment ENDING at this hit travelled through, -1 = none (currentMedium of
+                                    ray.py:117 at the yield; feeds the `media` list of *-rays.pkl, results_store.py:241-257) */
 } odw_hits_view;
 
 typedef struct odw_engine odw_engine;
@@ -314,6 +316,9 @@ int  odw_result_histogram(const odw_result*, int32_t binning, double* bins_out /
 int  odw_result_histogram_device(const odw_result*, int32_t binning, void** dptr, uint64_t* n_bins);
 /* per-ray end state for explicit lists / parity: n_segments[n] int32, final point [n][3], final power [n]; any may be NULL */
 int  odw_result_ray_summary(const odw_result*, int32_t* n_segments, double* final_points, double* final_powers);
+/* optical group each ray of an explicit list was travelling in when it ended, -1 = none (the medium of the last segment when
+ * the ray escaped; with odw_hits_view.medium this gives the `media` list of *-rays.pkl, results_store.py:241-257) */
+int  odw_result_ray_media(const odw_result*, int32_t* final_medium);
 /* kernel time of the trace (CUDA events on the engine stream), milliseconds */
 int  odw_result_kernel_ms(const odw_result*, double* ms);
 void odw_result_destroy(odw_result*);

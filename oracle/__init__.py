@@ -43,7 +43,7 @@ class Oracle:
     L.oracle_sample_mc.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_void_p]*4
     L.oracle_trace_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                     C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_trace_mc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_max_threads.restype = C.c_int
@@ -99,15 +99,15 @@ class Oracle:
     nh = C.c_uint64(0)
     counts = _abi.Counts()
     nseg = np.zeros(n, dtype=np.int32)
-    fp, fpow = np.zeros((n, 3)), np.zeros(n)
+    fp, fpow, fmed = np.zeros((n, 3)), np.zeros(n), np.zeros(n, dtype=np.int32)
     bins, sizes = self._bins(cfg)
     rc = self.lib.oracle_trace_rays(C.addressof(sa.desc), C.addressof(cfg.cfg), o.ctypes.data, d.ctypes.data,
                                     None if p is None else p.ctypes.data, float(wavelength),
                                     ign.ctypes.data if len(ign) else None, len(ign), n, int(ray_index_base),
                                     C.addressof(hits.view), C.addressof(nh), C.addressof(counts),
-                                    nseg.ctypes.data, fp.ctypes.data, fpow.ctypes.data, bins.ctypes.data, int(threads))
+                                    nseg.ctypes.data, fp.ctypes.data, fpow.ctypes.data, fmed.ctypes.data, bins.ctypes.data, int(threads))
     return dict(rc=rc, hits=hits.trimmed(nh.value, sort), counts=counts.as_dict(), n_segments=nseg,
-                final_points=fp, final_powers=fpow, histograms=self._split_bins(bins, cfg, sizes))
+                final_points=fp, final_powers=fpow, final_media=fmed, histograms=self._split_bins(bins, cfg, sizes))
 
   def trace_mc(self, scene, source, cfg, seed, first_ray, n, hit_capacity=None, threads=1, sort=True):
     sa = scene if isinstance(scene, _abi.SceneArgs) else _abi.SceneArgs(scene)

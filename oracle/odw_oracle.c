@@ -786,7 +786,7 @@ static void bin_hit(const sink_t* sk, int group, const double* P, double power) 
 }
 
 static void record_hit(const sink_t* sk, uint64_t ray_index, int bounce, int group, int face_id,
-                       const double* P, const double* dir, double power, int entering) {
+                       const double* P, const double* dir, double power, int entering, int medium) {
   bin_hit(sk, group, P, power);
   uint64_t slot;
 #ifdef _OPENMP
@@ -810,6 +810,7 @@ static void record_hit(const sink_t* sk, uint64_t ray_index, int bounce, int gro
   if (v->group)       v->group[slot] = group;
   if (v->bounce)      v->bounce[slot] = bounce;
   if (v->face_id)     v->face_id[slot] = face_id;
+  if (v->medium)      v->medium[slot] = medium;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -821,7 +822,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
                       double power0, double wavelength, double max_len, int max_isect,
                       const int32_t* ignored, int n_ignored, uint64_t ray_index, uint64_t seed, uint32_t source_id, const sink_t* sk,
                       cand_t* shell_c, cand_t* face_c, ray_stats_t* st,
-                      int32_t* n_segments, double* final_point, double* final_power) {
+                      int32_t* n_segments, double* final_point, double* final_power, int32_t* final_medium) {
   double point[3] = { origin[0], origin[1], origin[2] };
   double dir[3] = { dir0[0], dir0[1], dir0[2] };
   double power = power0;
@@ -862,7 +863,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
     for (int i = 0; i < 3; ++i) nrm[i] = entering ? -n_out[i] : n_out[i];
     /* onRayHit (:131; optical_group.py:206-209) */
     if (g->record_hits || cfg->record_all_hits)
-      record_hit(sk, ray_index, n_isect-1, f->group, f->face_id, point, dir, power, entering);
+      record_hit(sk, ray_index, n_isect-1, f->group, f->face_id, point, dir, power, entering, prev_medium);
     double dl = len3(dir);
     double dnrm[3] = { dir[0]/dl, dir[1]/dl, dir[2]/dl };
     switch (g->optical_type) {
@@ -922,6 +923,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
   if (n_segments) *n_segments = nseg;
   if (final_point) memcpy(final_point, point, 3*sizeof(double));
   if (final_power) *final_power = power;
+  if (final_medium) *final_medium = medium;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -937,7 +939,7 @@ int oracle_trace_rays(const odw_scene_desc* sc, const odw_trace_cfg* cfg,
                       const double* origins, const double* dirs, const double* powers, double wavelength,
                       const int32_t* ignored, int32_t n_ignored, uint64_t n, uint64_t ray_index_base,
                       odw_hits_view* hits, uint64_t* n_hits_out, odw_counts* counts,
-                      int32_t* n_segments, double* final_points, double* final_powers, double* bins,
+                      int32_t* n_segments, double* final_points, double* final_powers, int32_t* final_media, double* bins,
                       int n_threads) {
   uint64_t n_hits = 0, dropped = 0;
   uint64_t segs = 0, esc = 0, depth = 0;
@@ -960,7 +962,7 @@ int oracle_trace_rays(const odw_scene_desc* sc, const odw_trace_cfg* cfg,
                 cfg->scatter_seed, 0u, &sk,
                 shell_c, face_c, &st,
                 n_segments ? n_segments + i : NULL, final_points ? final_points + 3*i : NULL,
-                final_powers ? final_powers + i : NULL);
+                final_powers ? final_powers + i : NULL, final_media ? final_media + i : NULL);
     }
     segs += st.segments; esc += st.escaped; depth += st.depth_terminated;
     free(shell_c); free(face_c);
@@ -999,7 +1001,7 @@ int oracle_trace_mc(const odw_scene_desc* sc, const odw_source_desc* src, const 
       uint64_t ray = first_ray + (uint64_t)i;
       source_make_ray(src, seed, ray, NULL, NULL, o, d);
       trace_one(sc, cfg, o, d, 1.0, src->wavelength, max_len, max_isect, src->ignored_groups, src->n_ignored,
-                ray, seed, (uint32_t)src->source_id, &sk, shell_c, face_c, &st, NULL, NULL, NULL);
+                ray, seed, (uint32_t)src->source_id, &sk, shell_c, face_c, &st, NULL, NULL, NULL, NULL);
     }
     segs += st.segments; esc += st.escaped; depth += st.depth_terminated;
     free(shell_c); free(face_c);

@@ -33,6 +33,9 @@ class _Result:
   def histogram(self, index=0):
     return self._r['histograms'][index]
 
+  def ray_summary(self):
+    return {k: self._r[k] for k in ('n_segments', 'final_points', 'final_powers', 'final_media')}
+
 
 class _Scene:
   def __init__(self, orc, scene):

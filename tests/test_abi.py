@@ -45,7 +45,7 @@ def test_struct_layouts_match_header():
   assert C.sizeof(_abi.Binning) == csize(6)
   assert C.sizeof(_abi.TraceCfg) == csize(7)
   assert C.sizeof(_abi.Counts) == csize(8) == 64
-  assert C.sizeof(_abi.HitsView) == csize(9) == 72
+  assert C.sizeof(_abi.HitsView) == csize(9) == 80
 
 
 @pytest.mark.skipif(os.environ.get('ODW_EXPECT_GPU') == '1', reason='GPU box')

@@ -53,6 +53,7 @@ def compare_hits(g, o, n, max_bad_fraction=0.0, base=0, max_bounce=None, pos_tol
     o = {k: v[mo] for k, v in o.items()}
   assert np.array_equal(g['group'], o['group']) and np.array_equal(g['bounce'], o['bounce'])
   assert np.array_equal(g['is_entering'], o['is_entering'])
+  assert np.array_equal(g['medium'], o['medium'])          # medium the segment ending at the hit ran through (rays.pkl `media`)
   sel = slice(None) if max_bounce is None else (g['bounce'] <= max_bounce)
   assert np.abs(g['points'][sel]-o['points'][sel]).max(initial=0) < pos_tol
   assert np.abs(g['directions'][sel]-o['directions'][sel]).max(initial=0) < dir_tol

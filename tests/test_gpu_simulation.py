@@ -56,6 +56,21 @@ def test_simulation_run_matches_oracle_backed_run(tmp_path, gpu_engine, scene, a
       np.testing.assert_allclose(g[k], c[k], rtol=0, atol=1e-9, equal_nan=True)
 
 
+def test_record_rays_on_the_gpu_equals_oracle_backed_run(tmp_path, gpu_engine):
+  import pickle
+  out = {}
+  for label, eng in (('gpu', gpu_engine), ('cpu', OracleEngine())):
+    sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+    sim.source_records[0]['RecordRays'] = True
+    run = simulation_loop.runSimulation(sim, 'singletrue', engine=eng, basePath=str(tmp_path/f'{label}.OpticsDesign'))
+    out[label] = pickle.load(open(glob.glob(f'{run}/source-*/*-rays.pkl')[0], 'rb'))
+  assert len(out['gpu']) == len(out['cpu']) == 100
+  for g, c in zip(out['gpu'], out['cpu']):
+    assert g['media'] == c['media']
+    np.testing.assert_allclose(g['points'], c['points'], rtol=0, atol=1e-6)      # escape points: 460 mm lever arm
+    np.testing.assert_allclose(g['powers'], c['powers'], rtol=0, atol=1e-12)
+
+
 def _free_port():
   with socket.socket() as s:
     s.bind(('127.0.0.1', 0))

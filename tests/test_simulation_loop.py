@@ -213,3 +213,33 @@ def test_replay_source_re_emits_stored_hits(tmp_path, engine, oracle):
   np.testing.assert_allclose(hits['points'][key(hits['points'])], want['hits']['points'][key(want['hits']['points'])], atol=1e-9)
   np.testing.assert_allclose(hits['powers'], 0.7*np.ones(len(hits['powers'])))       # mirrors have Reflectivity 1 here
   assert hits['source'] == 'OpticalReplaySource'
+
+
+def test_record_rays_writes_the_reference_rays_file(tmp_path, engine):
+  '''
+  RecordRays (reference generic_source.py:80-100, results_store.py:241-257,380-403): *-rays.pkl = list of dict(points (M+1,3),
+  powers (M,), media [Name | None]*M) per ray, next to the hit files of the RecordHits groups.
+  '''
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  sim.source_records[0]['RecordRays'] = True
+  run = simulation_loop.runSimulation(sim, 'singletrue', engine=engine, basePath=str(tmp_path/'r.OpticsDesign'))
+  files = glob.glob(f'{run}/source-*/*-rays.pkl')
+  assert len(files) == 1 and os.path.dirname(files[0]).endswith('source-'+sim.source_records[0]['label'])
+  rays = pickle.load(open(files[0], 'rb'))
+  assert len(rays) == 100
+  full = [r for r in rays if len(r['powers']) == 7]
+  assert len(full) > 90                                  # the 7-segment path of SURVEY Appendix B
+  r = full[0]
+  assert r['points'].shape == (8, 3) and len(r['media']) == 7
+  np.testing.assert_allclose(r['points'][0], 0.0)        # the source sits at the origin
+  lens = [n for n, g in zip(sim.scene.group_names, sim.scene.groups) if int(g['optical_type']) == 1][0]
+  assert r['media'] == [None, None, lens, None, lens, None, None]
+  np.testing.assert_allclose(r['powers'], 1.0)
+  assert abs(r['points'][-1][2]-73.0) < 1e-6             # ends on the absorber box (z = 73)
+  # hit files still hold only the RecordHits groups
+  hits = load_hits(run)
+  assert len(hits['points']) >= 90 and set(np.atleast_1d(hits['obj']).tolist()) <= set(sim.scene.group_names)
+  # fans mode records rays too
+  run2 = simulation_loop.runSimulation(sim, 'fans', engine=engine, basePath=str(tmp_path/'r.OpticsDesign'))
+  rays2 = pickle.load(open(glob.glob(f'{run2}/source-*/*-rays.pkl')[0], 'rb'))
+  assert len(rays2) == 40
