@@ -165,6 +165,53 @@ def point_source_tables(rec):
   return build_tables(expr, var, dom, phi_dom, float(res), float(rec.get('PhiResolutionNumericMode', '1e2')))
 
 
+def draw_pseudo(tables, density, N, rng, overdraw_factor=0.1, overdraw_iterations=50, bins=None):
+  '''
+  Pseudo-random draws: N samples whose histogram follows the density more closely than N true random draws do
+  (reference distributions/random_number_generator.py:562-682 drawPseudo).  Start from (1 + f) N true draws; per round add
+  f N fresh draws, histogram the pool, and repeatedly delete one random sample from the bin that exceeds its expected share
+  the most until only N are left (or that bin is empty); after `overdraw_iterations` rounds return the last N kept.
+
+  tables   SamplerTables (true draws come from them);  density  sympy expression in (first variable, phi) used for the
+  expected histogram (the same expression the tables were built from);  rng  numpy Generator.
+  Returns (first, phi) arrays of length N.
+  '''
+  N = int(round(N))
+  if N <= 1:
+    raise ValueError('N must be greater than one in pseudo random mode')
+  expr = sy.sympify(density)
+  v1, v2 = sy.Symbol(tables.first_var), sy.Symbol('phi')
+  expected_of = sy.lambdify([v2, v1], expr, modules=['numpy', 'scipy'])       # reversed variable order like the reference
+  draw = lambda n: np.stack(tables.draw_from_uniforms(rng.random(n), rng.random(n)))      # rows: first, phi
+  if bins is None:
+    bins = max(1, int((overdraw_factor*np.sqrt(overdraw_iterations)*N)**(1/(3*2))))
+  pool = draw(int(round(N*(1+overdraw_factor))))
+  for it in range(int(round(overdraw_iterations))):
+    if it > 0:
+      pool = np.concatenate([pool[:, ~np.isnan(pool[0])], draw(int(round(N*overdraw_factor)))], axis=-1)
+    hist, edges = np.histogramdd(pool.T, bins=bins)
+    centres = [(e[1:]+e[:-1])/2 for e in edges]
+    expected = expected_of(*np.meshgrid(*reversed(centres)))
+    if not hasattr(expected, 'shape') or np.shape(expected) != hist.shape:
+      expected = expected*np.ones(hist.shape)
+    while True:
+      excess = hist/hist.sum()-expected/expected.sum()
+      worst = np.argwhere(excess == excess.max())[0]
+      inside = np.ones(pool.shape[1], dtype=bool)
+      for axis, k in enumerate(worst):
+        inside &= (edges[axis][k] < pool[axis]) & (pool[axis] <= edges[axis][k+1])
+      members = np.nonzero(inside)[0]
+      if len(members) == 0:
+        pool = pool[:, ~np.isnan(pool[0])][:, -N:]
+        break
+      pool[:, members[int(rng.random()*len(members))]] = np.nan
+      hist[tuple(worst)] -= 1
+      if np.count_nonzero(~np.isnan(pool[0])) <= N:
+        break
+  result = pool[:, ~np.isnan(pool[0])][:, -N:]
+  return result[0], result[1]
+
+
 def surface_source_tables(rec):
   '''
   Surface source record -> SamplerTables whose single conditional row is the theta CDF.  The reference builds a

@@ -37,6 +37,27 @@ class GenericSourceProxy:
                                             max_rays_per_fan=kwargs.get('maxRaysPerFan', np.inf))
     raise ValueError(f'unexpected ray placement mode {mode} for host-side ray generation')
 
+  def _pseudo_rays(self, obj, iterations):
+    '''
+    mode 'pseudo' (point_source.py:671-679): per iteration RaysPerIteration*scale pseudo-random (theta|r, phi) pairs from
+    drawPseudo, generated on the host (a sequential, data-dependent thinning procedure) and traced as an explicit list.
+    This rank's share of the iterations is drawn from a numpy stream derived from (seed, source id, first iteration).
+    '''
+    from ..distributions import sampler_tables as st
+    ctx = self.context
+    n_iter = point_source.rays_per_iteration(obj, ctx.sim.settings)
+    first_it, my_its = ctx.claim_rays(('pseudo', self.index), iterations)
+    sa = ctx.sim.source_args(self.index)
+    expr, _ = st.point_source_density(obj['PowerDensity'], float(obj['FocalLength']))
+    rng = np.random.default_rng([ctx.seed & 0xFFFFFFFF, ctx.seed >> 32, int(obj.get('source_id', self.index)), first_it])
+    firsts, phis = [], []
+    for _ in range(my_its):
+      f, p = st.draw_pseudo(sa.tables, expr, n_iter, rng)
+      firsts.append(f); phis.append(p)
+    firsts = np.concatenate(firsts) if firsts else np.zeros(0)
+    phis = np.concatenate(phis) if phis else np.zeros(0)
+    return point_source.make_rays(obj, obj['gpM'], firsts, phis)
+
   # -- the iteration --------------------------------------------------------------------------------
   def runSimulationIteration(self, obj=None, *, mode, draw=False, store=False, returnInitialConditions=False,
                              useInitialConditions=None, iterations=1, **kwargs):
@@ -59,11 +80,16 @@ class GenericSourceProxy:
       return self._replay_iteration(obj, mode, int(iterations), store, returnInitialConditions)
     if kind == 'SurfaceSourceProxy' and (mode in ('fans', 'multicorefans') and useInitialConditions is None):
       raise NotImplementedError('fan mode of surface sources (_makeSurfaceGrid, surface_source.py:122-267) is not on the engine yet')
-    if mode in ('pseudo', 'singlepseudo'):
-      raise NotImplementedError("pseudo-random mode (drawPseudo) is not implemented on the engine yet")
 
     if useInitialConditions is not None or mode in ('fans', 'multicorefans'):
       batch = useInitialConditions if useInitialConditions is not None else self._generateRays(obj, mode='fans', **kwargs)
+      if returnInitialConditions:
+        return batch
+      return self._trace_explicit(obj, batch, store, record_rays=bool(store and obj.get('RecordRays', False)))
+    if mode in ('pseudo', 'singlepseudo'):
+      if kind != 'PointSourceProxy':
+        raise NotImplementedError('pseudo-random mode is implemented for point sources only')
+      batch = self._pseudo_rays(obj, int(iterations))
       if returnInitialConditions:
         return batch
       return self._trace_explicit(obj, batch, store, record_rays=bool(store and obj.get('RecordRays', False)))

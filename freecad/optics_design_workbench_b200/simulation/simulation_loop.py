@@ -22,6 +22,34 @@ class SimulationEnded(RuntimeError):
   'control flow like the reference (freecad_elements/common.py:155): a light source ran dry / the run was finished'
 
 
+# ---- flag files (reference simulation/processes/simulation_loop.py:174-269) ------------------------------------
+# Empty files in <doc>.OpticsDesign/ are the reference's control channel: the Qt progress window, the toolbar's stop
+# button and FreecadDocument.runSimulation(endIf=...) (jupyter_utils/freecad_document.py:711-746) drop
+# `simulation-is-canceled` / `simulation-is-done` there, and everybody reads `simulation-is-running`.
+def _status_path(base, name):
+  return f'{base}/{name}'
+
+def query_status(base, name):
+  return os.path.exists(_status_path(base, name))
+
+def set_status(base, name, state):
+  path = _status_path(base, name)
+  if state and not os.path.exists(path):
+    os.makedirs(base, exist_ok=True)
+    with open(path, 'w'):
+      pass
+  elif not state and os.path.exists(path):
+    try:
+      os.remove(path)
+    except FileNotFoundError:
+      pass
+
+def cancelSimulation(basePath):
+  'what the stop action does (simulation_loop.py:249-251)'
+  if query_status(basePath, 'simulation-is-running'):
+    set_status(basePath, 'simulation-is-canceled', True)
+
+
 DEFAULT_SEED = 0x0DDB1A5E
 ACTIONS = ('fans', 'singlepseudo', 'singletrue', 'pseudo', 'true')
 
@@ -113,8 +141,6 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
   '''
   if action not in ACTIONS:
     raise ValueError(f'unknown simulation action {action}')
-  if action in ('pseudo', 'singlepseudo'):
-    raise NotImplementedError('pseudo-random mode (drawPseudo, reference random_number_generator.py:562-682) is not on the engine yet')
   sim = project if isinstance(project, PreparedSimulation) else prepare(project)
   if settings:
     sim.settings.update(settings)
@@ -129,6 +155,10 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
       raise ValueError('basePath (the <name>.OpticsDesign folder) is required when the project is not a .FCStd path')
   continuous = action in ('true', 'pseudo')
   mode = action
+  if rank == 0:                                    # simulation_loop.py:323-334: fresh flags for this run
+    set_status(basePath, 'simulation-is-canceled', False)
+    set_status(basePath, 'simulation-is-done', False)
+    set_status(basePath, 'simulation-is-running', True)
   s = sim.settings
   run_folder = results_store.generate_simulation_folder_name(basePath) if rank == 0 else None
   if rank == 0:
@@ -159,7 +189,7 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
           if rank == 0:
             src.runSimulationIteration(mode='fans', store=store)
         else:
-          src.runSimulationIteration(mode='true', store=store, iterations=1)
+          src.runSimulationIteration(mode='pseudo' if mode == 'singlepseudo' else 'true', store=store, iterations=1)
       store.incrementIterationCount()
     else:
       has_replay = any(r.get('proxy') == 'ReplaySourceProxy' for r in sim.source_records)
@@ -173,7 +203,7 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
         ended = False
         for src in sources:
           try:
-            src.runSimulationIteration(mode='true', store=store, iterations=k)
+            src.runSimulationIteration(mode='pseudo' if mode == 'pseudo' else 'true', store=store, iterations=k)
           except SimulationEnded:
             ended = True                                          # a replay source ran out of rays (replay_source.py:160-161)
         store.incrementIterationCount(k)
@@ -185,12 +215,21 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
         store._global = total
         if rank == 0:
           store.dumpMasterProgress(total)
-        if store.isEndReached(total) or ended:
+        stop = query_status(basePath, 'simulation-is-canceled') or query_status(basePath, 'simulation-is-done')
+        if world > 1:                                             # all ranks leave the loop in the same batch
+          stop = bool(sharding.all_reduce_counters(dict(stop=int(stop)))['stop'])
+        if store.isEndReached(total):
+          if rank == 0:
+            set_status(basePath, 'simulation-is-done', True)      # results_store.py:507-512 -> setIsFinished(True)
+          break
+        if ended or stop:
           break
         batch_rays = min(maxBatchRays, batch_rays*4)            # grow while only EndAfterHits is pending
   finally:
     store.flush()
     sharding.barrier()
+    if rank == 0:
+      set_status(basePath, 'simulation-is-running', False)        # simulation_loop.py:726-775
     if not keepProgressFiles:
       if rank == 0:
         store.cleanup()

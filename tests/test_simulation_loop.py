@@ -153,8 +153,6 @@ def test_unknown_action_and_missing_end_criterion(tmp_path, engine):
   with pytest.raises(ValueError):
     simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=str(tmp_path/'b'),
                                   settings=dict(EndAfterRays=np.inf, EndAfterHits=np.inf, EndAfterIterations=np.inf))
-  with pytest.raises(NotImplementedError):
-    simulation_loop.runSimulation(sim, 'pseudo', engine=engine, basePath=str(tmp_path/'c'), settings=dict(EndAfterRays=10))
 
 
 @pytest.mark.reference
@@ -243,3 +241,66 @@ def test_record_rays_writes_the_reference_rays_file(tmp_path, engine):
   run2 = simulation_loop.runSimulation(sim, 'fans', engine=engine, basePath=str(tmp_path/'r.OpticsDesign'))
   rays2 = pickle.load(open(glob.glob(f'{run2}/source-*/*-rays.pkl')[0], 'rb'))
   assert len(rays2) == 40
+
+
+def test_flag_files_cancel_a_running_simulation(tmp_path, engine):
+  'the reference protocol: simulation-is-running while it runs, simulation-is-canceled / -done stop it between batches'
+  import threading
+  base = str(tmp_path/'c.OpticsDesign')
+  sim = prepare(os.path.join(SCENES, 'minimal.npz'))
+  seen = {}
+  def canceller():
+    import time
+    for _ in range(2000):
+      if simulation_loop.query_status(base, 'simulation-is-running'):
+        seen['running'] = True
+        simulation_loop.cancelSimulation(base)
+        return
+      time.sleep(0.005)
+  t = threading.Thread(target=canceller); t.start()
+  run = simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=base, settings=dict(EndAfterRays=1e9), maxBatchRays=20000)
+  t.join()
+  assert seen.get('running') and not simulation_loop.query_status(base, 'simulation-is-running')
+  assert simulation_loop.query_status(base, 'simulation-is-canceled')
+  n = len(load_hits(run)['points'])
+  assert 0 < n < 1e8                                      # stopped long before EndAfterRays; what was traced is on disk
+  # a run that reaches its end criterion marks itself done
+  simulation_loop.runSimulation(sim, 'true', engine=engine, basePath=base, settings=dict(EndAfterRays=500), maxBatchRays=200)
+  assert simulation_loop.query_status(base, 'simulation-is-done') and not simulation_loop.query_status(base, 'simulation-is-canceled')
+
+
+def test_pseudo_mode_thins_towards_its_expected_histogram(tmp_path, engine):
+  '''
+  'pseudo' / 'singlepseudo' (reference point_source.py:671-679 -> drawPseudo, random_number_generator.py:562-682).  The
+  procedure deletes samples from the histogram bin that exceeds its expected share (density at the bin centre, a coarse
+  int((f sqrt(iterations) N)**(1/6))-bin grid) the most; so measured with ITS criterion the result is closer to the
+  expectation than true random draws of the same size.  (With the default 100 rays per iteration that grid is 2x2 — the
+  mode exists for nicer looking displayed rays, not for accuracy.)
+  '''
+  import sympy as sy
+  from freecad.optics_design_workbench_b200.distributions import sampler_tables as st
+  sim = prepare(os.path.join(SCENES, 'hugeArray.npz'))             # exp(-theta^2/0.2^2): a wide beam
+  rec = sim.source_records[0]
+  tables = sim.source_args(0).tables
+  expr, _ = st.point_source_density(rec['PowerDensity'], float(rec['FocalLength']))
+  lam = sy.lambdify([sy.Symbol('phi'), sy.Symbol('theta')], expr, modules=['numpy'])
+  rng = np.random.default_rng(5)
+  N, bins = 4000, 3                                                # int((0.1*sqrt(50)*4000)**(1/6)) = 3
+  def misfit(theta, phi):
+    hist, edges = np.histogramdd(np.stack([theta, phi]).T, bins=bins)
+    c = [(e[1:]+e[:-1])/2 for e in edges]
+    expected = lam(*np.meshgrid(*reversed(c)))
+    return np.abs(hist/hist.sum()-expected/expected.sum()).max()
+  th, ph = st.draw_pseudo(tables, expr, N, rng)
+  assert len(th) == len(ph) == N and th.min() >= 0 and th.max() <= np.pi/4 and ph.min() >= 0 and ph.max() <= 2*np.pi
+  t2, p2 = tables.draw_from_uniforms(rng.random(N), rng.random(N))
+  assert misfit(th, ph) < misfit(t2, p2)
+  a = st.draw_pseudo(tables, expr, 100, np.random.default_rng(1))
+  b = st.draw_pseudo(tables, expr, 100, np.random.default_rng(1))
+  np.testing.assert_array_equal(a[0], b[0])                        # reproducible for a given stream
+  run = simulation_loop.runSimulation(prepare(os.path.join(SCENES, 'minimal.npz')), 'singlepseudo', engine=engine,
+                                      basePath=str(tmp_path/'p.OpticsDesign'))
+  assert len(load_hits(run)['points']) == 100
+  run = simulation_loop.runSimulation(prepare(os.path.join(SCENES, 'minimal.npz')), 'pseudo', engine=engine,
+                                      basePath=str(tmp_path/'p.OpticsDesign'), settings=dict(EndAfterRays=250), maxBatchRays=200)
+  assert len(load_hits(run)['points']) == 300
