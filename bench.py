@@ -325,7 +325,7 @@ def main():
       line['e2e'] = dict(value=e_segs_all/e_seconds, unit=UNIT, h2d_bytes_per_step=e2e['h2d'], d2h_bytes_per_step=e2e['d2h'],
                          note='odw_trace_mc_host: hit lists (points, directions, powers, isEntering, group) delivered into pinned host arrays, '
                               'device->host copy of chunk c overlapped with the trace of chunk c+1')
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0)
       cb, _, _ = cpu_baseline(sim, 1, args.cpu_sample_rays, 'scalar C restatement (oracle/odw_oracle.c), 1 thread')
       line['cpu_baseline'] = cb
     print(json.dumps(line), flush=True)
