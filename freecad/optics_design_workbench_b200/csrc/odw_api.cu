@@ -653,8 +653,14 @@ static int ensure_bvh_margin(odw_scene* sc, float margin) {
   return ODW_OK;
 }
 
-static void set_ignore(TraceParams& p, const int32_t* ign, int n) {
-  for (int i = 0; i < n; ++i) if (ign[i] >= 0 && ign[i] < 256) p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
+// IgnoredOpticalElements as a 256-bit mask; a group index the mask cannot hold is an error, never silently not ignored
+static int set_ignore(TraceParams& p, const int32_t* ign, int n) {
+  for (int i = 0; i < n; ++i) {
+    if (ign[i] < 0) continue;
+    if (ign[i] >= 256) return fail(ODW_EUNSUPPORTED, "ignored optical group index " + std::to_string(ign[i]) + " >= 256");
+    p.ignore_mask[ign[i] >> 6] |= 1ull << (ign[i] & 63);
+  }
+  return ODW_OK;
 }
 
 // One wave of the wavefront formulation (BVH scenes, see odw_wavefront.cu): generate, then per bounce traverse + interact
@@ -767,7 +773,7 @@ extern "C" int odw_trace_mc(odw_scene* sc, odw_source* src, const odw_trace_cfg*
   p.max_len = cfg->max_ray_length*src->max_ray_length_scale;                 // ray.py:48-53
   p.max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
   p.wavelength = src->d.wavelength;
-  set_ignore(p, src->ignored.data(), (int)src->ignored.size());
+  if ((rc = set_ignore(p, src->ignored.data(), (int)src->ignored.size()))) { odw_result_destroy(*out); *out = nullptr; return rc; }
   set_cull_margin(p, sc, src->origin_bound);
   if ((rc = ensure_bvh_margin(sc, p.cull_margin))) { odw_result_destroy(*out); *out = nullptr; return rc; }
   rc = run_trace(eng, sc, *out, p, true);
@@ -802,7 +808,7 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
     p[b].max_len = cfg->max_ray_length*src->max_ray_length_scale;
     p[b].max_isect = (int)(cfg->max_intersections*src->max_intersections_scale);
     p[b].wavelength = src->d.wavelength;
-    set_ignore(p[b], src->ignored.data(), (int)src->ignored.size());
+    if ((rc = set_ignore(p[b], src->ignored.data(), (int)src->ignored.size()))) { cleanup(); return rc; }
     set_cull_margin(p[b], sc, src->origin_bound);
     if ((rc = ensure_bvh_margin(sc, p[b].cull_margin))) { cleanup(); return rc; }
   }
@@ -912,7 +918,7 @@ extern "C" int odw_trace_rays(odw_scene* sc, const odw_trace_cfg* cfg, const dou
   p.first_ray = 0;
   p.seed = cfg->scatter_seed; p.src.source_id = 0;       // Philox stream of the stochastic-surface draws of an explicit list
   p.wavelength = cfg->wavelength > 0 ? cfg->wavelength : 500.0;
-  set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0);
+  if ((rc = set_ignore(p, ignored_groups, ignored_groups ? n_ignored : 0))) return bail(rc);
   double origin_bound = 0;
   for (uint64_t i = 0; i < 3*n_rays; ++i) origin_bound = std::max(origin_bound, std::fabs(origins[i]));
   if (!std::isfinite(origin_bound)) return bail(fail(ODW_EINVAL, "odw_trace_rays: non-finite ray origin"));
