@@ -137,3 +137,34 @@ def test_face_aabb_contains_the_face():
     v = rng.uniform(f['uv_min'][1], f['uv_max'][1], 2000)
     p = sc.eval_face(f, u, v)
     assert np.all(p >= f['aabb_min']-1e-12) and np.all(p <= f['aabb_max']+1e-12)
+
+
+@pytest.mark.reference
+def test_live_export_from_freecad_like_objects():
+  '''
+  scene_export/freecad_live.py with stand-ins for FreeCAD objects: Shape.exportBrepToString() returns the stored BRep of
+  benchmark/minimal.FCStd's absorber box, the placement matrices are what allCoordinateTransformMatrices would give.
+  '''
+  import types, zipfile
+  from freecad.optics_design_workbench_b200.scene_export import freecad_live, fcstd
+  path = os.path.join(REF, 'benchmark', 'minimal.FCStd')
+  doc = fcstd.FCStdDocument(path)
+  group = doc.optical_groups()[0]
+  child = doc.objects[group.get('ElementList')[0]]
+  text = zipfile.ZipFile(path).read(child.get('Shape')).decode()
+  gp = doc.global_placements(group)[0][0]
+  class M:                                                  # FreeCAD.Matrix look-alike
+    def __init__(self, a):
+      for r in range(4):
+        for c in range(4):
+          setattr(self, f'A{r+1}{c+1}', float(a[r, c]))
+  pM = group.placement
+  obj = types.SimpleNamespace(Name=group.Name, Label=group.Label, OpticalType='Absorber', RecordHits=True,
+                              Shape=types.SimpleNamespace(exportBrepToString=lambda: text))
+  # group.Shape = pM * child shape in the reference; the stored child BRep stands in for it, so pMi = identity here
+  scene, info = freecad_live.build_scene([obj], lambda g: [[M(gp), M(np.linalg.inv(gp)), M(np.eye(4)), M(np.eye(4))]])
+  ref_scene, _ = fcstd.build_scene(doc)
+  assert len(scene.faces) == len(ref_scene.faces) == 6 and not info['skipped']
+  np.testing.assert_allclose(np.sort(scene.faces['aabb_min'], axis=0), np.sort(ref_scene.faces['aabb_min'], axis=0), atol=1e-12)
+  np.testing.assert_allclose(np.sort(scene.faces['aabb_max'], axis=0), np.sort(ref_scene.faces['aabb_max'], axis=0), atol=1e-12)
+  assert scene.group_names == ref_scene.group_names and int(scene.groups[0]['record_hits']) == 1
