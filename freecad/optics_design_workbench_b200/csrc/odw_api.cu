@@ -40,6 +40,9 @@ struct odw_engine {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks (odw_trace_mc_host)
+  static const int MAX_WAVE_STREAMS = 4;
+  cudaStream_t wave_stream[MAX_WAVE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] = stream; launch waves rotate over them, so that the tail of one wave overlaps the head of the next
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_WAVE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_trace[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
   Counters* pinned_counters = nullptr;  // [2], page-locked
@@ -139,6 +142,10 @@ extern "C" int odw_engine_create(int device_id, odw_engine** out) {
   eng->name = prop.name;
   CU(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&eng->copy_stream, cudaStreamNonBlocking));
+  eng->wave_stream[0] = eng->stream;
+  for (int i = 1; i < odw_engine::MAX_WAVE_STREAMS; ++i) CU(cudaStreamCreateWithFlags(&eng->wave_stream[i], cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&eng->ev_fork, cudaEventDisableTiming));
+  for (int i = 1; i < odw_engine::MAX_WAVE_STREAMS; ++i) CU(cudaEventCreateWithFlags(&eng->ev_join[i], cudaEventDisableTiming));
   CU(cudaEventCreate(&eng->ev0));
   CU(cudaEventCreate(&eng->ev1));
   for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&eng->ev_trace[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&eng->ev_copy[i], cudaEventDisableTiming)); }
@@ -156,6 +163,8 @@ extern "C" void odw_engine_destroy(odw_engine* eng) {
   for (int i = 0; i < 2; ++i) { if (eng->ev_trace[i]) cudaEventDestroy(eng->ev_trace[i]); if (eng->ev_copy[i]) cudaEventDestroy(eng->ev_copy[i]); }
   if (eng->pinned_counters) cudaFreeHost(eng->pinned_counters);
   if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
+  for (int i = 1; i < odw_engine::MAX_WAVE_STREAMS; ++i) { if (eng->wave_stream[i]) cudaStreamDestroy(eng->wave_stream[i]); if (eng->ev_join[i]) cudaEventDestroy(eng->ev_join[i]); }
+  if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
   if (eng->stream) cudaStreamDestroy(eng->stream);
   delete eng;
 }
@@ -707,15 +716,27 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
   // persistent grid: a multiple of the SM count, no more blocks than there is work
   const int blocks = eng->sm_count*per_sm;
-  // Waves: a long request is issued as back-to-back launches of `wave` rays each.  Every launch starts all CTAs
-  // in the same phase of the bounce loop; inside one very long launch the CTAs drift apart, their combined
-  // instruction working set no longer fits the shared instruction cache levels and the kernel slows down by ~35 %
-  // (measured on B200, lensesAndMirrors: 1e8 rays in one launch 146 ms, in 48 launches of 2^21 rays 106 ms).  Launches are
-  // asynchronous on one stream, so there is no host gap between them.
-  uint64_t wave = sc->use_bvh ? (1ull << 24) : (1ull << 21);   // BVH scenes: big waves amortise the per-bounce host round trip
+  // Waves: a long request is issued as launches of `wave` rays each.  Every launch starts all CTAs in the same phase of
+  // the bounce loop; inside one very long launch the CTAs drift apart, their combined instruction working set no longer
+  // fits the shared instruction cache levels and the kernel slows down by ~35 % (measured on B200, lensesAndMirrors: 1e8
+  // rays in one launch 146 ms, in 48 launches of 2^21 rays 106 ms).  A wave, however, drains unevenly (its last rays keep
+  // a few CTAs busy while the others have exited): back to back on ONE stream that tail cost a third of the time.  The
+  // waves therefore rotate over 4 streams — CTAs of the next waves take the freed slots — and are small (2^18 rays, about
+  // 2 rays per lane of the grid): 59 ms -> 40 ms per 1e8 rays (stream count / wave size sweep in profiles/README.md).
+  uint64_t wave = sc->use_bvh ? (1ull << 24)                   // BVH scenes: big waves amortise the per-bounce host round trip
+                              : (sc->d.n_faces <= 8 ? (1ull << 20) : (1ull << 18));   // trivial scenes are launch-latency bound
   if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
   wave = std::min<uint64_t>(wave, 1ull << 31);
-  for (uint64_t off = 0; off < p.n_rays; off += wave) {
+  // Hit append and counters are atomic, so overlapping waves of one request are safe.
+  int n_streams = odw_engine::MAX_WAVE_STREAMS;
+  if (const char* w = getenv("ODW_STREAMS")) n_streams = std::max(1, std::min(odw_engine::MAX_WAVE_STREAMS, atoi(w)));
+  if ((sc->use_bvh && sc->wavefront) || p.n_rays <= wave) n_streams = 1;
+  if (n_streams > 1) {
+    CU(cudaEventRecord(eng->ev_fork, eng->stream));
+    for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
+  }
+  uint64_t wave_index = 0;
+  for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
     q.n_rays = std::min<uint64_t>(wave, p.n_rays - off);
     q.first_ray = p.first_ray + off;
@@ -735,9 +756,10 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     const uint64_t tpb = (uint64_t)odw_trace_threads();
     uint64_t want_w = (q.n_rays + tpb - 1)/tpb;
     int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
-    CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->stream));
+    CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->wave_stream[wave_index % (uint64_t)n_streams]));
     if (launches) ++*launches;
   }
+  for (int i = 1; i < n_streams; ++i) { CU(cudaEventRecord(eng->ev_join[i], eng->wave_stream[i])); CU(cudaStreamWaitEvent(eng->stream, eng->ev_join[i], 0)); }
   return ODW_OK;
 }
 
