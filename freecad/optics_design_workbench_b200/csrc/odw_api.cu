@@ -301,6 +301,77 @@ struct BvhBuilder {
 
 static std::vector<uint32_t> build_guide(const double* cdf, int n);
 
+// ---- convex shells ---------------------------------------------------------------------------------------------
+// A shell bounds a convex solid iff every tangent plane of its surface is a supporting plane.  Checked on samples:
+// corner / boundary points of planar faces, a 17x17 (u, v) grid (end points included) of sphere / cylinder / cone faces
+// trimmed to a (u, v) box.  Anything else (torus, curved faces with loop trims, open shells of one face) is "not convex".
+// Used to skip a shell for the segment that starts on it and points away from it (odw_trace.cuh interact()).
+namespace {
+struct Sample { double p[3], n[3]; };
+
+void face_point_normal(const odw_face& f, double u, double v, Sample& s) {
+  const double cu = std::cos(u), su = std::sin(u);
+  double rad[3], g[3];
+  for (int i = 0; i < 3; ++i) rad[i] = cu*f.xdir[i] + su*f.ydir[i];
+  switch (f.kind) {
+    case ODW_SURF_PLANE:
+      for (int i = 0; i < 3; ++i) { s.p[i] = f.origin[i] + u*f.xdir[i] + v*f.ydir[i]; g[i] = f.zdir[i]; }
+      break;
+    case ODW_SURF_CYLINDER:
+      for (int i = 0; i < 3; ++i) { s.p[i] = f.origin[i] + f.p0*rad[i] + v*f.zdir[i]; g[i] = rad[i]; }
+      break;
+    case ODW_SURF_CONE: {
+      const double sa = std::sin(f.p1), ca = std::cos(f.p1), r = f.p0 + v*sa, sg = r >= 0 ? 1.0 : -1.0;
+      for (int i = 0; i < 3; ++i) { s.p[i] = f.origin[i] + r*rad[i] + v*ca*f.zdir[i]; g[i] = sg*(ca*rad[i]*sg - sa*f.zdir[i]); }
+      break;
+    }
+    default: {   // sphere
+      const double cv = std::cos(v), sv = std::sin(v);
+      for (int i = 0; i < 3; ++i) { g[i] = cv*rad[i] + sv*f.zdir[i]; s.p[i] = f.origin[i] + f.p0*g[i]; }
+    }
+  }
+  const double l = std::sqrt(g[0]*g[0] + g[1]*g[1] + g[2]*g[2]);
+  for (int i = 0; i < 3; ++i) s.n[i] = (double)f.nsign*g[i]/l;
+}
+
+bool shell_is_convex(const odw_scene_desc* sd, int face_first, int face_count) {
+  if (face_count < 2 && !(face_count == 1 && sd->faces[face_first].kind == ODW_SURF_SPHERE && sd->faces[face_first].trim_kind == ODW_TRIM_NONE))
+    return false;                                        // a single open face bounds nothing (a whole sphere does)
+  std::vector<Sample> samples;
+  double scale = 0;
+  for (int fi = face_first; fi < face_first + face_count; ++fi) {
+    const odw_face& f = sd->faces[fi];
+    if (f.kind == ODW_SURF_TORUS) return false;
+    Sample s;
+    if (f.kind == ODW_SURF_PLANE) {
+      if (f.trim_kind == ODW_TRIM_UVBOX) {
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { face_point_normal(f, a ? f.uv_max[0] : f.uv_min[0], b ? f.uv_max[1] : f.uv_min[1], s); samples.push_back(s); }
+      } else if (f.trim_kind == ODW_TRIM_LOOPS) {
+        for (int k = f.seg_first; k < f.seg_first + f.seg_count; ++k) {
+          const odw_trimseg& g = sd->segs[k];
+          if (g.kind == ODW_SEG_LINE) { face_point_normal(f, g.a[0], g.a[1], s); samples.push_back(s); face_point_normal(f, g.a[2], g.a[3], s); samples.push_back(s); }
+          else for (int m = 0; m <= 16; ++m) { const double ang = g.a[3] + g.a[4]*m/16.0; face_point_normal(f, g.a[0] + g.a[2]*std::cos(ang), g.a[1] + g.a[2]*std::sin(ang), s); samples.push_back(s); }
+        }
+      } else return false;
+    } else {
+      if (f.trim_kind == ODW_TRIM_LOOPS) return false;
+      double u0 = f.uv_min[0], u1 = f.uv_max[0], v0 = f.uv_min[1], v1 = f.uv_max[1];
+      if (f.trim_kind == ODW_TRIM_NONE) { u0 = 0; u1 = ODW_TWO_PI; v0 = -ODW_TWO_PI/4; v1 = ODW_TWO_PI/4; }
+      for (int a = 0; a <= 16; ++a) for (int b = 0; b <= 16; ++b) { face_point_normal(f, u0 + (u1 - u0)*a/16.0, v0 + (v1 - v0)*b/16.0, s); samples.push_back(s); }
+    }
+    if (samples.size() > 20000) return false;            // huge shells (tessellated bodies): not worth the quadratic test
+  }
+  for (const Sample& s : samples) for (int i = 0; i < 3; ++i) scale = std::max(scale, std::fabs(s.p[i]));
+  const double eps = 1e-9*std::max(1.0, scale);
+  for (const Sample& a : samples)
+    for (const Sample& b : samples) {
+      const double d = a.n[0]*(b.p[0] - a.p[0]) + a.n[1]*(b.p[1] - a.p[1]) + a.n[2]*(b.p[2] - a.p[2]);
+      if (d > eps) return false;
+    }
+  return true;
+}
+}  // namespace
+
 // odw_face -> the record the kernels read.  fast_paths: precompute the inline-test constants of the trace kernel
 // (emitting faces of a surface source are only evaluated / trim-tested, never intersected: no fast paths there).
 static void fill_dface(const odw_face& f, const odw_trimseg* segs, bool fast_paths, DFace& d) {
@@ -362,6 +433,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   // shells: the reference culls per shell box first; faces of one shell must be contiguous (odw.h: "sorted by shell")
   std::vector<DShell> shells;
   double extent = 0;                           // max |coordinate| of the scene (feeds the fp32 culling margin)
+  bool skip_convex = true;
+  if (const char* w = getenv("ODW_SKIP_CONVEX")) skip_convex = atoi(w) != 0;
   auto make_shell = [&](int face_first, int face_count, int group) {
     DShell d; memset(&d, 0, sizeof d);
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -372,6 +445,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
       if (face_count > 0) extent = std::max(extent, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
     }
     d.face_first = face_first; d.face_count = face_count; d.group = group;
+    d.convex = (skip_convex && shell_is_convex(sd, face_first, face_count)) ? 1 : 0;
+    for (int f = face_first; f < face_first + face_count; ++f) faces[(size_t)f].shell = (int32_t)shells.size();
     if (face_count > 0) { d.seqmask[0] = faces[(size_t)face_first].seqmask[0]; d.seqmask[1] = faces[(size_t)face_first].seqmask[1]; }
     return d;
   };

@@ -20,7 +20,8 @@ struct DFace {
   int32_t kind, trim, nsign, group;
   int32_t seg_first, seg_count, face_id, flags;
   unsigned long long seqmask[2];   // bit s set <=> the face's group is in SequentialModeElements step s
-  double c0, c1, c2, c3;           // fast-path constants: plane (o.z, o.x, o.y) | sphere/cylinder axial bounds (lo, hi)
+  double c0, c1, c2;               // fast-path constants: plane (o.z, o.x, o.y) | sphere/cylinder axial bounds (lo, hi)
+  int32_t shell, pad_c;            // index of the face's shell (DScene::shells)
 };
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
 #define DFACE_FAST   2             // plane/uvbox, plane/disc, sphere (whole or full-u cap), cylinder (full-u band): inline test
@@ -33,7 +34,9 @@ struct DShell {                    // 64 B
   float lo[3], hi[3];
   int32_t face_first, face_count;
   unsigned long long seqmask[2];
-  int32_t group, pad[3];
+  int32_t group;
+  int32_t convex;                  // the shell bounds a convex solid: a ray leaving its surface outwards cannot hit it again
+  int32_t pad[2];
 };
 
 struct DGroup {

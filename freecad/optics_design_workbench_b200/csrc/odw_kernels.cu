@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   // i = index of the lane's current ray; a lane steps through the launch by the grid size
   unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
   double point[3] = {0, 0, 0}, dn[3] = {0, 0, 1}, dscale = 1, power = 0;
-  int medium = -1, seq_index = 0, n_isect = 0;
-  const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+  int medium = -1, seq_index = 0, n_isect = 0, skip_shell = -1;
+  const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
   bool alive = false;
   for (;;) {
     if (!alive && i < p.n_rays) { fetch_ray<MC>(p, i, r); alive = true; }
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
         ++n_isect;
         double t;
         const int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
-                           : find_nearest_smem(sshells, sfaces, p, point, dn, medium, seq_index, p.max_len, t);
-        done = interact<MC>(p, BVH ? p.scene.faces : sfaces, groups, fi, t, i, r, s_cnt);
+                           : find_nearest_smem(sshells, sfaces, p, point, dn, medium, seq_index, skip_shell, p.max_len, t);
+        done = interact<MC>(p, BVH ? p.scene.faces : sfaces, BVH ? nullptr : sshells, groups, fi, t, i, r, s_cnt);
       }
       if (done) { finish_ray<MC>(p, i, r, s_cnt); alive = false; i += stride; }
     }

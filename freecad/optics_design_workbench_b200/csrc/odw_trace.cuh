@@ -142,7 +142,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
 // of all executed instructions (fmin/fmax on doubles are multi-instruction sequences; FMNMX is one).
 __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DFace* sfaces, const TraceParams& p,
                                                  const double* s, const double* dn,
-                                                 int medium, int seq_index, double max_len, double& t_out) {
+                                                 int medium, int seq_index, int skip_shell, double max_len, double& t_out) {
   const double tol = p.tol;
   const double tmax = max_len + tol;
   NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = tmax; h.fA = -1; h.fB = -1;
@@ -155,6 +155,7 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
   const int ns = p.scene.n_shells;
   for (int si = 0; si < ns; ++si) {
     const DShell& sh = sshells[si];
+    if (si == skip_shell) continue;
     if (!seq_off && (seq_dead || !((sh.seqmask[sw] >> sb) & 1ull))) continue;
     float ta = (sh.lo[0] - sx)*ix, tb = (sh.hi[0] - sx)*ix;             // NaN (0*inf) is dropped by fminf/fmaxf
     float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
@@ -346,6 +347,7 @@ __device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long
 struct RayState {
   double* point; double* dn; double& dscale; double& power;
   int& medium; int& seq_index; int& n_isect;
+  int& skip_shell;     // shell the next segment cannot hit (it starts on that convex shell and points away from it), -1 = none
 };
 
 // next ray: Monte-Carlo draw (Philox counter = global ray index) or row i of the explicit list
@@ -366,7 +368,7 @@ __device__ __forceinline__ void fetch_ray(const TraceParams& p, unsigned long lo
   const double d2 = dot3(r.dn, r.dn), li = fast_rsqrt(d2);
   r.dn[0] *= li; r.dn[1] *= li; r.dn[2] *= li;
   if (!MC) r.dscale = d2*li;            // Monte-Carlo rays start (and stay, to rounding) unit: no length to carry
-  r.medium = -1; r.seq_index = 0; r.n_isect = 0;
+  r.medium = -1; r.seq_index = 0; r.n_isect = 0; r.skip_shell = -1;
 }
 
 // the ray has ended: count its segments, write the per-ray summary of explicit lists.  CNT: shared-memory counters
@@ -409,7 +411,7 @@ __device__ __noinline__ Vec3 apply_scatter(const DScatter* scatters, int main_i,
 // Everything Ray.traceRay does after findNearestIntersection returned (ray.py:105-281): escape segment, or move to the
 // hit, absorption in the traversed medium, normal, onRayHit, the OpticalType rule.  true = the ray has ended.
 template <bool MC>
-__device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face_table, const DGroup* __restrict__ groups,
+__device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face_table, const DShell* shells, const DGroup* __restrict__ groups,
                                          int fi, double t, unsigned long long i, const RayState& r, unsigned int* s_cnt) {
   double* point = r.point; double* dn = r.dn;
   if (fi < 0) {                                                                  // ray.py:105-109
@@ -485,6 +487,13 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
     default: ++r.seq_index; break;                                               // Vacuum, ray.py:276-277
   }
   if (r.power < p.power_tol) return true;                                        // ray.py:280
+  // A ray that leaves the surface of a convex solid outwards cannot meet that solid again: its shell is skipped on the
+  // next segment (the reference tests it and finds nothing beyond distTol).  n_out = entering ? -nrm : nrm.
+  r.skip_shell = -1;
+  if (shells && shells[f.shell].convex) {
+    const double out = dot3(o, nrm);
+    if (entering ? out < 0 : out > 0) r.skip_shell = f.shell;
+  }
   // next segment: unit direction and the length the reference would carry along
   const double o2 = dot3(o, o), li = fast_rsqrt(o2);
   dn[0] = o[0]*li; dn[1] = o[1]*li; dn[2] = o[2]*li;

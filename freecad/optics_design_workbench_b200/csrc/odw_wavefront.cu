@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
   const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
   if (idx < n) {
     double point[3], dn[3], dscale = 1, power = 0;
-    int medium = -1, seq_index = 0, n_isect = 0;
-    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+    int medium = -1, seq_index = 0, n_isect = 0, skip_shell = -1;
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
     fetch_ray<MC>(p, idx, r);
     if (p.max_isect <= 0) {                                                      // ray.py:96-98 before the first segment
       atomicAdd(&s_cnt[CNT_DEPTH], 1u);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ Trace
   const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
   bool survive = false;
   double point[3], dn[3], dscale = 1, power = 0;
-  int medium = -1, seq_index = 0, n_isect = bounce + 1;          // every ray of this wave has done `bounce` segments before
+  int medium = -1, seq_index = 0, n_isect = bounce + 1, skip_shell = -1;   // every ray of this wave has done `bounce` segments before
   unsigned long long i = 0;
   if (idx < n) {
     const double2 a0 = pool_in.a0[idx], a1 = pool_in.a1[idx], a2 = pool_in.a2[idx], a3 = pool_in.a3[idx];
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ Trace
     point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
     power = a3.x; dscale = a3.y; i = a4.x;
     medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
-    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
-    bool done = interact<MC>(p, p.scene.faces, p.scene.groups, (int)__double_as_longlong(h.y), h.x, i, r, s_cnt);
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
+    bool done = interact<MC>(p, p.scene.faces, nullptr, p.scene.groups, (int)__double_as_longlong(h.y), h.x, i, r, s_cnt);
     if (!done && n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); done = true; }   // ray.py:96-98
     if (done) finish_ray<MC>(p, i, r, s_cnt);
     survive = !done;
@@ -252,20 +252,20 @@ __global__ void __launch_bounds__(256) wf_tail(const __grid_constant__ TracePara
   const unsigned int idx = blockIdx.x*blockDim.x + threadIdx.x;
   if (idx < n) {
     double point[3], dn[3], dscale, power;
-    int medium, seq_index, n_isect = bounce;
+    int medium, seq_index, n_isect = bounce, skip_shell = -1;
     const double2 a0 = pool.a0[idx], a1 = pool.a1[idx], a2 = pool.a2[idx], a3 = pool.a3[idx];
     const ulonglong2 a4 = pool.a4[idx];
     point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
     power = a3.x; dscale = a3.y;
     const unsigned long long i = a4.x;
     medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
-    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect };
+    const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
     for (;;) {
       if (n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); break; }
       ++n_isect;
       double t;
       const int fi = find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t);
-      if (interact<MC>(p, p.scene.faces, p.scene.groups, fi, t, i, r, s_cnt)) break;
+      if (interact<MC>(p, p.scene.faces, nullptr, p.scene.groups, fi, t, i, r, s_cnt)) break;
     }
     finish_ray<MC>(p, i, r, s_cnt);
   }
