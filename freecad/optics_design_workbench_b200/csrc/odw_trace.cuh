@@ -48,16 +48,24 @@ __device__ __noinline__ double general_nearest(const DFace* fp, const odw_trimse
   const DFace& f = *fp;
   const double s[3] = { sx, sy, sz }, dn[3] = { dx, dy, dz };
   if (f.kind == ODW_SURF_TORUS) {
-    // slab test against the face's box (ray.py:390-398 culls with the face BoundBox the same way);
-    // 1/0 = inf is fine here: fmin/fmax drop the NaN of 0*inf
-    double t0 = -1e300, t1 = 1e300;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double inv = 1.0/dn[i];
-      double ta = (f.bmin[i] - tol - s[i])*inv, tb = (f.bmax[i] + tol - s[i])*inv;
-      t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
-    }
-    if (t0 > t1) return 1e300;
+    // Cheap exact rejects before the quartic: the torus lies between the planes |z| <= r and between the cylinders
+    // R - r <= rho <= R + r of its own frame.  Where the ray is inside the slab (a t interval), rho^2(t) is a convex
+    // parabola: its maximum over the interval is at an end, its minimum at the clamped vertex.  (A ray through the hole of
+    // the ring — the last segment of every ray of lensesAndMirrors — is rejected here without solving anything.)
+    const double w[3] = { s[0]-f.o[0], s[1]-f.o[1], s[2]-f.o[2] };
+    const double wz = dot3(w, f.z), dz = dot3(dn, f.z), rr = f.p1 + tol;
+    double ta = 0.0, tb = lim;
+    if (fabs(dz) > 1e-300) {
+      const double t1 = (-rr - wz)/dz, t2 = (rr - wz)/dz;
+      ta = fmax(ta, fmin(t1, t2)); tb = fmin(tb, fmax(t1, t2));
+    } else if (fabs(wz) > rr) return 1e300;
+    if (!(ta <= tb)) return 1e300;
+    const double A = 1.0 - dz*dz, B = dot3(w, dn) - wz*dz, C = dot3(w, w) - wz*wz;
+    const double ra = (A*ta + 2*B)*ta + C, rb = (A*tb + 2*B)*tb + C;
+    const double inner = f.p0 - rr, outer = f.p0 + rr;
+    if (inner > 0 && fmax(ra, rb) < inner*inner) return 1e300;
+    double tv = A > 1e-300 ? fmin(tb, fmax(ta, -B/A)) : ta;
+    if ((A*tv + 2*B)*tv + C > outer*outer) return 1e300;
   }
   double ts[4];
   int nt = line_surface(f, s, dn, ts);
