@@ -249,16 +249,12 @@ def main():
   # ---- e2e: the same call with HOST result buffers (pinned), D2H inside the timed region
   e2e = None
   if not args.no_e2e:
-    pinned = {}
-    def pin(shape, dtype):
-      t = torch.empty(shape, dtype=dtype).pin_memory()
-      return t
-    t_points, t_dirs = pin((cap, 3), torch.float64), pin((cap, 3), torch.float64)
-    t_pow, t_ent, t_grp = pin((cap,), torch.float64), pin((cap,), torch.uint8), pin((cap,), torch.int32)
-    view = _abi.HitsView()
-    view.capacity = cap
-    view.points, view.directions, view.powers = t_points.data_ptr(), t_dirs.data_ptr(), t_pow.data_ptr()
-    view.is_entering, view.group = t_ent.data_ptr(), t_grp.data_ptr()
+    # what the plugin's runSimulationIteration requests (freecad_elements/generic_source.py): the four columns of the
+    # reference's hit files; the group column only when more than one optical group records hits
+    recording = int(np.count_nonzero(sim.scene.groups['record_hits']))
+    columns = ('points', 'directions', 'powers', 'is_entering') + (('group',) if recording != 1 else ())
+    _arrays, view = eng.pinned_hit_arrays(cap, columns)
+    bytes_per_hit = 24+24+8+1+(4 if recording != 1 else 0)
     import ctypes as C
     cfg_host = sim.cfg(store_hits=True)
     def e2e_step(k):
@@ -274,7 +270,7 @@ def main():
       assert c['hits_dropped'] == 0, c
     barrier()
     e_dt = time.perf_counter()-t0
-    d2h = int(e_hits/args.steps*(24+24+8+1+4))
+    d2h = int(e_hits/args.steps*bytes_per_hit)
     h2d = C.sizeof(_abi.TraceCfg) + 3*8     # the call's scalar arguments; MC rays are generated on the device
     e2e = dict(seconds=e_dt, segments=e_segs, d2h=d2h, h2d=h2d)
   clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
@@ -323,7 +319,7 @@ def main():
       clocks=clk)
     if e2e:
       line['e2e'] = dict(value=e_segs_all/e_seconds, unit=UNIT, h2d_bytes_per_step=e2e['h2d'], d2h_bytes_per_step=e2e['d2h'],
-                         note='odw_trace_mc_host: hit lists (points, directions, powers, isEntering, group) delivered into pinned host arrays, '
+                         note='odw_trace_mc_host: hit lists (points, directions, powers, isEntering; + group when several groups record) delivered into pinned host arrays, '
                               'device->host copy of chunk c overlapped with the trace of chunk c+1')
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0)
       cb, _, _ = cpu_baseline(sim, 1, args.cpu_sample_rays, 'scalar C restatement (oracle/odw_oracle.c), 1 thread')

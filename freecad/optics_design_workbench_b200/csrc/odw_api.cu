@@ -181,6 +181,21 @@ extern "C" int odw_engine_stream(const odw_engine* eng, void** stream_out) {
   return ODW_OK;
 }
 
+extern "C" int odw_host_alloc(odw_engine* eng, uint64_t bytes, void** out) {
+  if (!eng || !out) return fail(ODW_EINVAL, "odw_host_alloc: NULL argument");
+  *out = nullptr;
+  CU(cudaSetDevice(eng->device));
+  cudaError_t e = cudaHostAlloc(out, std::max<uint64_t>(bytes, 16), cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); *out = nullptr; return fail(ODW_ENOMEM, "cudaHostAlloc(" + std::to_string(bytes) + " bytes) failed"); }
+  return ODW_OK;
+}
+
+extern "C" void odw_host_free(odw_engine* eng, void* p) {
+  if (!eng || !p) return;
+  cudaSetDevice(eng->device);
+  cudaFreeHost(p);
+}
+
 template <typename T>
 static int upload(odw_engine* eng, std::vector<void*>& owned, const T* host, size_t n, const T** dev) {
   void* p = nullptr;

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('ODW_LIB') or os.path.join(_HERE, 'libodw_b200.so')   # ODW_LIB: developer override (kernel variants)
 
 EXPORTS = ['odw_abi_version', 'odw_last_error', 'odw_engine_create', 'odw_engine_destroy', 'odw_engine_device_name', 'odw_engine_stream',
+           'odw_host_alloc', 'odw_host_free',
            'odw_scene_create', 'odw_scene_destroy', 'odw_source_create', 'odw_source_destroy',
            'odw_trace_mc', 'odw_trace_mc_host', 'odw_sample_mc', 'odw_trace_rays', 'odw_result_counts', 'odw_result_hits',
            'odw_result_histogram', 'odw_result_histogram_device', 'odw_result_ray_summary', 'odw_result_ray_media',
@@ -61,6 +62,8 @@ def load_library():
   L.odw_engine_destroy.argtypes = [vp]; L.odw_engine_destroy.restype = None
   L.odw_engine_device_name.argtypes = [vp, C.c_char_p, C.c_int]
   L.odw_engine_stream.argtypes = [vp, C.POINTER(vp)]
+  L.odw_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+  L.odw_host_free.argtypes = [vp, vp]; L.odw_host_free.restype = None
   L.odw_scene_create.argtypes = [vp, vp, C.POINTER(vp)]
   L.odw_scene_destroy.argtypes = [vp]; L.odw_scene_destroy.restype = None
   L.odw_source_create.argtypes = [vp, vp, C.POINTER(vp)]
@@ -239,9 +242,13 @@ class Engine:
     _check(L.odw_engine_create(int(device_id), C.byref(h)))
     self._h = h
     self.device_id = device_id
+    self._pinned = []
 
   def close(self):
     if getattr(self, '_h', None):
+      for ptr in self._pinned:
+        load_library().odw_host_free(self._h, ptr)
+      self._pinned = []
       load_library().odw_engine_destroy(self._h)
       self._h = None
 
@@ -255,6 +262,28 @@ class Engine:
     st = C.c_void_p()
     _check(load_library().odw_engine_stream(self._h, C.byref(st)))
     return st.value or 0
+
+  def pinned_hit_arrays(self, capacity, columns=('points', 'directions', 'powers', 'is_entering', 'group')):
+    '''
+    Page-locked host arrays for odw_trace_mc_host: returns (dict of numpy arrays, _abi.HitsView).  Only the listed
+    columns are allocated; the others stay NULL and are not copied.  The memory lives as long as the engine.
+    '''
+    spec = dict(points=(np.float64, 3), directions=(np.float64, 3), powers=(np.float64, 1), is_entering=(np.uint8, 1),
+                ray_index=(np.uint64, 1), group=(np.int32, 1), bounce=(np.int32, 1), face_id=(np.int32, 1), medium=(np.int32, 1))
+    view = _abi.HitsView()
+    view.capacity = int(capacity)
+    arrays = {}
+    for name in columns:
+      dtype, width = spec[name]
+      nbytes = int(capacity)*width*np.dtype(dtype).itemsize
+      ptr = C.c_void_p()
+      _check(load_library().odw_host_alloc(self._h, nbytes, C.byref(ptr)))
+      self._pinned.append(ptr)
+      buf = (C.c_char*max(nbytes, 1)).from_address(ptr.value)
+      a = np.frombuffer(buf, dtype=dtype, count=int(capacity)*width)
+      arrays[name] = a.reshape(int(capacity), 3) if width == 3 else a
+      setattr(view, name, ptr.value)
+    return arrays, view
 
   def scene(self, scene):
     return DeviceScene(self, scene)

@@ -214,18 +214,30 @@ class GenericSourceProxy:
     n_total = n_iter_rays*iterations
     first, n = ctx.claim_rays(self.index, n_total)        # this rank's shard of the next n_total global ray indices
     dsrc = ctx.device_source(self.index)
+    if not store:
+      with ctx.device_scene.trace_mc(dsrc, ctx.cfg(obj, store_hits=False), ctx.seed, first, n) as res:
+        return res.counts
+    # Hit delivery straight into page-locked host arrays (odw_trace_mc_host: the device->host copy of one chunk overlaps
+    # the trace of the next) with only the columns the result files need: the group column only when more than one
+    # optical group records hits, the ray index only for StoreHit* metadata.
+    scene = ctx.sim.scene
+    recording = np.nonzero(scene.groups['record_hits'])[0]
+    keys = ctx.sim.settings.get('store_hit_keys', [])
+    columns = ['points', 'directions', 'powers', 'is_entering'] + (['group'] if len(recording) != 1 else []) + (['ray_index'] if keys else [])
     capacity = max(1024, 2*n)
     while True:
-      cfg = ctx.cfg(obj, store_hits=bool(store), hit_capacity=capacity)
-      with ctx.device_scene.trace_mc(dsrc, cfg, ctx.seed, first, n) as res:
-        counts = res.counts
-        overflow = res.overflow
-        hits = res.hits(sort=True) if (store and not overflow) else None
-      if not overflow:
+      arrays, view = ctx.pinned_hits(capacity, tuple(columns))
+      counts, got = ctx.device_scene.trace_mc_host(dsrc, ctx.cfg(obj, store_hits=True), ctx.seed, first, n, view)
+      if not counts['hits_dropped']:
         break
       # more recorded hits than rows (transparent detectors record two hits per pass): the same ray range again with
       # room for all of them — the Philox stream makes the repeat identical
       capacity = max(4*capacity, int(counts['hits'])+1024)
+    hits = {k: v[:got] for k, v in arrays.items()}
+    if 'group' not in hits:
+      hits['group'] = np.full(got, int(recording[0]), dtype=np.int32)
+    if 'ray_index' not in hits:
+      hits['ray_index'] = np.zeros(got, dtype=np.uint64)
     if store:
       def metadata_of(ray_index, keys):
         s = dsrc.sample(ctx.seed, first, n)               # same Philox stream -> the rays' initial conditions

@@ -67,6 +67,7 @@ class SimulationContext:
     self._device_sources = {}
     self._next_ray = {}                   # per light source: next unused global ray index
     self._replay = {}                     # per replay source: its stock of rays
+    self._pinned = {}                     # page-locked hit arrays by column set
 
   def device_source(self, index):
     if index not in self._device_sources:
@@ -82,6 +83,23 @@ class SimulationContext:
     first = self._next_ray.get(source_index, 0)
     self._next_ray[source_index] = first+int(n_global)
     return sharding.shard_range(first, n_global, self.rank, self.world)
+
+  def pinned_hits(self, capacity, columns):
+    'page-locked hit arrays of at least `capacity` rows with these columns, reused from call to call'
+    have = self._pinned.get(columns)
+    if have is None or have[2] < capacity:
+      if hasattr(self.engine, 'pinned_hit_arrays'):
+        arrays, view = self.engine.pinned_hit_arrays(capacity, columns)
+      else:                                              # engines without page-locked memory (the CPU test double)
+        from .. import _abi
+        h = _abi.HitArrays(capacity)
+        arrays, view = {k: getattr(h, k) for k in columns}, h.view
+        for k in ('points', 'directions', 'powers', 'is_entering', 'ray_index', 'group', 'bounce', 'face_id', 'medium'):
+          if k not in columns:
+            setattr(view, k, None)
+        self._keep = h
+      have = self._pinned[columns] = (arrays, view, capacity)
+    return have[0], have[1]
 
   def replay_stock(self, index, loader):
     if index not in self._replay:

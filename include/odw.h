@@ -280,6 +280,10 @@ int  odw_engine_device_name(const odw_engine*, char* buf, int buflen);
 /* the cudaStream_t every kernel/copy of this engine is issued on (so callers can time it with events) */
 int  odw_engine_stream(const odw_engine*, void** stream_out);
 
+/* page-locked host memory for hit delivery (odw_trace_mc_host copies device->host asynchronously into it) */
+int  odw_host_alloc(odw_engine*, uint64_t bytes, void** out);
+void odw_host_free(odw_engine*, void* p);
+
 int  odw_scene_create(odw_engine*, const odw_scene_desc*, odw_scene** out);
 void odw_scene_destroy(odw_scene*);
 

@@ -45,6 +45,19 @@ class _Scene:
     return _Result(self.orc.trace_mc(self.scene, source.args, cfg, seed, first_ray, n_rays,
                                      hit_capacity=max(16, int(cfg.cfg.hit_capacity) or 4*n_rays), threads=0))
 
+  def trace_mc_host(self, source, cfg, seed, first_ray, n_rays, view):
+    'same contract as DeviceScene.trace_mc_host: rows go into the arrays behind the odw_hits_view'
+    import ctypes as C
+    r = self.orc.trace_mc(self.scene, source.args, cfg, seed, first_ray, n_rays, hit_capacity=int(view.capacity), threads=0, sort=False)
+    h, got = r['hits'], len(r['hits']['powers'])
+    for name, width in (('points', 3), ('directions', 3), ('powers', 1), ('is_entering', 1), ('ray_index', 1), ('group', 1),
+                        ('bounce', 1), ('face_id', 1), ('medium', 1)):
+      ptr = getattr(view, name)
+      if ptr:
+        src = np.ascontiguousarray(h[name])
+        C.memmove(ptr, src.ctypes.data, src.nbytes)
+    return r['counts'], got
+
   def trace_rays(self, cfg, origins, directions, powers=None, ignored=()):
     return _Result(self.orc.trace_rays(self.scene, cfg, origins, directions, powers, ignored=ignored, threads=0))
 
