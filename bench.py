@@ -311,9 +311,13 @@ def main():
       rays_per_s=n_rays*world*args.steps/(elapsed_ms*1e-3),
       recorded_hits_per_s=hits_all/(elapsed_ms*1e-3),
       roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved/peak,
-                    traffic=(traffic or {}).get('dram_bytes_per_launch'),
+                    traffic=(traffic['dram_bytes_per_launch']*(n_rays*args.steps/launches)/traffic.get('rays_per_launch', 2097152)
+                             if traffic and launches else None),
                     peak_source=peak_src,
-                    algorithmic_bytes_per_launch=alg_bytes/args.steps,
+                    algorithmic_bytes_per_launch=alg_bytes/max(launches, 1), rays_per_launch=n_rays*args.steps/max(launches, 1),
+                    launch_overlap='the launches of a step run on 4 streams; achieved = bytes of all launches / CUDA-event time from the first '
+                                   'launch to the last completion (per-launch durations overlap); traffic = ncu dram bytes of a 2^21-ray launch '
+                                   'scaled to this launch size (profiles/traffic.json)',
                     note='algorithmic bytes = 144 B/segment + 64 B/recorded hit (wavefront formulation, SURVEY.md §8d); the '
                          'register-resident kernel moves far fewer bytes and is bounded by fp64 issue, see DESIGN.md'),
       clocks=clk)

@@ -43,7 +43,9 @@ def main():
     with open(path, 'w') as f:
       json.dump(dict(kernel=d['kernel'], dram_bytes_per_launch=rd+wr, dram_read_bytes=rd, dram_write_bytes=wr,
                      duration_ms=d['gpu__time_duration.sum']['value']*(1e-3 if d['gpu__time_duration.sum']['unit'] == 'us' else 1 if d['gpu__time_duration.sum']['unit'] == 'ms' else 1e-6),
-                     source=os.path.basename(rep), launch='2^21 Monte-Carlo rays of lensesAndMirrors, hit lists stored'), f, indent=1)
+                     source=os.path.basename(rep), rays_per_launch=2097152,
+                     launch='2^21 Monte-Carlo rays of lensesAndMirrors, hit lists stored (ODW_RAYS_PER_LAUNCH=2097152: the default 2^18-ray '
+                            'launch leaves most of its hit list dirty in the 126 MB L2 when the kernel ends, which hides the writes from the counter)'), f, indent=1)
   print('wrote', prefix+'_details.csv', prefix+'_raw.json')
 
 if __name__ == '__main__':
