@@ -47,6 +47,26 @@ class Oracle:
     L.oracle_trace_mc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.oracle_max_threads.restype = C.c_int
+    L.oracle_find_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int32,
+                                      C.c_void_p, C.c_int32, C.c_void_p]
+    L.oracle_face_normal.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+
+  def find_nearest(self, scene_args, cfg, start, direction, medium, max_len, seq_index, ignored=()):
+    'one Ray.findNearestIntersection: (face index, point) or (-1, None)'
+    s, d, P = np.array(start, dtype=np.float64), np.array(direction, dtype=np.float64), np.empty(3)
+    ign = np.ascontiguousarray(list(ignored), dtype=np.int32)
+    fi = self.lib.oracle_find_nearest(C.addressof(scene_args.desc), C.addressof(cfg.cfg), s.ctypes.data, d.ctypes.data,
+                                      int(medium), float(max_len), int(seq_index), ign.ctypes.data if len(ign) else None,
+                                      len(ign), P.ctypes.data)
+    return (fi, P) if fi >= 0 else (-1, None)
+
+  def face_normal(self, scene_args, face, point):
+    'Surface.parameter + normalAt of a face at a point: ((u, v), unit normal)'
+    P, uv, n = np.array(point, dtype=np.float64), np.empty(2), np.empty(3)
+    rc = self.lib.oracle_face_normal(C.addressof(scene_args.desc), int(face), P.ctypes.data, uv.ctypes.data, n.ctypes.data)
+    if rc:
+      raise ValueError(f'face {face} out of range')
+    return uv, n
 
   def max_threads(self):
     return int(self.lib.oracle_max_threads())

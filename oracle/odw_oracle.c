@@ -1015,6 +1015,29 @@ int oracle_trace_mc(const odw_scene_desc* sc, const odw_source_desc* src, const 
   return dropped ? ODW_EOVERFLOW : 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* The two geometry questions the reference asks OpenCASCADE, exported one at a time: tests/golden/make_traceray_golden.py
+ * runs the reference's OWN Ray.traceRay (ray.py:36-281) with these as its geometry provider. */
+
+/* Ray.findNearestIntersection (ray.py:290-452) for one segment; returns the face index or -1 */
+int oracle_find_nearest(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const double* start, const double* dir,
+                        int32_t medium, double max_len, int32_t seq_index, const int32_t* ignored, int32_t n_ignored,
+                        double* point_out) {
+  cand_t* shell_c = (cand_t*)malloc(sizeof(cand_t)*(size_t)(sc->n_shells + 1));
+  cand_t* face_c  = (cand_t*)malloc(sizeof(cand_t)*(size_t)(sc->n_faces + 1));
+  double dist;
+  int fi = find_nearest(sc, cfg, start, dir, medium, max_len, seq_index, ignored, n_ignored, shell_c, face_c, point_out, &dist);
+  free(shell_c); free(face_c);
+  return fi;
+}
+
+/* Surface.parameter + Face.normalAt (ray.py:463-466): (u, v) and the orientation-aware unit normal of a face at P */
+int oracle_face_normal(const odw_scene_desc* sc, int32_t face, const double* P, double* uv_out, double* normal_out) {
+  if (face < 0 || face >= sc->n_faces) return ODW_EINVAL;
+  surface_uv_normal(&sc->faces[face], P, uv_out, normal_out);
+  return 0;
+}
+
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

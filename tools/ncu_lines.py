@@ -55,6 +55,26 @@ def main():
   for (ins, c), r in zip(seq, b):
     byline[c] += int(r[iE]); bys[c] += int(r[iS])
   src = {}
+  # per function: a line belongs to the last `__device__` / `__global__` definition that starts at or before it
+  byfun, byfuns = collections.Counter(), collections.Counter()
+  starts = {}
+  for k, c in byline.items():
+    f, l = k if k else ('?', 0)
+    if f not in starts:
+      try:
+        lines = open(os.path.join(srcdir, f)).read().split('\n')
+      except OSError:
+        lines = []
+      starts[f] = [(i+1, re.sub(r'\(.*', '', ln.split('(')[0]).split()[-1]) for i, ln in enumerate(lines)
+                   if re.match(r'\s*(template\s*<[^>]*>\s*)?(static\s+)?__(device|global)__', ln) and '(' in ln]
+    name = '?'
+    for l0, n in starts[f]:
+      if l0 <= l:
+        name = n
+    byfun[(f, name)] += c; byfuns[(f, name)] += bys[k]
+  print('by function (inlined code is attributed to the function it was written in):')
+  for (f, name), c in byfun.most_common(25):
+    print(f'  {f[:16]:16s} {name[:28]:28s} {c/tot*100:5.2f}% instr {byfuns[(f, name)]/tots*100:5.2f}% samples')
   for k, c in byline.most_common(top):
     f, l = k if k else ('?', 0)
     if f not in src:
