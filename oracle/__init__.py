@@ -2,9 +2,10 @@
 CPU oracle loader — TEST INFRASTRUCTURE ONLY (see oracle/odw_oracle.c).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
-package.  The product package never does.  "parity unpinned" for per-ray hit sequences (no FreeCAD /
-OpenCASCADE here and no golden ray vectors in the reference); the sampler and fan grid ARE pinned
-against the reference's importable `distributions` module (tests/golden/).
+package.  The product package never does.  Pinned against the reference's own code: the bounce loop, the interaction
+formulas and _makeRay (tests/golden/make_traceray_golden.py), the sampler and the fan grid (tests/golden/).
+"parity unpinned" for the geometry answers the reference obtains from FreeCAD / OpenCASCADE (absent here; the
+reference holds no golden ray vectors) — see the header of odw_oracle.c.
 '''
 
 import ctypes as C
@@ -50,6 +51,8 @@ class Oracle:
     L.oracle_find_nearest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p]
     L.oracle_face_normal.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.oracle_scatter_draw.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32,
+                                      C.c_void_p, C.c_void_p]
 
   def find_nearest(self, scene_args, cfg, start, direction, medium, max_len, seq_index, ignored=()):
     'one Ray.findNearestIntersection: (face index, point) or (-1, None)'
@@ -67,6 +70,14 @@ class Oracle:
     if rc:
       raise ValueError(f'face {face} out of range')
     return uv, n
+
+  def scatter_draw(self, scene_args, group, which, seed, source_id, ray, bounce):
+    '(theta, phi) of the stochastic surface model for one interaction, or None when that density is empty'
+    th, ph = C.c_double(0), C.c_double(0)
+    if not self.lib.oracle_scatter_draw(C.addressof(scene_args.desc), int(group), int(which), int(seed), int(source_id),
+                                        int(ray), int(bounce), C.byref(th), C.byref(ph)):
+      return None
+    return th.value, ph.value
 
   def max_threads(self):
     return int(self.lib.oracle_max_threads())

@@ -4,12 +4,20 @@
  * This file is the parity oracle: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product (libodw_b200.so) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned" for per-ray hit sequences — the reference's own tests hold no golden
- * vector for a single ray, and the reference's arithmetic lives in FreeCAD/OpenCASCADE (unpinned "system
- * FreeCAD / latest AppImage", benchmark files written by FreeCAD 1.1R20260725), which is absent here.
- * What IS pinned: the sampler (against the importable reference `distributions` module, fixtures under
- * tests/golden/), the fan grid, and hand-derived known answers for the benchmark scenes
- * (SURVEY.md Appendix B).
+ * PARITY STATUS
+ *   pinned   — the bounce loop (traceRay state machine, getNormal flip / isEntering, mirror, snellsLaw incl. total
+ *              reflection, lineGrating, power / medium / sequence-index bookkeeping, the powerTol and maxIntersections
+ *              exits, what onRayHit hands to the store, the rotation formula of applyStochasticRayCorrections) and
+ *              _makeRay: against the reference's OWN ray.py / point_source.py / optical_group.py executed under FreeCAD
+ *              stand-ins with this file answering the two OpenCASCADE questions (tests/golden/make_traceray_golden.py,
+ *              tests/test_traceray_golden.py);
+ *            — the sampler (numeric mode), the fan grid and the fan ray list: against the importable reference
+ *              `distributions` / `point_source` modules (tests/golden/make_sampler_golden.py, make_fan_golden.py).
+ *   "parity unpinned" — the geometry answers themselves (line/surface intersection, trimmed-face membership, normals):
+ *              the reference delegates them to FreeCAD/OpenCASCADE (unpinned "system FreeCAD / latest AppImage",
+ *              benchmark files written by FreeCAD 1.1R20260725), absent here, and its tests hold no golden vector for
+ *              a single ray.  They are anchored on hand-derived known answers for the benchmark scenes
+ *              (tests/test_oracle_known_answers.py) and on the reference's statistical assertions.
  *
  * Each function cites the reference code it follows (paths relative to
  * /root/reference/freecad/optics_design_workbench/).  Where the reference calls OCC
@@ -1036,6 +1044,19 @@ int oracle_face_normal(const odw_scene_desc* sc, int32_t face, const double* P, 
   if (face < 0 || face >= sc->n_faces) return ODW_EINVAL;
   surface_uv_normal(&sc->faces[face], P, uv_out, normal_out);
   return 0;
+}
+
+/* the (theta, phi) applyStochasticRayCorrections draws for interaction `bounce` of ray `ray` on `group`
+ * (which = 0: Reflected/RefractedProbabilityDensity, 1: RayModificationProbabilityDensity); 0 = that density is empty */
+int oracle_scatter_draw(const odw_scene_desc* sc, int32_t group, int32_t which, uint64_t seed, uint32_t source_id,
+                        uint64_t ray, int32_t bounce, double* theta, double* phi) {
+  if (!sc->n_scatters || !sc->group_scatter || group < 0 || group >= sc->n_groups) return 0;
+  int idx = sc->group_scatter[2*group + (which ? 1 : 0)];
+  if (idx < 0) return 0;
+  double u[2];
+  oracle_philox(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce + (which ? 1u : 0u), u);
+  scatter_sample(&sc->scatters[idx], u[0], u[1], theta, phi);
+  return 1;
 }
 
 int oracle_max_threads(void) {

@@ -2,7 +2,9 @@
 Generates tests/golden/traceray_golden.npz by running the reference's OWN Python for the hot path
   PointSourceProxy._makeRay            (freecad_elements/point_source.py:411-460)
   Ray.traceRay / getNormal / mirror / snellsLaw / lineGrating   (freecad_elements/ray.py:36-281,455-539)
-  OpticalGroupProxy.onRayHit / applyStochasticRayCorrections   (freecad_elements/optical_group.py:206-209,279-323)
+  OpticalGroupProxy.onRayHit / applyStochasticRayCorrections   (freecad_elements/optical_group.py:206-209,279-323;
+                                        its (theta, phi) draws come from the engine's Philox stream: numpy's process-seeded
+                                        RNG of the reference is not reproducible — the rotation formula is the reference's)
 imported unmodified from /root/reference in the build container.  FreeCAD is absent, so
   * FreeCAD.Vector / Rotation / Matrix are the stand-ins of tests/freecad_stub.py, and
   * the two questions the reference asks OpenCASCADE — Ray.findNearestIntersection (ray.py:290-452) and
@@ -85,8 +87,26 @@ def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=()):
     def normalAt(self, u, v):
       return self._n
 
+  state = dict(ray=0, bounce=-1)
+
+  class Draw:
+    'stands in for the VectorRandomVariable of a surface density: compile() is a no-op (no per-hit parameters in these cases)'
+    def __init__(self, group, which):
+      self.group, self.which = group, which
+    def compile(self, **kw):
+      pass
+    def draw(self):
+      return oracle.scatter_draw(sa, self.group, self.which, cfg.cfg.scatter_seed, 0, state['ray'], state['bounce'])
+
+  for o in objs:
+    def get_vrv(obj, kind, _o=o):
+      which = 0 if kind in ('reflect', 'refract') else 1
+      return Draw(_o.group_index, which) if oracle.scatter_draw(sa, _o.group_index, which, 0, 0, 0, 0) else False
+    o.Proxy._getVrv = get_vrv
+
   class TracedRay(ray_mod.Ray):
     def findNearestIntersection(self, start, direction, currentMedium, maxRayLength, distTol=None, sequenceIndex=None):
+      state['bounce'] += 1
       fi, P = oracle.find_nearest(sa, cfg, list(start), list(direction), -1 if currentMedium is None else currentMedium.group_index,
                                   maxRayLength, sequenceIndex, ignored)
       if fi < 0:
@@ -99,6 +119,7 @@ def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=()):
   hit_ray, hit_rows = [], []
   for i, r in enumerate(rays):
     r.__class__ = TracedRay
+    state.update(ray=i, bounce=-1)
     store = Store()
     for (p1, p2), power, medium, _color in r.traceRay(store=store):
       seg_p1.append(tuple(p1)); seg_p2.append(tuple(p2)); seg_power.append(float(power))

@@ -2,7 +2,8 @@
 Cases of the traceRay golden (tests/golden/make_traceray_golden.py writes it, tests/test_traceray_golden.py reads it):
 benchmark / example scene fixtures with rays drawn from their own light source, and small synthetic scenes that
 drive the branches of Ray.traceRay (reference freecad_elements/ray.py:36-281) the shipped scenes do not reach —
-total internal reflection, a ray born inside a lens, power decay on lossy mirrors, both grating types, maxIntersections.
+total internal reflection, a ray born inside a lens, power decay on lossy mirrors, both grating types, maxIntersections,
+and the stochastic surface model (optical_group.py:279-323) on a mirror and on a lens.
 '''
 import os
 
@@ -90,11 +91,37 @@ def gratings():
   return b.build(), np.zeros((2*n, 3)), np.vstack([up, down]), dict(max_ray_length=300.0, max_intersections=20)
 
 
+def diffuse_surfaces():
+  '''
+  applyStochasticRayCorrections: a mirror whose reflected direction is drawn from a density and then modified, and a
+  lens whose refracted direction is modified (frosted glass).  The (theta, phi) draws are the engine's Philox draws; the
+  rotation formula that turns them into a direction is the reference's.
+  '''
+  b = SceneBuilder()
+  m = b.add_group('Diffuser', 'Diffuser', optical_type='Mirror', reflectivity=0.8, record_hits=True,
+                  scatter_density='cos(theta)**2*abs(sin(theta))', power_theta_domain='-pi, -pi/2', power_phi_domain='-pi, pi',
+                  modify_density='exp(-theta**2/0.01)*abs(sin(theta))', modify_theta_domain='0, 0.5', modify_phi_domain='0, 2*pi',
+                  scatter_resolution=401)
+  b.add_shape(m, prim.box(60, 60, 1), prim.translation(-30, -30, 20))
+  l = b.add_group('Frosted', 'Frosted', optical_type='Lens', refractive_index=1.5,
+                  modify_density='exp(-theta**2/0.02)*abs(sin(theta))', modify_theta_domain='0, 0.6', modify_phi_domain='0, 2*pi',
+                  scatter_resolution=401)
+  b.add_shape(l, prim.box(60, 60, 4), prim.translation(-30, -30, -24))
+  ab = b.add_group('Shell', 'Shell', optical_type='Absorber', record_hits=True)
+  b.add_shape(ab, prim.sphere(100.0), np.eye(4))
+  rng = np.random.default_rng(15)
+  n = 150
+  up = _unit(np.column_stack([rng.uniform(-0.4, 0.4, n), rng.uniform(-0.4, 0.4, n), np.ones(n)]))
+  down = up*np.array([1.0, 1.0, -1.0])
+  return b.build(), np.zeros((2*n, 3)), np.vstack([up, down]), dict(max_ray_length=400.0, max_intersections=40, scatter_seed=77)
+
+
 SYNTHETIC_CASES = {
   'glass_ball': (glass_ball, (500.0,)),
   'glass_cube': (glass_cube, (500.0,)),
   'lossy_mirrors': (lossy_mirrors, (500.0,)),
   'gratings': (gratings, (450.0, 633.0, 1000.0)),
+  'diffuse_surfaces': (diffuse_surfaces, (500.0,)),
 }
 
 
