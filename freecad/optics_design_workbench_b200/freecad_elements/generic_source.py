@@ -32,6 +32,12 @@ class GenericSourceProxy:
 
   # -- ray generation (PointSourceProxy._generateRays) --------------------------------------------
   def _generateRays(self, obj, mode, **kwargs):
+    if mode == 'fans' and obj.get('proxy') == 'SurfaceSourceProxy':
+      from . import surface_source
+      emit = obj.get('emit')
+      if emit is None or not len(emit.faces):
+        raise NotImplementedError(f"surface source {obj['name']}: no emitting faces ({obj.get('emit_error') or 'ActiveSurfaces empty'})")
+      return surface_source.generate_fan_rays(obj, emit, self.context.sim.settings.get('DistanceTolerance', 1e-6))
     if mode == 'fans':
       return point_source.generate_fan_rays(obj, obj['gpM'], max_fan_count=kwargs.get('maxFanCount', np.inf),
                                             max_rays_per_fan=kwargs.get('maxRaysPerFan', np.inf))
@@ -78,8 +84,6 @@ class GenericSourceProxy:
       raise NotImplementedError(f"light source kind {kind} is not handled by the engine yet")
     if kind == 'ReplaySourceProxy':
       return self._replay_iteration(obj, mode, int(iterations), store, returnInitialConditions)
-    if kind == 'SurfaceSourceProxy' and (mode in ('fans', 'multicorefans') and useInitialConditions is None):
-      raise NotImplementedError('fan mode of surface sources (_makeSurfaceGrid, surface_source.py:122-267) is not on the engine yet')
 
     if useInitialConditions is not None or mode in ('fans', 'multicorefans'):
       batch = useInitialConditions if useInitialConditions is not None else self._generateRays(obj, mode='fans', **kwargs)

@@ -153,3 +153,210 @@ def emitting_faces_from_instances(selections):
     seg_arr[i]['kind'] = kind
     seg_arr[i]['a'] = a
   return EmittingFaces(np.array(faces, dtype=sc.FACE_DTYPE) if faces else np.zeros(0, dtype=sc.FACE_DTYPE), seg_arr)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fan mode (reference surface_source.py:122-267 _makeSurfaceGrid, :469-517 the 'fans' branch of _generateRays):
+# a deterministic, approximately equidistant grid of points on every emitting face, one ray along the face normal
+# from each.  Host side: at most FanModeRayCount rays, traced as an explicit list (odw_trace_rays).
+
+class FaceEvaluator:
+  '''
+  What _makeSurfaceGrid asks OpenCASCADE about a face, in closed form on a FACE_DTYPE row in the world frame:
+  ParameterRange, valueAt, derivative1At, normalAt and "is this surface point on the trimmed face within distTol"
+  (the reference's Part.Vertex(p).distToShape(face)[0] < distTol, :176-178).
+  '''
+  def __init__(self, f, segs):
+    self.f = f
+    self.segs = segs[int(f['seg_first']):int(f['seg_first'])+int(f['seg_count'])]
+    self.kind, self.trim = int(f['kind']), int(f['trim_kind'])
+    self.O, self.X, self.Y, self.Z = (np.asarray(f[k], dtype=np.float64) for k in ('origin', 'xdir', 'ydir', 'zdir'))
+    self.p0, self.p1 = float(f['p0']), float(f['p1'])
+
+  @property
+  def area(self):
+    return face_area(self.f, self.segs if self.trim == sc.TRIM_LOOPS else self.segs)
+
+  def parameter_range(self):
+    return _window(self.f)
+
+  def value_at(self, u, v):
+    return sc.eval_face(self.f, u, v).reshape(3)
+
+  def derivative1_at(self, u, v):
+    k = self.kind
+    if k == sc.SURF_PLANE:
+      return self.X.copy(), self.Y.copy()
+    er = np.cos(u)*self.X + np.sin(u)*self.Y
+    et = -np.sin(u)*self.X + np.cos(u)*self.Y
+    if k == sc.SURF_CYLINDER:
+      return self.p0*et, self.Z.copy()
+    if k == sc.SURF_CONE:
+      return (self.p0 + v*np.sin(self.p1))*et, np.sin(self.p1)*er + np.cos(self.p1)*self.Z
+    if k == sc.SURF_SPHERE:
+      return self.p0*np.cos(v)*et, self.p0*(-np.sin(v)*er + np.cos(v)*self.Z)
+    return (self.p0 + self.p1*np.cos(v))*et, self.p1*(-np.sin(v)*er + np.cos(v)*self.Z)
+
+  def normal_at(self, u, v):
+    'unit normal pointing out of the solid (orientation-aware, like Face.normalAt)'
+    k = self.kind
+    er = np.cos(u)*self.X + np.sin(u)*self.Y
+    if k == sc.SURF_PLANE:
+      n = self.Z
+    elif k == sc.SURF_CYLINDER:
+      n = er
+    elif k == sc.SURF_CONE:
+      sgn = 1.0 if self.p0 + v*np.sin(self.p1) >= 0 else -1.0
+      n = sgn*(np.cos(self.p1)*er - np.sin(self.p1)*self.Z)
+    else:                                       # sphere and torus: same expression in their own (u, v)
+      n = np.cos(v)*er + np.sin(v)*self.Z
+    return float(self.f['nsign'])*n
+
+  def _uv_boundary_distance(self, u, v):
+    'distance of (u, v) to the trim loops, in parameter units'
+    best = np.inf
+    for s in self.segs:
+      a = s['a']
+      if int(s['kind']) == sc.SEG_LINE:
+        p, q = np.array([a[0], a[1]]), np.array([a[2], a[3]])
+        d = q-p
+        t = 0.0 if not d.any() else min(1.0, max(0.0, float(np.dot([u-p[0], v-p[1]], d)/np.dot(d, d))))
+        best = min(best, float(np.hypot(u-(p[0]+t*d[0]), v-(p[1]+t*d[1]))))
+      else:
+        cu, cv, r, a0, span = a[:5]
+        ang = (np.arctan2(v-cv, u-cu)-a0) % TWO_PI
+        if ang <= span:
+          best = min(best, abs(float(np.hypot(u-cu, v-cv))-r))
+        else:
+          for e in (a0, a0+span):
+            best = min(best, float(np.hypot(u-(cu+r*np.cos(e)), v-(cv+r*np.sin(e)))))
+    return best
+
+  def on_face(self, u, v, tol):
+    if self.trim == sc.TRIM_NONE:
+      return True
+    du, dv = self.derivative1_at(u, v)
+    lu, lv = max(np.linalg.norm(du), 1e-300), max(np.linalg.norm(dv), 1e-300)
+    if self.trim == sc.TRIM_UVBOX:
+      u0, u1, v0, v1 = _window(self.f)
+      return bool(u0-tol/lu <= u <= u1+tol/lu and v0-tol/lv <= v <= v1+tol/lv)
+    if sc.point_in_segs(self.segs, u, v):
+      return True
+    return bool(self._uv_boundary_distance(u, v)*max(lu, lv) < tol)
+
+
+def make_surface_grid(face, total_grid_points, dist_tol, uniform_param=None, fill_factor=1, effective_sizes=None,
+                      recursion_depth=0):
+  '''
+  _makeSurfaceGrid (surface_source.py:122-267) on a FaceEvaluator: five passes that refine (i) which parameter is laid
+  out first, (ii) the effective lengths of the two parameter axes, (iii) the fraction of the rectangular (u, v) grid
+  that lies on the face; rows of a "uniform" parametrisation are thinned by powers of two where they are short (the
+  poles of a sphere).  Returns [((u, v), point, (du, dv))].  numpy's sum / mean / round are used where the reference's
+  `from numpy import *` makes it use them.
+  '''
+  r = face.parameter_range()
+  limits = dict(u=(r[0], r[1]), v=(r[2], r[3]))
+  param_sizes = dict(u=r[1]-r[0], v=r[3]-r[2])
+  if effective_sizes is None:
+    effective_sizes = param_sizes
+  order = 'uv' if effective_sizes['u'] >= effective_sizes['v'] else 'vu'
+  if uniform_param is not None:
+    order = uniform_param + {'u': 'v', 'v': 'u'}[uniform_param]
+  P1, P2 = [np.linspace(limits[p][0], limits[p][1],
+                        max(5, 1+int(2*np.round(np.sqrt(effective_sizes[p]/effective_sizes[q]*total_grid_points/fill_factor)/2))))
+            for p, q in zip(order, reversed(order))]
+  p1_step, p2_step = P1[1]-P1[0], P2[1]-P2[0]
+  uv = (lambda a, b: (a, b)) if order == 'uv' else (lambda a, b: (b, a))
+  points = [[face.value_at(*uv(p1, p2)) for p2 in P2] for p1 in P1]
+  valid = [[face.on_face(*uv(p1, p2), dist_tol) for p2 in P2] for p1 in P1]
+  deriv = [[uv(*face.derivative1_at(*uv(p1, p2))) if valid[i][j] else (None, None) for j, p2 in enumerate(P2)]
+           for i, p1 in enumerate(P1)]
+  length = lambda d: None if d is None else float(np.sqrt(d[0]*d[0]+d[1]*d[1]+d[2]*d[2]))
+  d1 = [[length(d[0]) for d in row] for row in deriv]
+  d2 = [[length(d[1]) for d in row] for row in deriv]
+  area = [[a*b if a is not None and b is not None else None for a, b in zip(r1, r2)] for r1, r2 in zip(d1, d2)]
+  some = lambda A: [a for a in A if a is not None]
+  mean_ = lambda A: np.mean(some(A)) if len(some(A)) else None
+  max_ = lambda A: np.max(some(A)) if len(some(A)) else None
+  sum_ = lambda A: np.sum(some(A))
+  uniform = lambda rows: all(all(abs(d-avg)*p1_step*p2_step < dist_tol**2 for d in row if d is not None)
+                             for avg, row in zip([mean_(row) for row in rows], rows))
+  if uniform(area):
+    uniform_param = order[0]
+  elif uniform(list(zip(*area))):
+    uniform_param = order[1]
+  else:
+    uniform_param = None
+  eff1 = sum_([max_(row) for row in d1])*p1_step
+  eff2 = sum_([max_(col) for col in zip(*d2)])*p2_step
+  effective_sizes = {order[0]: eff1, order[1]: eff2}
+  if uniform_param is not None:
+    for i, row in enumerate(d2):
+      row_len = max(1e-20, p2_step*sum_(row))
+      keep_every = 2**np.round(np.log2(eff2/row_len))
+      if keep_every > len(valid[i]):
+        for j in range(1, len(valid[i])):
+          valid[i][j] = False
+      else:
+        for j in range(len(valid[i])):
+          if j % keep_every != 0:
+            valid[i][j] = False
+  count = sum(sum(1 if v else 0 for v in row) for row in valid)
+  if recursion_depth < 4:
+    return make_surface_grid(face, total_grid_points, dist_tol, uniform_param=uniform_param,
+                             fill_factor=max(fill_factor/10, count/(len(P1)*len(P2))),
+                             effective_sizes=effective_sizes, recursion_depth=recursion_depth+1)
+  drops = [lambda i, j: False, lambda i, j: i % 2 == 0 or j % 2 == 0, lambda i, j: ((i+1)//2) % 2 == 0 or ((j+1)//2) % 2 == 0]
+  while len(drops) and total_grid_points < 20 and count > total_grid_points:
+    drop = drops.pop(0)
+    valid = [[valid[i][j] and not drop(i, j) for j in range(len(P2))] for i in range(len(P1))]
+    count = sum(sum(1 if v else 0 for v in row) for row in valid)
+  return [(uv(p1, p2), points[i][j], uv(*deriv[i][j])) for i, p1 in enumerate(P1) for j, p2 in enumerate(P2) if valid[i][j]]
+
+
+def _custom_round(x):
+  'ray counts per face: 1, 4, 9 or any larger integer (surface_source.py:474-476)'
+  return round(x) if x > 9 else [1, 4, 9][int(np.argmin(np.abs(x-np.array([1, 4, 9]))))]
+
+
+def fan_ray_counts(weights, fan_mode_ray_count):
+  '''
+  which faces get rays and how many (surface_source.py:478-503): by area weight, but at least one per face; when that
+  overshoots FanModeRayCount by more than 30 % a matching fraction of the faces is skipped.  Returns [(face index, rays)].
+  The reference itself raises NameError on that branch (its warning text uses the undefined names `warnings` and
+  `rayCount`, :485-488); the skipping rule below is its code taken literally, without the warning.
+  '''
+  total = sum(_custom_round(w*fan_mode_ray_count) for w in weights)
+  skip_fraction = max(0, 1-fan_mode_ray_count/total)
+  if skip_fraction <= 0.3:
+    skip_fraction = 0
+  out, face_i = [], 0
+  for i, w in enumerate(weights):
+    if skip_fraction > 0:
+      step = skip_fraction/w*len(weights)
+      if round(face_i) != round(face_i+step):
+        continue
+      face_i += step
+    out.append((i, _custom_round(w*fan_mode_ray_count)))
+  return out
+
+
+def generate_fan_rays(obj, emit, dist_tol):
+  '''
+  SurfaceSourceProxy._generateRays(mode='fans') (surface_source.py:469-517) + _makeRay with theta = phi = 0 (:85-111):
+  one ray per grid point, leaving along the face normal.  Returns a point_source.RayBatch.
+  '''
+  from .point_source import RayBatch
+  dist_tol = max(float(dist_tol), 1e-9)                                   # _getDistTol, :114-119
+  weights = emit.areas/np.sum(emit.areas)
+  origins, directions, face_index = [], [], []
+  for i, n_rays in fan_ray_counts(weights, float(obj.get('FanModeRayCount', 100))):
+    face = FaceEvaluator(emit.faces[i], emit.segs)
+    for (u, v), point, (du, dv) in make_surface_grid(face, n_rays, dist_tol):
+      normal = face.normal_at(u, v)
+      origins.append(point)
+      directions.append((point+normal)-point)                             # gpM*pMi*(origin+direction) - origin, :104-106
+      face_index.append(i)
+  n = len(origins)
+  return RayBatch(np.array(origins).reshape(-1, 3), np.array(directions).reshape(-1, 3), np.ones(n), float(obj.get('Wavelength', 500.0)),
+                  dict(initPhi=np.zeros(n), initTheta=np.zeros(n), emitFace=np.array(face_index, dtype=np.int64)))

@@ -1,0 +1,102 @@
+'''
+Fan mode of the surface light source (reference freecad_elements/surface_source.py:122-267 _makeSurfaceGrid,
+:469-517 the 'fans' branch of _generateRays, :85-111 _makeRay): the restated grid algorithm against what the
+reference's own code produces for the same faces (tests/golden/surface_fan_golden.npz, generator
+tests/golden/make_surface_fan_golden.py), then through runSimulationIteration / runSimulation on a shipped scene.
+'''
+import os
+
+import numpy as np
+import pytest
+
+import surface_fan_cases as cases
+from freecad.optics_design_workbench_b200.freecad_elements import surface_source as ss
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'surface_fan_golden.npz')
+
+
+@pytest.fixture(scope='module')
+def golden():
+  return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize('name', list(cases.GRID_CASES))
+def test_grid_equals_reference_make_surface_grid(name, golden):
+  build, tol, counts = cases.GRID_CASES[name]
+  emit = build()
+  face = ss.FaceEvaluator(emit.faces[0], emit.segs)
+  for n in counts:
+    grid = ss.make_surface_grid(face, n, tol)
+    want = golden[f'{name}@{n}/uv']
+    assert len(grid) == len(want), (name, n)
+    if not len(grid):
+      continue                                           # the reference places nothing either (1 or 4 points on a disc / sphere)
+    np.testing.assert_array_equal(np.array([g[0] for g in grid]), want)
+    np.testing.assert_array_equal(np.array([g[1] for g in grid]), golden[f'{name}@{n}/points'])
+    np.testing.assert_array_equal(np.array([g[2][0] for g in grid]), golden[f'{name}@{n}/du'])
+    np.testing.assert_array_equal(np.array([g[2][1] for g in grid]), golden[f'{name}@{n}/dv'])
+
+
+def test_grid_is_roughly_equidistant_on_a_sphere(golden):
+  'the point of the five passes: rows near the poles are thinned'
+  uv = golden['sphere@300/uv']
+  per_row = {round(float(v), 9): int((np.abs(uv[:, 1]-v) < 1e-9).sum()) for v in np.unique(uv[:, 1])}
+  rows = sorted(per_row)
+  assert per_row[rows[len(rows)//2]] >= 4*per_row[rows[0]] and per_row[rows[0]] >= 1
+
+
+@pytest.mark.parametrize('name', list(cases.SOURCE_CASES))
+def test_fan_rays_equal_reference_generate_rays(name, golden):
+  build, tol, count = cases.SOURCE_CASES[name]
+  emit = build()
+  batch = ss.generate_fan_rays(dict(FanModeRayCount=count, Wavelength=500.0), emit, tol)
+  if f'{name}/origins' not in golden.files:
+    # more than 30 % of the faces would have to be skipped: the reference raises NameError here (its warning uses the
+    # undefined names `warnings` and `rayCount`, surface_source.py:485-488).  The restatement follows the skipping rule
+    # literally instead of raising; with 24 equal faces its step (skip fraction / weight * face count) exceeds 1 for
+    # every face, so every face is skipped.
+    assert name == 'many_faces_10' and len(batch) == 0
+    return
+  np.testing.assert_array_equal(batch.origins, golden[f'{name}/origins'])
+  np.testing.assert_allclose(batch.directions, golden[f'{name}/directions'], rtol=0, atol=1e-15)
+  assert np.abs(np.linalg.norm(batch.directions, axis=1)-1).max() < 1e-12
+
+
+def test_fan_rays_leave_along_the_outward_normal():
+  emit = cases.SOURCE_CASES['box_and_sphere_60'][0]()
+  batch = ss.generate_fan_rays(dict(FanModeRayCount=60), emit, 1e-2)
+  sphere = batch.metadata['emitFace'] == 6
+  centre = np.array([0.0, 0.0, -20.0])
+  np.testing.assert_allclose(batch.directions[sphere], (batch.origins[sphere]-centre)/3.0, atol=1e-12)
+
+
+def run_fans(sim, engine, tmp_path):
+  from freecad.optics_design_workbench_b200.simulation import simulation_loop
+  from test_simulation_loop import load_hits
+  run = simulation_loop.runSimulation(sim, 'fans', engine=engine, basePath=str(tmp_path/'f.OpticsDesign'))
+  return load_hits(run)
+
+
+def test_simulation_loop_fans_of_a_surface_source(tmp_path, sims, oracle):
+  'test/21-simulation-modes/main.FCStd: the z = 38 face of a 10x10 box emits along -z, 11 x 11 grid for FanModeRayCount = 100'
+  from oracle_engine import OracleEngine
+  sim = sims('surfaceSourceTest21')
+  rec = sim.source_records[0]
+  batch = ss.generate_fan_rays(rec, rec['emit'], sim.settings['DistanceTolerance'])
+  assert len(batch) == 121 and np.abs(batch.directions-[0, 0, -1]).max() < 1e-12
+  xy = np.unique(np.round(batch.origins[:, :2], 9), axis=0)
+  assert len(xy) == 121 and np.allclose(np.unique(xy[:, 0]), np.arange(-5, 6)) and np.all(batch.origins[:, 2] == 38)
+  hits = run_fans(sim, OracleEngine(), tmp_path)                 # a ball lens sits between the emitter and the absorber
+  direct = oracle.trace_rays(sim.scene, sim.cfg(), batch.origins, batch.directions)
+  assert len(hits['points']) == direct['counts']['hits'] > 30
+  assert np.abs(hits['points'][:, 2]-10).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_fans_of_a_surface_source(tmp_path, sims, gpu_engine):
+  from oracle_engine import OracleEngine
+  g = run_fans(sims('surfaceSourceTest21'), gpu_engine, tmp_path/'gpu')
+  o = run_fans(sims('surfaceSourceTest21'), OracleEngine(), tmp_path/'cpu')
+  assert len(g['points']) == len(o['points']) > 30
+  np.testing.assert_allclose(g['points'], o['points'], rtol=0, atol=1e-9)
+  np.testing.assert_array_equal(g['directions'], o['directions'])
