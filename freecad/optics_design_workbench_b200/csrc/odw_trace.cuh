@@ -155,7 +155,13 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
   const double tmax = max_len + tol;
   NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = tmax; h.fA = -1; h.fB = -1;
   const float sx = (float)s[0], sy = (float)s[1], sz = (float)s[2];
-  const float ix = __frcp_rn((float)dn[0]), iy = __frcp_rn((float)dn[1]), iz = __frcp_rn((float)dn[2]);   // 1/0 = inf is fine
+  // MUFU reciprocal: 1 ulp, inside the culling margin; 1/0 = inf is fine.  (The slab distances must stay
+  // (lo - s)*inv: as one FMA, lo*inv - s*inv, an axis-parallel ray gives inf - inf = NaN for ONE side of a slab and
+  // the other side then serves as both entry and exit — measured: every ray of a collimated source was culled.)
+  float ix, iy, iz;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"((float)dn[0]));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"((float)dn[1]));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dn[2]));
   float limf = (float)tmax*1.000002f;                                  // nothing beyond this can still matter
   const bool seq_off = !p.sequential;
   const bool seq_dead = seq_index >= 128;

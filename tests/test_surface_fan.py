@@ -99,4 +99,4 @@ def test_gpu_fans_of_a_surface_source(tmp_path, sims, gpu_engine):
   o = run_fans(sims('surfaceSourceTest21'), OracleEngine(), tmp_path/'cpu')
   assert len(g['points']) == len(o['points']) > 30
   np.testing.assert_allclose(g['points'], o['points'], rtol=0, atol=1e-9)
-  np.testing.assert_array_equal(g['directions'], o['directions'])
+  np.testing.assert_allclose(g['directions'], o['directions'], rtol=0, atol=1e-9)
