@@ -356,7 +356,7 @@ bool shell_is_convex(const odw_scene_desc* sd, int face_first, int face_count) {
   double scale = 0;
   for (int fi = face_first; fi < face_first + face_count; ++fi) {
     const odw_face& f = sd->faces[fi];
-    if (f.kind == ODW_SURF_TORUS) return false;
+    if (f.kind == ODW_SURF_TORUS || f.kind == ODW_SURF_CONICOID) return false;
     Sample s;
     if (f.kind == ODW_SURF_PLANE) {
       if (f.trim_kind == ODW_TRIM_UVBOX) {
@@ -435,7 +435,9 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   for (int i = 0; i < sd->n_faces; ++i) {
     const odw_face& f = sd->faces[i];
     if (f.group < 0 || f.group >= sd->n_groups) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": group out of range");
-    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_TORUS) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": unknown surface kind");
+    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_CONICOID) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": unknown surface kind");
+    if (f.kind == ODW_SURF_CONICOID && !(f.p0 != 0 && std::isfinite(f.p0) && std::isfinite(f.p1)))
+      return fail(ODW_EINVAL, "face " + std::to_string(i) + ": a conicoid needs a finite non-zero vertex curvature (p0) and a finite conic constant (p1)");
     if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_segs))
       return fail(ODW_EINVAL, "face " + std::to_string(i) + ": trim segment range out of bounds");
     DFace& d = faces[(size_t)i];
@@ -571,7 +573,7 @@ static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw
   if (!(std::fabs(sd->emit_cdf[sd->n_emit-1] - 1.0) < 1e-12)) return fail(ODW_EINVAL, "surface source: emit_cdf must end at 1");
   for (int i = 0; i < sd->n_emit; ++i) {
     const odw_face& f = sd->emit_faces[i];
-    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_TORUS) return fail(ODW_EINVAL, "surface source: unknown surface kind of an emitting face");
+    if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_TORUS) return fail(ODW_EINVAL, "surface source: unknown surface kind of an emitting face");   // conicoids do not emit (no area-uniform draw yet): mesh them
     if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_emit_segs || !sd->emit_segs))
       return fail(ODW_EINVAL, "surface source: trim segment range of an emitting face out of bounds");
     if (i && sd->emit_cdf[i] < sd->emit_cdf[i-1]) return fail(ODW_EINVAL, "surface source: emit_cdf must be non-decreasing");

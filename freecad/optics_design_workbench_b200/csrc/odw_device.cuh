@@ -367,6 +367,17 @@ __device__ __noinline__ int line_surface(const DFace& f, const double* s, const 
     }
     case ODW_SURF_TORUS:
       return line_torus(f, w, d, t);
+    case ODW_SURF_CONICOID: {
+      // c (rho^2 + (1+k) z^2) - 2 z = 0 along w + t d; a paraboloid met along its axis has a = 0 (one root).  Only the
+      // sheet the sag formula describes counts: q = 1 - (1+k) c z >= 0.
+      const double c = f.p0, k = f.p1;
+      const double wz = dot3(w, f.z), dz = dot3(d, f.z);
+      double r[2];
+      const int n = solve_quadratic(c*(1.0 + k*dz*dz), 2*(c*(dot3(w, d) + k*wz*dz) - dz), c*(dot3(w, w) + k*wz*wz) - 2*wz, r);
+      int m = 0;
+      for (int i = 0; i < n; ++i) if (1.0 - (1.0 + k)*c*(wz + r[i]*dz) >= 0) t[m++] = r[i];
+      return m;
+    }
   }
   return 0;
 }
@@ -443,6 +454,11 @@ __device__ __noinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* 
       double sn = fmin(1.0, fmax(-1.0, dot3(w, f.z)/f.p0));
       v = asin(sn); su = f.p0*sqrt(fmax(0.0, 1 - sn*sn)); sv = f.p0; u = 0; break;
     }
+    case ODW_SURF_CONICOID: {   // v = rho; meridian arc length per unit rho = sqrt(1 + z'^2), z' = c rho / q
+      v = sqrt(x*x + y*y);
+      const double q2 = fmax(1e-12, 1.0 - (1.0 + f.p1)*f.p0*f.p0*v*v);
+      su = v; sv = sqrt(1.0 + f.p0*f.p0*v*v/q2); u = 0; break;
+    }
     default: {   // torus
       double rho = sqrt(x*x + y*y);
       v = atan2(dot3(w, f.z), rho - f.p0);
@@ -483,6 +499,10 @@ __device__ __forceinline__ void outward_normal_general(const DFace& f, const dou
       double rho = sqrt(rx*rx + ry*ry + rz*rz);
       double sg = (f.p0 + z/ca*sa) >= 0 ? 1.0 : -1.0;
       g[0] = ca*rx/rho - sg*sa*f.z[0]; g[1] = ca*ry/rho - sg*sa*f.z[1]; g[2] = ca*rz/rho - sg*sa*f.z[2]; break;
+    }
+    case ODW_SURF_CONICOID: {   // du x dv ~ c rho_vec - q Z, q = 1 - (1+k) c z
+      const double z = dot3(w, f.z), q = 1.0 - (1.0 + f.p1)*f.p0*z;
+      g[0] = f.p0*(w[0]-z*f.z[0]) - q*f.z[0]; g[1] = f.p0*(w[1]-z*f.z[1]) - q*f.z[1]; g[2] = f.p0*(w[2]-z*f.z[2]) - q*f.z[2]; break;
     }
     default: {
       double z = dot3(w, f.z);

@@ -118,6 +118,30 @@ def plano_convex_lens(R, aperture_radius, edge_thickness=0.0):
   return faces
 
 
+def conicoid_surface(c, k, vertex=(0, 0, 0)):
+  'conic of revolution about +z with its vertex at `vertex`: sag c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2)) (include/odw.h)'
+  return Surface('conicoid', p=np.asarray(vertex, float), n=_Z.copy(), dx=_X.copy(), dy=_Y.copy(), c=float(c), k=float(k))
+
+
+def conic_dish(c, k, aperture_radius, inner_radius=0.0, reversed_=False):
+  '''
+  Open single-face shell: the conic of revolution z = sag(rho) for inner_radius <= rho <= aperture_radius (a parabolic
+  mirror for k = -1: focal length 1/(2c), focus at z = 1/(2c)).  Geometric normal c rho - q z: away from the focus side.
+  '''
+  return [_face(conicoid_surface(c, k), [_rect_loop(0, TWO_PI, inner_radius, aperture_radius)], reversed_=reversed_, shell_key=None)]
+
+
+def revolved_parabola_dish(focal, aperture_radius):
+  '''
+  The same paraboloid the way OCC writes it: surface of revolution (BRep surface type 7) of a Geom_Parabola about its own
+  axis, trimmed to 0 <= t <= aperture_radius.  Exercises the revolution -> conicoid recognition of scene.face_record.
+  '''
+  from .brep import Curve3d
+  par = Curve3d('parabola', p=np.zeros(3), n=_Y.copy(), dx=_Z.copy(), dy=_X.copy(), f=float(focal))
+  surf = Surface('revolution', p=np.zeros(3), d=_Z.copy(), curve=par)
+  return [_face(surf, [_rect_loop(0, TWO_PI, 0.0, aperture_radius)], shell_key=None)]
+
+
 # ------------------------------------------------------------------------------------------
 # rigid transforms
 

@@ -5,12 +5,12 @@ CPU oracle and the tests.  numpy structured dtypes below mirror the C structs by
 What the reference does per segment — walk every optical group, every placement of it, every
 shell, every face, and ask OCC (reference freecad_elements/ray.py:328-432) — is replaced by a
 one-shot export: every face instance is written once, in WORLD coordinates, as a closed-form
-surface (plane / cylinder / cone / sphere / torus) plus its trimming region in (u, v) space.
+surface (plane / cylinder / cone / sphere / torus / conic of revolution) plus its trimming region in (u, v) space.
 '''
 
 import numpy as np
 
-SURF_PLANE, SURF_CYLINDER, SURF_CONE, SURF_SPHERE, SURF_TORUS = 1, 2, 3, 4, 5
+SURF_PLANE, SURF_CYLINDER, SURF_CONE, SURF_SPHERE, SURF_TORUS, SURF_CONICOID = 1, 2, 3, 4, 5, 6
 TRIM_NONE, TRIM_UVBOX, TRIM_LOOPS = 0, 1, 2
 SEG_LINE, SEG_ARC = 1, 2
 OPT_MIRROR, OPT_LENS, OPT_GRATING, OPT_ABSORBER, OPT_VACUUM = 0, 1, 2, 3, 4
@@ -19,7 +19,7 @@ GRATING_TYPES = ('Reflection', 'Transmission')
 SRC_POINT_SPHERICAL, SRC_POINT_COLLIMATED, SRC_SURFACE = 0, 1, 2
 
 _KIND_ID = dict(plane=SURF_PLANE, cylinder=SURF_CYLINDER, cone=SURF_CONE, sphere=SURF_SPHERE,
-                torus=SURF_TORUS)
+                torus=SURF_TORUS, conicoid=SURF_CONICOID)
 
 FACE_DTYPE = np.dtype([
   ('origin', '<f8', 3), ('xdir', '<f8', 3), ('ydir', '<f8', 3), ('zdir', '<f8', 3),
@@ -168,12 +168,46 @@ def _rigid(transform):
   return R, transform[:3, 3]
 
 
+def conic_sag(c, k, rho):
+  'optical sag of a conic of revolution: z = c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2))'
+  rho = np.asarray(rho, dtype=float)
+  return c*rho*rho/(1+np.sqrt(np.maximum(0.0, 1-(1+k)*c*c*rho*rho)))
+
+
+def _revolved_conic(surf):
+  '''
+  A surface of revolution that is a conic of revolution in closed form, as a 'conicoid' Surface (frame + c, k), or None.
+  Recognised: a Geom_Parabola revolved about its own axis (what Part.Parabola + Revolve writes) = paraboloid, k = -1,
+  c = 1/(2 F).  OCC's (u, v) = (rotation angle about the axis, parabola parameter t = signed distance from the axis):
+  the frame is chosen so that v = t = rho on the t >= 0 branch.
+  '''
+  from .brep import Surface
+  curve = surf.curve
+  while curve.kind == 'trimmed':
+    curve = curve.basis
+  if curve.kind != 'parabola':
+    return None
+  axis = np.asarray(surf.d, dtype=float)
+  axis = axis/np.linalg.norm(axis)
+  Z = np.asarray(curve.dx, dtype=float)                  # symmetry axis of the parabola, apex -> focus
+  if np.linalg.norm(np.cross(axis, Z)) > 1e-12:
+    return None                                           # revolved about another line: not a paraboloid
+  off = np.asarray(curve.p, dtype=float)-np.asarray(surf.p, dtype=float)
+  if np.linalg.norm(off-np.dot(off, axis)*axis) > 1e-9*max(1.0, abs(curve.f)):
+    return None                                           # the axis of revolution misses the apex
+  X = np.asarray(curve.dy, dtype=float)
+  Y = np.cross(axis, X)                                   # rotation by u about `axis` takes X towards Y
+  return Surface('conicoid', p=np.asarray(curve.p, dtype=float), n=Z, dx=X, dy=Y, c=1.0/(2.0*curve.f), k=-1.0)
+
+
 def face_record(fi, transform, group, shell, face_id, segs_out):
   '''
   Convert a brep.FaceInstance (+ an extra world transform applied on the left) into a FACE_DTYPE
   row; trim segments are appended to segs_out (list of (kind, a)).
   '''
   surf = fi.surface
+  if surf.kind == 'revolution':
+    surf = _revolved_conic(surf) or surf
   if surf.kind not in _KIND_ID:
     raise UnsupportedGeometry(f'surface kind {surf.kind!r} has no closed form')
   R, T = _rigid(transform @ fi.transform)
@@ -190,6 +224,10 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
     f['p0'], f['p1'] = surf.r, surf.angle
   elif surf.kind == 'torus':
     f['p0'], f['p1'] = surf.r, surf.r2
+  elif surf.kind == 'conicoid':
+    if not (np.isfinite(surf.c) and surf.c != 0 and np.isfinite(surf.k)):
+      raise UnsupportedGeometry('conicoid needs a finite non-zero vertex curvature and a finite conic constant')
+    f['p0'], f['p1'] = surf.c, surf.k
   f['group'], f['shell'], f['face_id'] = group, shell, face_id
 
   segs = []
@@ -206,6 +244,12 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
   else:
     lo, hi = _segs_bbox(segs)
     trim = TRIM_UVBOX if _is_uvbox(segs, lo, hi) else TRIM_LOOPS
+    if surf.kind == 'conicoid':
+      if lo[1] < -1e-9*max(1.0, abs(hi[1])):
+        raise UnsupportedGeometry('conicoid face on the negative branch of its meridian')
+      lo[1] = max(lo[1], 0.0)
+      if (1+surf.k)*surf.c**2*hi[1]**2 > 1:
+        raise ValueError('conicoid face reaches beyond the equator of its ellipsoid: the sag formula has no value there')
     if trim == TRIM_UVBOX:
       full_u = abs((hi[0]-lo[0])-TWO_PI) < 1e-9
       if surf.kind == 'sphere' and full_u and lo[1] < -np.pi/2+1e-9 and hi[1] > np.pi/2-1e-9:
@@ -238,6 +282,8 @@ def eval_face(f, u, v):
     return O + f['p0']*np.cos(v)*er + f['p0']*np.sin(v)*Z
   if k == SURF_TORUS:
     return O + (f['p0']+f['p1']*np.cos(v))*er + f['p1']*np.sin(v)*Z
+  if k == SURF_CONICOID:
+    return O + v*er + conic_sag(float(f['p0']), float(f['p1']), v)*Z
   raise ValueError(k)
 
 
@@ -253,8 +299,14 @@ def _face_aabb(f, n=65):
   # sagitta of the sampling: a point between samples can stick out by R(1-cos(h/2))
   hu = (hi[0]-lo[0])/(n-1)
   rmax = {SURF_CYLINDER: f['p0'], SURF_SPHERE: f['p0'], SURF_TORUS: f['p0']+f['p1'],
-          SURF_CONE: abs(f['p0'])+max(abs(lo[1]), abs(hi[1]))*abs(np.sin(f['p1']))}[k]
+          SURF_CONE: abs(f['p0'])+max(abs(lo[1]), abs(hi[1]))*abs(np.sin(f['p1'])),
+          SURF_CONICOID: hi[1]}[k]
   pad = rmax*(1-np.cos(hu/2))
+  if k == SURF_CONICOID:
+    # between two samples of a meridian the sag deviates from the chord by at most h^2/8 max|z''|, z'' = c / q^3
+    hv = (hi[1]-lo[1])/(n-1)
+    q = np.sqrt(max(1e-12, 1-(1+float(f['p1']))*float(f['p0'])**2*hi[1]**2))
+    pad += hv*hv/8*abs(float(f['p0']))/q**3
   if k in (SURF_SPHERE, SURF_TORUS):
     hv = (hi[1]-lo[1])/(n-1)
     rv = f['p0'] if k == SURF_SPHERE else f['p1']

@@ -51,6 +51,7 @@ extern "C" {
 #define ODW_SURF_CONE      3
 #define ODW_SURF_SPHERE    4
 #define ODW_SURF_TORUS     5
+#define ODW_SURF_CONICOID  6   /* conic of revolution (paraboloid, ellipsoid, hyperboloid sheet, sphere cap), see odw_face */
 
 /* trim kinds: how "point lies on the trimmed face" (ray.py:426) is decided in the surface's (u,v) space */
 #define ODW_TRIM_NONE   0    /* whole (closed) surface, e.g. full sphere / full torus */
@@ -80,7 +81,12 @@ extern "C" {
  * M = gpM * pMi of ray.py:338-339 folded into origin/xdir/ydir/zdir).
  * Parametrisations are OCC's:  plane O+u X+v Y;  cylinder O+r(cos u X+sin u Y)+v Z;
  * cone O+(r+v sin a)(cos u X+sin u Y)+v cos a Z;  sphere O+R cos v(cos u X+sin u Y)+R sin v Z;
- * torus O+(R+r cos v)(cos u X+sin u Y)+r sin v Z.
+ * torus O+(R+r cos v)(cos u X+sin u Y)+r sin v Z;
+ * conicoid O+v(cos u X+sin u Y)+sag(v) Z with the optical sag sag(v) = c v^2/(1+sqrt(1-(1+k) c^2 v^2)), v = distance from
+ * the axis >= 0, c = vertex curvature (p0), k = conic constant (p1): k = -1 paraboloid of focal length 1/(2c) (what OCC
+ * writes as the surface of revolution of a Geom_Parabola about its own axis), -1 < k < 0 prolate / k > 0 oblate
+ * ellipsoid, k < -1 hyperboloid sheet, k = 0 sphere.  n_geom of a conicoid = du x dv / |du x dv| ~ c rho_vec - q Z,
+ * q = 1 - (1+k) c z (the side the vertex bulges towards for c > 0).
  * Outward normal n_out = nsign * n_geom, n_geom = the radial-outward normal written with (X,Y,Z)
  * (plane: Z); nsign folds the face orientation (TopAbs_REVERSED) and the handedness of the frame. */
 typedef struct odw_face {
@@ -88,8 +94,8 @@ typedef struct odw_face {
   double xdir[3];
   double ydir[3];
   double zdir[3];
-  double p0;            /* cylinder r | cone r (at v=0) | sphere R | torus major R */
-  double p1;            /* cone semi-angle | torus minor r */
+  double p0;            /* cylinder r | cone r (at v=0) | sphere R | torus major R | conicoid vertex curvature c */
+  double p1;            /* cone semi-angle | torus minor r | conicoid conic constant k */
   double uv_min[2];     /* trim bounding box in (u,v); also the start of the period window */
   double uv_max[2];
   double aabb_min[3];   /* world AABB of the trimmed face (not enlarged; tolerance added by the consumer) */

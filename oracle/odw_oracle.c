@@ -345,6 +345,17 @@ static int line_surface(const odw_face* f, const double* s, const double* d, dou
       for (int i = 0; i < n; ++i) t[i] = t0 + roots[i];
       return n;
     }
+    case ODW_SURF_CONICOID: {
+      /* c (rho^2 + (1+k) z^2) - 2 z = 0 along w + t d:  A t^2 + B t + C = 0; a paraboloid met along its axis has A = 0 */
+      double c = f->p0, k = f->p1;
+      double wz = dot3(w, f->zdir), dz = dot3(d, f->zdir);
+      double A = c*(1.0 + k*dz*dz), B = 2*(c*(dot3(w, d) + k*wz*dz) - dz), C = c*(dot3(w, w) + k*wz*wz) - 2*wz;
+      double r[2];
+      int n = solve_quadratic(A, B, C, r), m = 0;
+      /* the sheet of the quadric that the sag formula describes: q = 1 - (1+k) c z >= 0 */
+      for (int i = 0; i < n; ++i) if (1.0 - (1.0 + k)*c*(wz + r[i]*dz) >= 0) t[m++] = r[i];
+      return m;
+    }
   }
   return 0;
 }
@@ -396,6 +407,13 @@ static void surface_uv_normal(const odw_face* f, const double* P, double* uv, do
       }
       break;
     }
+    case ODW_SURF_CONICOID: {
+      /* v = rho; du x dv is along c rho_vec - q Z, q = 1 - (1+k) c z (= the square root of the sag formula) */
+      double q = 1.0 - (1.0 + f->p1)*f->p0*z;
+      uv[0] = atan2(y, x); uv[1] = sqrt(x*x + y*y);
+      for (int i = 0; i < 3; ++i) ng[i] = f->p0*(x*f->xdir[i] + y*f->ydir[i]) - q*f->zdir[i];
+      break;
+    }
     default:
       uv[0] = uv[1] = 0; ng[0] = ng[1] = 0; ng[2] = 1;
   }
@@ -432,6 +450,11 @@ static int trim_contains(const odw_face* f, const odw_trimseg* segs, double* uv,
     case ODW_SURF_CONE:     su = fabs(f->p0 + v*sin(f->p1)); uper = 1; break;
     case ODW_SURF_SPHERE:   su = f->p0*cos(v); sv = f->p0; uper = 1; break;
     case ODW_SURF_TORUS:    su = f->p0 + f->p1*cos(v); sv = f->p1; uper = 1; vper = 1; break;
+    case ODW_SURF_CONICOID: {   /* meridian arc length per unit rho: sqrt(1 + z'^2), z' = c rho / q */
+      double q2 = 1.0 - (1.0 + f->p1)*f->p0*f->p0*v*v;
+      if (q2 < 1e-12) q2 = 1e-12;
+      su = v; sv = sqrt(1.0 + f->p0*f->p0*v*v/q2); uper = 1; break;
+    }
   }
   if (su < 1e-12) su = 1e-12;
   double tu = tol/su, tv = tol/sv;
