@@ -201,6 +201,7 @@ def main():
   torch.cuda.set_device(local_rank)
   distributed = world > 1
   if distributed:
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not share stdout with the JSON line
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
   n_rays = int(args.rays)

@@ -12,11 +12,11 @@
 #include <vector>
 #include "odw_device.cuh"
 
-extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int blocks, size_t smem, cudaStream_t st);
+extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int need, int blocks, size_t smem, cudaStream_t st);
 extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
                                          unsigned long long n, double* first_out, double* phi_out, double* origins,
                                          double* dirs, int blocks, cudaStream_t st);
-extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem);
+extern "C" int odw_trace_occupancy(bool mc, bool bvh, int need, size_t smem);
 extern "C" int odw_trace_threads(void);
 // wavefront kernels (odw_wavefront.cu)
 extern "C" size_t odw_wf_pool_bytes_per_ray(void);
@@ -88,6 +88,7 @@ struct odw_scene {
   size_t smem = 0;
   int n_groups = 0;
   double extent = 0;                    // max |coordinate| over all face boxes
+  bool ext_optics = false;              // a grating, a stochastic surface model or a finite absorption length somewhere (FEAT_EXT)
   std::vector<BvhNode2> bvh_host;       // un-widened device nodes (boxes rounded outward)
   std::vector<BvhNode2> bvh_staging;    // widened copy being uploaded
   BvhNode2* bvh_dev = nullptr;
@@ -503,6 +504,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   }
   odw_scene* sc = new odw_scene();
   sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
+  for (const DGroup& g : groups)
+    if (g.type == ODW_OPT_GRATING || g.scat_main >= 0 || g.scat_modify >= 0 || std::isfinite(g.absorption_length)) sc->ext_optics = true;
   int rc;
   if ((rc = upload(eng, sc->owned, faces.data(), faces.size(), &sc->d.faces))) { odw_scene_destroy(sc); return rc; }
   if ((rc = upload(eng, sc->owned, shells.data(), shells.size(), &sc->d.shells))) { odw_scene_destroy(sc); return rc; }
@@ -803,8 +806,14 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, ui
 }
 
 // Issues the trace of p.n_rays rays as back-to-back launches on the engine stream (no synchronisation).
+// features the launch needs (FEAT_* of odw_trace.cuh): the kernel instance is chosen from these
+static int launch_features(const odw_scene* sc, const TraceParams& p, bool mc) {
+  return (sc->ext_optics ? 1 : 0) | ((mc && p.src.kind == ODW_SRC_SURFACE) ? 2 : 0) | (p.sequential ? 4 : 0) | (p.n_binnings > 0 ? 8 : 0);
+}
+
 static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams& p, bool mc, uint64_t* launches) {
-  int per_sm = odw_trace_occupancy(mc, sc->use_bvh, sc->smem);
+  const int need = launch_features(sc, p, mc);
+  int per_sm = odw_trace_occupancy(mc, sc->use_bvh, need, sc->smem);
   if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
   // persistent grid: a multiple of the SM count, no more blocks than there is work
   const int blocks = eng->sm_count*per_sm;
@@ -848,7 +857,7 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     const uint64_t tpb = (uint64_t)odw_trace_threads();
     uint64_t want_w = (q.n_rays + tpb - 1)/tpb;
     int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
-    CU(odw_launch_trace(&q, mc, sc->use_bvh, blocks_w, sc->smem, eng->wave_stream[wave_index % (uint64_t)n_streams]));
+    CU(odw_launch_trace(&q, mc, sc->use_bvh, need, blocks_w, sc->smem, eng->wave_stream[wave_index % (uint64_t)n_streams]));
     if (launches) ++*launches;
   }
   for (int i = 1; i < n_streams; ++i) { CU(cudaEventRecord(eng->ev_join[i], eng->wave_stream[i])); CU(cudaStreamWaitEvent(eng->stream, eng->ev_join[i], 0)); }

@@ -17,7 +17,7 @@
 #ifndef ODW_THREADS
 #define ODW_THREADS 256          // threads per CTA of the trace kernel
 #endif
-template <bool MC, bool BVH>
+template <bool MC, bool BVH, int FEAT>
 __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DShell* sshells = reinterpret_cast<DShell*>(smem_raw);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
   bool alive = false;
   for (;;) {
-    if (!alive && i < p.n_rays) { fetch_ray<MC>(p, i, r); alive = true; }
+    if (!alive && i < p.n_rays) { fetch_ray<MC, FEAT>(p, i, r); alive = true; }
 #if ODW_BLOCK_SYNC
     // block-wide re-convergence: all warps of a CTA stay in the same phase of the loop, so the CTA's instruction
     // working set is one phase (init / intersect / interact) instead of all of them at once
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
         ++n_isect;
         double t;
         const int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
-                           : find_nearest_smem(sshells, sfaces, p, point, dn, medium, seq_index, skip_shell, p.max_len, t);
-        done = interact<MC>(p, BVH ? p.scene.faces : sfaces, BVH ? nullptr : sshells, groups, fi, t, i, r, s_cnt);
+                           : find_nearest_smem<FEAT>(sshells, sfaces, p, point, dn, medium, seq_index, skip_shell, p.max_len, t);
+        done = interact<MC, FEAT>(p, BVH ? p.scene.faces : sfaces, BVH ? nullptr : sshells, groups, fi, t, i, r, s_cnt);
       }
       if (done) { finish_ray<MC>(p, i, r, s_cnt); alive = false; i += stride; }
     }
@@ -130,21 +130,41 @@ __global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long 
 // ------------------------------------------------------------------------------------------
 // launch helpers used by odw_api.cu
 
-extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int blocks, size_t smem, cudaStream_t st) {
-  if (mc) {
-    if (bvh) trace_kernel<true, true><<<blocks, ODW_THREADS, 0, st>>>(*p);
-    else {
-      cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      trace_kernel<true, false><<<blocks, ODW_THREADS, smem, st>>>(*p);
-    }
-  } else {
-    if (bvh) trace_kernel<false, true><<<blocks, ODW_THREADS, 0, st>>>(*p);
-    else {
-      cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      trace_kernel<false, false><<<blocks, ODW_THREADS, smem, st>>>(*p);
-    }
-  }
+// Kernel instances: the Monte-Carlo kernel for scenes staged in shared memory (the hot configuration) exists in three
+// feature sets, everything else only with all features.  pick_feat() maps the features a launch needs to the leanest
+// instance that covers them.
+static int pick_feat(bool mc, bool bvh, int need) {
+  if (!mc || bvh) return FEAT_ALL;
+  if (need == 0) return 0;
+  if ((need & ~FEAT_SEQ) == 0) return FEAT_SEQ;
+  return FEAT_ALL;
+}
+
+template <bool MC, bool BVH, int FEAT>
+static cudaError_t launch_instance(const TraceParams* p, int blocks, size_t smem, cudaStream_t st) {
+  if (!BVH) cudaFuncSetAttribute(trace_kernel<MC, BVH, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  trace_kernel<MC, BVH, FEAT><<<blocks, ODW_THREADS, BVH ? 0 : smem, st>>>(*p);
   return cudaGetLastError();
+}
+
+template <bool MC, bool BVH, int FEAT>
+static int occupancy_instance(size_t smem) {
+  int nb = 0;
+  if (!BVH) cudaFuncSetAttribute(trace_kernel<MC, BVH, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<MC, BVH, FEAT>, ODW_THREADS, BVH ? 0 : smem);
+  return nb;
+}
+
+extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int need, int blocks, size_t smem, cudaStream_t st) {
+  const int feat = pick_feat(mc, bvh, need);
+  if (mc && !bvh) {
+    if (feat == 0) return launch_instance<true, false, 0>(p, blocks, smem, st);
+    if (feat == FEAT_SEQ) return launch_instance<true, false, FEAT_SEQ>(p, blocks, smem, st);
+    return launch_instance<true, false, FEAT_ALL>(p, blocks, smem, st);
+  }
+  if (mc) return launch_instance<true, true, FEAT_ALL>(p, blocks, smem, st);
+  if (bvh) return launch_instance<false, true, FEAT_ALL>(p, blocks, smem, st);
+  return launch_instance<false, false, FEAT_ALL>(p, blocks, smem, st);
 }
 
 extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
@@ -156,13 +176,16 @@ extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long 
 
 extern "C" int odw_trace_threads(void) { return ODW_THREADS; }
 
-extern "C" int odw_trace_occupancy(bool mc, bool bvh, size_t smem) {
-  int nb = 0;
-  if (mc && bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, true>, ODW_THREADS, 0);
-  else if (mc) { cudaFuncSetAttribute(trace_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<true, false>, ODW_THREADS, smem); }
-  else if (bvh) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, true>, ODW_THREADS, 0);
-  else { cudaFuncSetAttribute(trace_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, trace_kernel<false, false>, ODW_THREADS, smem); }
-  return nb;
+extern "C" int odw_trace_occupancy(bool mc, bool bvh, int need, size_t smem) {
+  const int feat = pick_feat(mc, bvh, need);
+  if (mc && !bvh) {
+    if (feat == 0) return occupancy_instance<true, false, 0>(smem);
+    if (feat == FEAT_SEQ) return occupancy_instance<true, false, FEAT_SEQ>(smem);
+    return occupancy_instance<true, false, FEAT_ALL>(smem);
+  }
+  if (mc) return occupancy_instance<true, true, FEAT_ALL>(smem);
+  if (bvh) return occupancy_instance<false, true, FEAT_ALL>(smem);
+  return occupancy_instance<false, false, FEAT_ALL>(smem);
 }
+
+extern "C" int odw_trace_instance(bool mc, bool bvh, int need) { return pick_feat(mc, bvh, need); }

@@ -11,6 +11,15 @@ namespace {   // internal linkage, see odw_device.cuh
 
 namespace cg = cooperative_groups;
 
+// Scene / launch features a kernel instance is compiled for.  The trace kernel is one big state machine; code for features
+// the scene does not use still costs registers (spills) and instruction-cache room in the bounce loop, so the host picks
+// the leanest instance that covers the launch (odw_api.cu launch_features): measured +12 % on lensesAndMirrors.
+enum { FEAT_EXT = 1,        // gratings, stochastic surface models, finite absorption lengths
+       FEAT_SURFSRC = 2,    // surface light source (init_ray_surface)
+       FEAT_SEQ = 4,        // SequentialMode filtering
+       FEAT_BIN = 8,        // detector binning on the device
+       FEAT_ALL = 15 };
+
 // per-CTA event counters in shared memory (flushed to the global Counters once per CTA): keeping them in registers
 // cost five registers per lane for values touched once per ray
 enum { CNT_SEGMENTS = 0, CNT_HITS, CNT_DROPPED, CNT_ESCAPED, CNT_DEPTH, CNT_N };
@@ -148,6 +157,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
 // The shell cull is a conservative fp32 slab test (boxes widened by cull_margin while staging, see odw_api.cu):
 // it only decides which faces get the exact fp64 test, so it cannot change a result.  In fp64 this cull was 45 %
 // of all executed instructions (fmin/fmax on doubles are multi-instruction sequences; FMNMX is one).
+template <int FEAT>
 __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DFace* sfaces, const TraceParams& p,
                                                  const double* s, const double* dn,
                                                  int medium, int seq_index, int skip_shell, double max_len, double& t_out) {
@@ -163,7 +173,7 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"((float)dn[1]));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dn[2]));
   float limf = (float)tmax*1.000002f;                                  // nothing beyond this can still matter
-  const bool seq_off = !p.sequential;
+  const bool seq_off = !(FEAT & FEAT_SEQ) || !p.sequential;
   const bool seq_dead = seq_index >= 128;
   const int sw = (seq_index >> 6) & 1, sb = seq_index & 63;
   const int ns = p.scene.n_shells;
@@ -262,10 +272,11 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
 
 // OpticalGroupProxy.onRayHit -> SimulationResults.addRayHit (optical_group.py:206-209, results_store.py:641-648):
 // warp-aggregated append (one atomic per converged group of lanes) + optional detector binning
+template <int FEAT>
 __device__ __forceinline__ void record_hit(const TraceParams& p, unsigned long long ray, int bounce, int group, int face_id,
                                            const double* P, const double* dir, double power, bool entering, int medium,
                                            unsigned int* s_cnt) {
-  for (int b = 0; b < p.n_binnings; ++b) {
+  for (int b = 0; (FEAT & FEAT_BIN) && b < p.n_binnings; ++b) {
     const DBinning& bn = p.binnings[b];
     if (bn.group != group) continue;
     double w[3] = { P[0]-bn.origin[0], P[1]-bn.origin[1], P[2]-bn.origin[2] };
@@ -365,10 +376,10 @@ struct RayState {
 };
 
 // next ray: Monte-Carlo draw (Philox counter = global ray index) or row i of the explicit list
-template <bool MC>
+template <bool MC, int FEAT>
 __device__ __forceinline__ void fetch_ray(const TraceParams& p, unsigned long long i, const RayState& r) {
   if (MC) {
-    const RayInit q = p.src.kind == ODW_SRC_SURFACE ? init_ray_surface(p.src, p.seed, p.first_ray + i, nullptr, nullptr)
+    const RayInit q = ((FEAT & FEAT_SURFSRC) && p.src.kind == ODW_SRC_SURFACE) ? init_ray_surface(p.src, p.seed, p.first_ray + i, nullptr, nullptr)
                                                      : init_ray_mc(p, p.first_ray + i);
     r.point[0] = q.o[0]; r.point[1] = q.o[1]; r.point[2] = q.o[2];
     r.dn[0] = q.d[0]; r.dn[1] = q.d[1]; r.dn[2] = q.d[2];
@@ -424,7 +435,7 @@ __device__ __noinline__ Vec3 apply_scatter(const DScatter* scatters, int main_i,
 
 // Everything Ray.traceRay does after findNearestIntersection returned (ray.py:105-281): escape segment, or move to the
 // hit, absorption in the traversed medium, normal, onRayHit, the OpticalType rule.  true = the ray has ended.
-template <bool MC>
+template <bool MC, int FEAT>
 __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face_table, const DShell* shells, const DGroup* __restrict__ groups,
                                          int fi, double t, unsigned long long i, const RayState& r, unsigned int* s_cnt) {
   double* point = r.point; double* dn = r.dn;
@@ -438,7 +449,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
   const DGroup& g = groups[fgroup];
   const int prev_medium = r.medium;
   point[0] += t*dn[0]; point[1] += t*dn[1]; point[2] += t*dn[2];                 // ray.py:117
-  if (r.medium >= 0) {                                                           // ray.py:120-125 (multiplicative)
+  if ((FEAT & FEAT_EXT) && r.medium >= 0) {                                      // ray.py:120-125 (multiplicative)
     double L = groups[r.medium].absorption_length;
     if (L == 0) r.power = 0; else if (isfinite(L)) r.power *= exp(-t/L);
   }
@@ -449,14 +460,14 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
   if (g.record || p.record_all) {
     const double ds = MC ? 1.0 : r.dscale;
     const double dir[3] = { dn[0]*ds, dn[1]*ds, dn[2]*ds };
-    record_hit(p, p.first_ray + i, r.n_isect-1, fgroup, f.face_id, point, dir, r.power, entering, prev_medium, s_cnt);
+    record_hit<FEAT>(p, p.first_ray + i, r.n_isect-1, fgroup, f.face_id, point, dir, r.power, entering, prev_medium, s_cnt);
   }
   double o[3] = { dn[0], dn[1], dn[2] };                                         // outgoing direction / its length
   double oscale = MC ? 1.0 : r.dscale;
   switch (g.type) {
     case ODW_OPT_MIRROR: {                                                       // ray.py:146-161
       mirror_dir(dn, nrm, o);                                                    // d - 2(d.n)n is linear in d: the length carries over
-      if (p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {        // ray.py:151-155 (uniform test first: no scene table, no loads)
+      if ((FEAT & FEAT_EXT) && p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {   // ray.py:151-155 (uniform test first: no scene table, no loads)
         const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
                                      r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
         o[0] = q.x; o[1] = q.y; o[2] = q.z; oscale = 1.0;
@@ -469,7 +480,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
       if (entering) { r.medium = fgroup; n2 = g.n; }
       bool tir = snell(dn, n1, n2, nrm, o);
       oscale = 1.0;                                                              // snellsLaw works on the unit direction
-      if (p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {        // ray.py:197-201
+      if ((FEAT & FEAT_EXT) && p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {   // ray.py:197-201
         const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
                                      r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
         o[0] = q.x; o[1] = q.y; o[2] = q.z;
@@ -478,6 +489,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
       break;
     }
     case ODW_OPT_GRATING: {                                                      // ray.py:216-268
+      if (!(FEAT & FEAT_EXT)) break;                                             // never reached: the host picks an instance with FEAT_EXT for scenes with gratings
       if (g.gtype == ODW_GRATING_REFLECTION) {
         if (entering) {
           double n = r.medium >= 0 ? groups[r.medium].n : 1.0;

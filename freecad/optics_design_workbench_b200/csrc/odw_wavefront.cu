@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
     double point[3], dn[3], dscale = 1, power = 0;
     int medium = -1, seq_index = 0, n_isect = 0, skip_shell = -1;
     const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
-    fetch_ray<MC>(p, idx, r);
+    fetch_ray<MC, FEAT_ALL>(p, idx, r);
     if (p.max_isect <= 0) {                                                      // ray.py:96-98 before the first segment
       atomicAdd(&s_cnt[CNT_DEPTH], 1u);
       finish_ray<MC>(p, idx, r, s_cnt);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ Trace
     power = a3.x; dscale = a3.y; i = a4.x;
     medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
     const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
-    bool done = interact<MC>(p, p.scene.faces, nullptr, p.scene.groups, (int)__double_as_longlong(h.y), h.x, i, r, s_cnt);
+    bool done = interact<MC, FEAT_ALL>(p, p.scene.faces, nullptr, p.scene.groups, (int)__double_as_longlong(h.y), h.x, i, r, s_cnt);
     if (!done && n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); done = true; }   // ray.py:96-98
     if (done) finish_ray<MC>(p, i, r, s_cnt);
     survive = !done;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) wf_tail(const __grid_constant__ TracePara
       ++n_isect;
       double t;
       const int fi = find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t);
-      if (interact<MC>(p, p.scene.faces, nullptr, p.scene.groups, fi, t, i, r, s_cnt)) break;
+      if (interact<MC, FEAT_ALL>(p, p.scene.faces, nullptr, p.scene.groups, fi, t, i, r, s_cnt)) break;
     }
     finish_ray<MC>(p, i, r, s_cnt);
   }
