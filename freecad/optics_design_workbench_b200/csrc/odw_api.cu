@@ -40,9 +40,11 @@ struct odw_engine {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks (odw_trace_mc_host)
-  static const int MAX_WAVE_STREAMS = 4;
-  cudaStream_t wave_stream[MAX_WAVE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};   // [0] = stream; launch waves rotate over them, so that the tail of one wave overlaps the head of the next
-  cudaEvent_t ev_fork = nullptr, ev_join[MAX_WAVE_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  static const int MAX_WAVE_STREAMS = 8, DEFAULT_WAVE_STREAMS = 4;
+  cudaStream_t wave_stream[MAX_WAVE_STREAMS] = {};   // [0] = stream; launch waves rotate over them, so that the tail of one wave overlaps the head of the next
+  static const uint64_t MAX_WAVES = 16384;
+  unsigned long long* wave_counters = nullptr;   // [MAX_WAVES] device: next unclaimed ray of each launch wave of the request in flight
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_WAVE_STREAMS] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_trace[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
   Counters* pinned_counters = nullptr;  // [2], page-locked
@@ -151,6 +153,7 @@ extern "C" int odw_engine_create(int device_id, odw_engine** out) {
   CU(cudaEventCreate(&eng->ev1));
   for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&eng->ev_trace[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&eng->ev_copy[i], cudaEventDisableTiming)); }
   CU(cudaHostAlloc((void**)&eng->pinned_counters, 2*sizeof(Counters), cudaHostAllocDefault));
+  CU(cudaMalloc((void**)&eng->wave_counters, odw_engine::MAX_WAVES*sizeof(unsigned long long)));
   *out = eng;
   return ODW_OK;
 }
@@ -163,6 +166,7 @@ extern "C" void odw_engine_destroy(odw_engine* eng) {
   if (eng->ev1) cudaEventDestroy(eng->ev1);
   for (int i = 0; i < 2; ++i) { if (eng->ev_trace[i]) cudaEventDestroy(eng->ev_trace[i]); if (eng->ev_copy[i]) cudaEventDestroy(eng->ev_copy[i]); }
   if (eng->pinned_counters) cudaFreeHost(eng->pinned_counters);
+  if (eng->wave_counters) cudaFree(eng->wave_counters);
   if (eng->copy_stream) cudaStreamDestroy(eng->copy_stream);
   for (int i = 1; i < odw_engine::MAX_WAVE_STREAMS; ++i) { if (eng->wave_stream[i]) cudaStreamDestroy(eng->wave_stream[i]); if (eng->ev_join[i]) cudaEventDestroy(eng->ev_join[i]); }
   if (eng->ev_fork) cudaEventDestroy(eng->ev_fork);
@@ -817,28 +821,31 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
   // persistent grid: a multiple of the SM count, no more blocks than there is work
   const int blocks = eng->sm_count*per_sm;
-  // Waves: a long request is issued as launches of `wave` rays each.  Every launch starts all CTAs in the same phase of
-  // the bounce loop; inside one very long launch the CTAs drift apart, their combined instruction working set no longer
-  // fits the shared instruction cache levels and the kernel slows down by ~35 % (measured on B200, lensesAndMirrors: 1e8
-  // rays in one launch 146 ms, in 48 launches of 2^21 rays 106 ms).  A wave, however, drains unevenly (its last rays keep
-  // a few CTAs busy while the others have exited): back to back on ONE stream that tail cost a third of the time.  The
-  // waves therefore rotate over 4 streams — CTAs of the next waves take the freed slots — and are small (2^18 rays, about
-  // 2 rays per lane of the grid): 59 ms -> 40 ms per 1e8 rays (stream count / wave size sweep in profiles/README.md).
+  // Waves: a long request is issued as launches of `wave` rays each, rotating over 4 streams so that the drain of one
+  // wave (its last rays keep a few warps busy) overlaps the head of the next.  Inside a wave the warps claim rays
+  // dynamically (TraceParams::ray_counter), so a wave has no fixed-assignment imbalance and its size is uncritical from
+  // 2^19 up (wave size x stream count sweep in profiles/README.md: 29.5-29.9 ms per 1e8 rays for 2^19..2^23 rays on 2-8
+  // streams, 30.5 ms for one stream of 2^23-ray waves; with the earlier fixed lane -> ray stride the optimum was 2^18 rays on 4
+  // streams and one stream cost 50 % more).
   uint64_t wave = sc->use_bvh ? (1ull << 24)                   // BVH scenes: big waves amortise the per-bounce host round trip
-                              : (sc->d.n_faces <= 8 ? (1ull << 20) : (1ull << 18));   // trivial scenes are launch-latency bound
+                              : (1ull << 21);
   if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
   wave = std::min<uint64_t>(wave, 1ull << 31);
+  wave = std::max<uint64_t>(wave, (p.n_rays + odw_engine::MAX_WAVES - 1)/odw_engine::MAX_WAVES);   // one claim counter per wave
   // Hit append and counters are atomic, so overlapping waves of one request are safe.
-  int n_streams = odw_engine::MAX_WAVE_STREAMS;
+  int n_streams = odw_engine::DEFAULT_WAVE_STREAMS;
   if (const char* w = getenv("ODW_STREAMS")) n_streams = std::max(1, std::min(odw_engine::MAX_WAVE_STREAMS, atoi(w)));
   if ((sc->use_bvh && sc->wavefront) || p.n_rays <= wave) n_streams = 1;
   if (n_streams > 1) {
     CU(cudaEventRecord(eng->ev_fork, eng->stream));
     for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
   }
+  if (!(sc->use_bvh && sc->wavefront) && p.n_rays > 0)      // before the fork: every wave stream sees its counter zeroed
+    CU(cudaMemsetAsync(eng->wave_counters, 0, ((p.n_rays + wave - 1)/wave)*sizeof(unsigned long long), eng->stream));
   uint64_t wave_index = 0;
   for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
+    q.ray_counter = eng->wave_counters + wave_index;
     q.n_rays = std::min<uint64_t>(wave, p.n_rays - off);
     q.first_ray = p.first_ray + off;
     if (!mc) {

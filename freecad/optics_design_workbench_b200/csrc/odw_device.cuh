@@ -127,6 +127,7 @@ struct TraceParams {
   int32_t* out_nseg; double* out_final_point; double* out_final_power; int32_t* out_final_medium;
   unsigned long long ignore_mask[4];
   unsigned long long seed, first_ray, n_rays;
+  unsigned long long* ray_counter;   // next unclaimed ray of this launch (zeroed by the host): warps claim rays in chunks, see trace_kernel
   double max_len, tol, power_tol, wavelength;
   int32_t max_isect, sequential, record_all, store_hits;
   float cull_margin;                 // widening of the fp32 shell / BVH boxes, see odw_api.cu cull_margin()

@@ -14,6 +14,9 @@
 #ifndef ODW_MIN_BLOCKS
 #define ODW_MIN_BLOCKS 3          // 3 CTAs x 8 warps per SM (80 registers): the kernel is latency-bound, 24 warps beat 16 despite spills
 #endif
+#ifndef ODW_RAY_CHUNK
+#define ODW_RAY_CHUNK 32        // rays a warp claims per atomic
+#endif
 #ifndef ODW_THREADS
 #define ODW_THREADS 256          // threads per CTA of the trace kernel
 #endif
@@ -53,30 +56,49 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   unsigned long long t_start = 0, c_start = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start)); c_start = clock64(); }
   const DGroup* __restrict__ groups = p.scene.groups;
-  const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
-  // Persistent lanes: a lane whose ray has ended fetches its next ray (index + stride) and initialises it; then
-  // every lane with a live ray does ONE bounce.  The warp re-converges once per bounce (the __any_sync below),
-  // so the expensive part (find nearest intersection) always runs with all live lanes together, no matter how
-  // differently long the rays of a warp are.  Without this the lanes of a warp drift apart over the ~1e3 rays a
-  // lane traces in a 1e8-ray launch and SIMT efficiency collapses.
+  // Persistent lanes: a lane whose ray has ended takes its next ray and initialises it; then every lane with a live ray
+  // does ONE bounce.  The warp re-converges once per bounce (the __any_sync below), so the expensive part (find nearest
+  // intersection) always runs with all live lanes together, no matter how differently long the rays of a warp are.
+  // Rays are claimed dynamically: a warp takes ODW_RAY_CHUNK consecutive ray numbers from the launch's counter (one
+  // atomic per chunk) and hands them to its lanes as they become free.  With a fixed lane -> ray stride a 2^18-ray launch
+  // gave each lane two or three rays of one to seven segments each, and the launch lasted as long as its unluckiest lane.
+  // (Monte-Carlo rays are a function of their number alone, so who traces which ray does not change a result.)
   // (Measured and rejected for the BVH path, where only ~6 of 32 lanes are active on hugeArray because traversal lengths
   // differ wildly: alternating "traversal step" / "interaction" phases gated by the number of lanes still traversing.
   // The interaction + ray-initialisation code then runs once per few traversal steps instead of once per bounce and
   // costs more than the idle lanes it saves: 7.5e8 vs 9.3e8 segments/s.)
-  // i = index of the lane's current ray; a lane steps through the launch by the grid size
-  unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const unsigned int lane = threadIdx.x & 31u;
+  unsigned long long pool_next = 0;          // warp-uniform: next ray number of the warp's chunk
+  unsigned int pool_left = 0;                // warp-uniform: rays left in it
+  bool exhausted = false;                    // warp-uniform: the launch has no unclaimed rays
+  unsigned long long i = 0;                  // number of the lane's current ray inside the launch
   double point[3] = {0, 0, 0}, dn[3] = {0, 0, 1}, dscale = 1, power = 0;
   int medium = -1, seq_index = 0, n_isect = 0, skip_shell = -1;
   const RayState r = { point, dn, dscale, power, medium, seq_index, n_isect, skip_shell };
   bool alive = false;
   for (;;) {
-    if (!alive && i < p.n_rays) { fetch_ray<MC, FEAT>(p, i, r); alive = true; }
+    const unsigned int need = __ballot_sync(0xffffffffu, !alive);
+    if (need && !exhausted) {
+      if (pool_left == 0) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(p.ray_counter, (unsigned long long)ODW_RAY_CHUNK);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= p.n_rays) exhausted = true;
+        else { pool_next = b; pool_left = (unsigned int)min((unsigned long long)ODW_RAY_CHUNK, p.n_rays - b); }
+      }
+      if (pool_left) {
+        const unsigned int k = __popc(need & ((1u << lane) - 1u));
+        if (!alive && k < pool_left) { i = pool_next + k; fetch_ray<MC, FEAT>(p, i, r); alive = true; }
+        const unsigned int taken = min((unsigned int)__popc(need), pool_left);
+        pool_next += taken; pool_left -= taken;
+      }
+    }
 #if ODW_BLOCK_SYNC
     // block-wide re-convergence: all warps of a CTA stay in the same phase of the loop, so the CTA's instruction
     // working set is one phase (init / intersect / interact) instead of all of them at once
-    if (!__syncthreads_or(alive)) break;
+    if (!__syncthreads_or(alive || !exhausted)) break;
 #else
-    if (!__any_sync(0xffffffffu, alive)) break;
+    if (!__any_sync(0xffffffffu, alive)) { if (exhausted) break; else continue; }
 #endif
     if (alive) {
       bool done;
@@ -88,7 +110,7 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
                            : find_nearest_smem<FEAT>(sshells, sfaces, p, point, dn, medium, seq_index, skip_shell, p.max_len, t);
         done = interact<MC, FEAT>(p, BVH ? p.scene.faces : sfaces, BVH ? nullptr : sshells, groups, fi, t, i, r, s_cnt);
       }
-      if (done) { finish_ray<MC>(p, i, r, s_cnt); alive = false; i += stride; }
+      if (done) { finish_ray<MC>(p, i, r, s_cnt); alive = false; }
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
