@@ -16,6 +16,7 @@
 //
 // HBM traffic per segment is the wavefront figure of SURVEY.md §8d (ray state read + written once per bounce).
 #include "odw_trace.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 // ---- ray pool ------------------------------------------------------------------------------
 struct WfPool {
@@ -24,7 +25,37 @@ struct WfPool {
   double2* a2;       // (dy, dz)          d = unit direction
   double2* a3;       // (power, dscale)
   ulonglong2* a4;    // (ray number inside the launch, medium | seq_index << 32)
+  unsigned int* key; // coherence key of the ray (origin cell, direction), see ray_sort_key
+  float bound;       // origins are binned on a 16^3 grid over [-bound, bound]^3
 };
+
+// Coherence key: rays that start in the same region and point the same way walk the same BVH nodes, so a warp of
+// neighbours in key order stays converged.  12 bits origin cell (16^3 grid, Morton order) above 20 bits direction (octahedral map,
+// 1024 x 1024, Morton order: a narrow beam from one point still spreads over thousands of direction cells).  Measured on hugeArray with the rays of the FIRST bounce sorted by direction on the host:
+// 1.98e9 -> 3.11e9 segments/s (tools/gpu_coherence_probe.py).
+#define ODW_SORT_KEY_BITS 32
+__device__ __forceinline__ unsigned int spread2(unsigned int x) {     // 10 bits -> every second bit
+  x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ unsigned int spread3(unsigned int x) {     // 4 bits -> every third bit
+  x = (x | (x << 4)) & 0x0c3u; x = (x | (x << 2)) & 0x249u;
+  return x;
+}
+__device__ __forceinline__ unsigned int ray_sort_key(const double* point, const double* dn, float bound) {
+  const float sc = 8.0f/bound;
+  const int cx = min(15, max(0, (int)(((float)point[0] + bound)*sc)));
+  const int cy = min(15, max(0, (int)(((float)point[1] + bound)*sc)));
+  const int cz = min(15, max(0, (int)(((float)point[2] + bound)*sc)));
+  const float dx = (float)dn[0], dy = (float)dn[1], dz = (float)dn[2];
+  const float l1 = 1.0f/(fabsf(dx) + fabsf(dy) + fabsf(dz) + 1e-30f);
+  float px = dx*l1, py = dy*l1;
+  if (dz < 0) { const float qx = (1.0f - fabsf(py))*(px >= 0 ? 1.0f : -1.0f), qy = (1.0f - fabsf(px))*(py >= 0 ? 1.0f : -1.0f); px = qx; py = qy; }
+  const unsigned int ux = (unsigned int)min(1023, max(0, (int)((px + 1.0f)*512.0f)));
+  const unsigned int uy = (unsigned int)min(1023, max(0, (int)((py + 1.0f)*512.0f)));
+  const unsigned int cell = spread3((unsigned int)cx) | (spread3((unsigned int)cy) << 1) | (spread3((unsigned int)cz) << 2);
+  return (cell << 20) | spread2(ux) | (spread2(uy) << 1);
+}
 
 struct WfRay {
   double point[3], dn[3], power, dscale;
@@ -39,6 +70,7 @@ __device__ __forceinline__ void pool_store(const WfPool& pl, unsigned int slot, 
   pl.a2[slot] = make_double2(dn[1], dn[2]);
   pl.a3[slot] = make_double2(power, dscale);
   pl.a4[slot] = make_ulonglong2(i, (unsigned long long)(unsigned int)medium | ((unsigned long long)(unsigned int)seq_index << 32));
+  pl.key[slot] = ray_sort_key(point, dn, pl.bound);
 }
 
 // ---- resumable BVH traversal, "while-while" form --------------------------------------------------------------
@@ -156,7 +188,7 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 #define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
 #endif
 __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
-                                                      unsigned int n, unsigned int* fetch_counter) {
+                                                      unsigned int n, unsigned int* fetch_counter, const unsigned int* __restrict__ order) {
   const unsigned int lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;
   unsigned int slot = 0;
@@ -175,6 +207,7 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
       if (!have) {
         slot = base + __popc(need & ((1u << lane) - 1u));
         if (slot < n) {
+          if (order) slot = __ldg(order + slot);            // k-th ray in coherence order; results stay in pool order
           const double2 a0 = pool.a0[slot], a1 = pool.a1[slot], a2 = pool.a2[slot];
           const ulonglong2 a4 = pool.a4[slot];
           s[0] = a0.x; s[1] = a0.y; s[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
@@ -207,7 +240,8 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
 // surface interaction of every ray of pool_in with its hit; survivors are appended to pool_out
 template <bool MC>
 __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ TraceParams p, WfPool pool_in, const double2* __restrict__ hits,
-                                                   WfPool pool_out, unsigned int n, unsigned int* n_next, int bounce) {
+                                                   WfPool pool_out, unsigned int n, unsigned int* n_next, int bounce,
+                                                   const unsigned int* __restrict__ order) {
   __shared__ unsigned int s_cnt[CNT_N];
   if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -217,9 +251,11 @@ __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ Trace
   int medium = -1, seq_index = 0, n_isect = bounce + 1, skip_shell = -1;   // every ray of this wave has done `bounce` segments before
   unsigned long long i = 0;
   if (idx < n) {
-    const double2 a0 = pool_in.a0[idx], a1 = pool_in.a1[idx], a2 = pool_in.a2[idx], a3 = pool_in.a3[idx];
-    const ulonglong2 a4 = pool_in.a4[idx];
-    const double2 h = hits[idx];
+    // in coherence order when there is one: the survivors then land in the next pool roughly ordered already
+    const unsigned int src = order ? __ldg(order + idx) : idx;
+    const double2 a0 = pool_in.a0[src], a1 = pool_in.a1[src], a2 = pool_in.a2[src], a3 = pool_in.a3[src];
+    const ulonglong2 a4 = pool_in.a4[src];
+    const double2 h = hits[src];
     point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
     power = a3.x; dscale = a3.y; i = a4.x;
     medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
@@ -274,39 +310,41 @@ __global__ void __launch_bounds__(256) wf_tail(const __grid_constant__ TracePara
 }
 
 // ---- launch helpers used by odw_api.cu ---------------------------------------------------------
-extern "C" size_t odw_wf_pool_bytes_per_ray(void) { return 4*sizeof(double2) + sizeof(ulonglong2); }
+extern "C" size_t odw_wf_pool_bytes_per_ray(void) { return 4*sizeof(double2) + sizeof(ulonglong2) + sizeof(unsigned int); }
 
-static WfPool make_pool(void* base, size_t cap) {
+static WfPool make_pool(void* base, size_t cap, float bound = 1.0f) {
   WfPool pl;
   char* b = static_cast<char*>(base);
   pl.a0 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
   pl.a1 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
   pl.a2 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
   pl.a3 = reinterpret_cast<double2*>(b); b += cap*sizeof(double2);
-  pl.a4 = reinterpret_cast<ulonglong2*>(b);
+  pl.a4 = reinterpret_cast<ulonglong2*>(b); b += cap*sizeof(ulonglong2);
+  pl.key = reinterpret_cast<unsigned int*>(b);
+  pl.bound = bound;
   return pl;
 }
 
-extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, cudaStream_t st) {
-  const WfPool pl = make_pool(pool, cap);
+extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, float bound, unsigned int n, cudaStream_t st) {
+  const WfPool pl = make_pool(pool, cap, bound);
   const unsigned int blocks = (n + 255u)/256u;
   if (mc) wf_generate<true><<<blocks, 256, 0, st>>>(*p, pl, n); else wf_generate<false><<<blocks, 256, 0, st>>>(*p, pl, n);
   return cudaGetLastError();
 }
 
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
-                                       unsigned int* fetch_counter, int blocks, cudaStream_t st) {
+                                       unsigned int* fetch_counter, const unsigned int* order, int blocks, cudaStream_t st) {
   const unsigned int want = (n + 255u)/256u;
-  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter);
+  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter, order);
   return cudaGetLastError();
 }
 
-extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap,
-                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st) {
+extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap, float bound,
+                                       unsigned int n, unsigned int* n_next, int bounce, const unsigned int* order, cudaStream_t st) {
   const unsigned int blocks = (n + 255u)/256u;
-  const WfPool pi = make_pool(pool_in, cap), po = make_pool(pool_out, cap);
-  if (mc) wf_interact<true><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
-  else wf_interact<false><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
+  const WfPool pi = make_pool(pool_in, cap, bound), po = make_pool(pool_out, cap, bound);
+  if (mc) wf_interact<true><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce, order);
+  else wf_interact<false><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce, order);
   return cudaGetLastError();
 }
 
@@ -315,6 +353,22 @@ extern "C" cudaError_t odw_wf_tail(const TraceParams* p, bool mc, void* pool, si
   if (mc) wf_tail<true><<<blocks, 256, 0, st>>>(*p, make_pool(pool, cap), n, bounce);
   else wf_tail<false><<<blocks, 256, 0, st>>>(*p, make_pool(pool, cap), n, bounce);
   return cudaGetLastError();
+}
+
+// coherence order of the first n rays of a pool: order[k] = pool slot of the k-th ray by key (radix sort of (key, slot) pairs)
+__global__ void wf_iota(unsigned int* v, unsigned int n) {
+  const unsigned int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+extern "C" cudaError_t odw_wf_iota(unsigned int* v, unsigned int n, cudaStream_t st) {
+  wf_iota<<<(n + 255u)/256u, 256, 0, st>>>(v, n);
+  return cudaGetLastError();
+}
+// temp == nullptr: size query
+extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, size_t cap, unsigned int* keys_out, const unsigned int* iota,
+                                   unsigned int* order, unsigned int n, cudaStream_t st) {
+  const WfPool pl = make_pool(pool, cap);
+  return cub::DeviceRadixSort::SortPairs(temp, *temp_bytes, (const unsigned int*)pl.key, keys_out, iota, order, (int)n, 0, ODW_SORT_KEY_BITS, st);
 }
 
 extern "C" int odw_wf_traverse_occupancy(void) {
