@@ -80,13 +80,12 @@ __device__ __forceinline__ void pool_store(const WfPool& pl, unsigned int slot, 
 // leaf or is done, then all lanes holding a leaf run the exact fp64 face tests together.  Testing a leaf the moment it
 // is found (as find_nearest_bvh does) left 7 of 32 lanes active: every lane sat in a different part of the step.
 #define TRAV_DONE (-1)
-struct BvhTrav {
-  NearestHit h;
+struct BvhTrav {       // scalars only: the two stack arrays are separate locals of the kernel, so that the dynamic indexing
+  NearestHit h;        // they need does not drag cur / sp / limf into local memory with them
   float sx, sy, sz, ix, iy, iz, limf;
   int cur, sp;
-  int stack_ref[ODW_BVH_STACK];
-  float stack_t[ODW_BVH_STACK];
 };
+struct BvhStack { int* ref; float* t; };
 
 __device__ __forceinline__ int leaf_ref(int first, int count) { return -2 - ((first << 4) | count); }
 
@@ -100,16 +99,16 @@ __device__ __forceinline__ void bvh_begin(BvhTrav& tr, const TraceParams& p, con
 }
 
 // next stacked item that can still matter
-__device__ __forceinline__ int bvh_pop(BvhTrav& tr) {
+__device__ __forceinline__ int bvh_pop(BvhTrav& tr, const BvhStack& st) {
   while (tr.sp > 0) {
     --tr.sp;
-    if (tr.stack_t[tr.sp] <= tr.limf) return tr.stack_ref[tr.sp];
+    if (st.t[tr.sp] <= tr.limf) return st.ref[tr.sp];
   }
   return TRAV_DONE;
 }
 
 // cur is an inner node: test both children, go to the nearer one, stack the other
-__device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const TraceParams& p) {
+__device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const BvhStack& st, const TraceParams& p) {
   const float sx = tr.sx, sy = tr.sy, sz = tr.sz, ix = tr.ix, iy = tr.iy, iz = tr.iz;
   const float4* q = reinterpret_cast<const float4*>(p.scene.bvh + tr.cur);
   const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
@@ -132,15 +131,15 @@ __device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const TraceParams& p
   const int r0 = d.z > 0 ? leaf_ref(d.x, d.z) : d.x, r1 = d.w > 0 ? leaf_ref(d.y, d.w) : d.y;
   if (hit0 && hit1) {
     const bool first0 = n0 <= n1;
-    if (tr.sp < ODW_BVH_STACK) { tr.stack_ref[tr.sp] = first0 ? r1 : r0; tr.stack_t[tr.sp] = first0 ? n1 : n0; ++tr.sp; }
+    if (tr.sp < ODW_BVH_STACK) { st.ref[tr.sp] = first0 ? r1 : r0; st.t[tr.sp] = first0 ? n1 : n0; ++tr.sp; }
     tr.cur = first0 ? r0 : r1;
   } else if (hit0) tr.cur = r0;
   else if (hit1) tr.cur = r1;
-  else tr.cur = bvh_pop(tr);
+  else tr.cur = bvh_pop(tr, st);
 }
 
 // cur is a leaf: exact fp64 tests of its faces
-__device__ __forceinline__ void bvh_leaf_step(BvhTrav& tr, const TraceParams& p, const double* s, const double* dn, int medium, int seq_index) {
+__device__ __forceinline__ void bvh_leaf_step(BvhTrav& tr, const BvhStack& st, const TraceParams& p, const double* s, const double* dn, int medium, int seq_index) {
   const int packed = -2 - tr.cur, first = packed >> 4, count = packed & 15;
   const double tmax = p.max_len + p.tol;
   for (int k = 0; k < count; ++k) {
@@ -148,7 +147,7 @@ __device__ __forceinline__ void bvh_leaf_step(BvhTrav& tr, const TraceParams& p,
     test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, tr.h);
   }
   tr.limf = (float)tr.h.lim*1.000002f;
-  tr.cur = bvh_pop(tr);
+  tr.cur = bvh_pop(tr, st);
 }
 
 __device__ __forceinline__ void flush_counters(const TraceParams& p, const unsigned int* s_cnt) {
@@ -196,6 +195,8 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
   int medium = -1, seq_index = 0;
   BvhTrav tr;
   tr.cur = TRAV_DONE; tr.sp = 0;
+  int stack_ref[ODW_BVH_STACK]; float stack_t[ODW_BVH_STACK];
+  const BvhStack st = { stack_ref, stack_t };
   for (;;) {
     const unsigned int need = __ballot_sync(0xffffffffu, !have);
     if (need && !exhausted) {
@@ -221,10 +222,10 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
     if (!__any_sync(0xffffffffu, have)) break;
     // descend: every lane walks inner nodes until it holds a leaf or has finished
     while (__any_sync(0xffffffffu, have && tr.cur >= 0)) {
-      if (have && tr.cur >= 0) bvh_inner_step(tr, p);
+      if (have && tr.cur >= 0) bvh_inner_step(tr, st, p);
     }
     // leaves: exact face tests, all lanes that hold one together
-    if (have && tr.cur < TRAV_DONE) bvh_leaf_step(tr, p, s, dn, medium, seq_index);
+    if (have && tr.cur < TRAV_DONE) bvh_leaf_step(tr, st, p, s, dn, medium, seq_index);
     if (have && tr.cur == TRAV_DONE) {
       const double tol = p.tol;
       double t = 0; int fi = -1;
