@@ -22,9 +22,9 @@ extern "C" int odw_trace_threads(void);
 extern "C" size_t odw_wf_pool_bytes_per_ray(void);
 extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, float bound, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
-                                       unsigned int* fetch_counter, const unsigned int* order, int blocks, cudaStream_t st);
+                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int blocks, cudaStream_t st);
 extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap, float bound,
-                                       unsigned int n, unsigned int* n_next, int bounce, const unsigned int* order, cudaStream_t st);
+                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st);
 extern "C" cudaError_t odw_wf_iota(unsigned int* v, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, size_t cap, unsigned int* keys_out, const unsigned int* iota,
                                    unsigned int* order, unsigned int n, cudaStream_t st);
@@ -781,10 +781,10 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
   const unsigned int n0 = (unsigned int)q.n_rays;
   if (n0 == 0) return ODW_OK;
   const size_t cap = n0;
-  void *pool_a = nullptr, *pool_b = nullptr, *hits = nullptr, *sort_temp = nullptr; unsigned int* ctr = nullptr;
+  void *pool_a = nullptr, *pool_b = nullptr, *pool_c = nullptr, *hits = nullptr, *sort_temp = nullptr; unsigned int* ctr = nullptr;
   unsigned int *keys_out = nullptr, *iota = nullptr, *order = nullptr;
   int rc;
-  auto cleanup = [&]() { eng->release(pool_a); eng->release(pool_b); eng->release(hits); eng->release(ctr);
+  auto cleanup = [&]() { eng->release(pool_a); eng->release(pool_b); eng->release(pool_c); eng->release(hits); eng->release(ctr);
                          eng->release(sort_temp); eng->release(keys_out); eng->release(iota); eng->release(order); };
   if ((rc = eng->alloc(&pool_a, cap*odw_wf_pool_bytes_per_ray())) || (rc = eng->alloc(&pool_b, cap*odw_wf_pool_bytes_per_ray())) ||
       (rc = eng->alloc(&hits, cap*16)) || (rc = eng->alloc((void**)&ctr, 16))) { cleanup(); return rc; }
@@ -801,7 +801,8 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
     cudaError_t es = odw_wf_sort(nullptr, &temp_bytes, pool_a, cap, nullptr, nullptr, nullptr, n0, eng->stream);
     if (es != cudaSuccess) { cleanup(); return fail(ODW_ECUDA, std::string("wavefront sort: ") + cudaGetErrorString(es)); }
     if ((rc = eng->alloc(&sort_temp, std::max<size_t>(temp_bytes, 16))) || (rc = eng->alloc((void**)&keys_out, cap*4)) ||
-        (rc = eng->alloc((void**)&iota, cap*4)) || (rc = eng->alloc((void**)&order, cap*4))) { cleanup(); return rc; }
+        (rc = eng->alloc((void**)&iota, cap*4)) || (rc = eng->alloc((void**)&order, cap*4)) ||
+        (rc = eng->alloc(&pool_c, cap*odw_wf_pool_bytes_per_ray()))) { cleanup(); return rc; }
     if ((es = odw_wf_iota(iota, n0, eng->stream)) != cudaSuccess) { cleanup(); return fail(ODW_ECUDA, std::string("wavefront sort: ") + cudaGetErrorString(es)); }
   } else sort_bounces = 0;
   unsigned int tail = 8192;
@@ -818,8 +819,9 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
     if ((e = cudaMemsetAsync(ctr, 0, 16, st)) != cudaSuccess) break;                    // ctr[0] = survivors, ctr[1] = fetch counter
     const bool sorted = bounce < sort_bounces && n >= sort_min;
     if (sorted) { if ((e = odw_wf_sort(sort_temp, &temp_bytes, cur, cap, keys_out, iota, order, n, st)) != cudaSuccess) break; }
-    if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, blocks, st)) != cudaSuccess) break;
-    if ((e = odw_wf_interact(&q, mc, cur, hits, nxt, cap, bound, n, ctr, bounce, sorted ? order : nullptr, st)) != cudaSuccess) break;
+    // sorted: the traversal moves every ray to its place in the ordered pool (pool_c) and the interaction reads that one
+    if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, pool_c, blocks, st)) != cudaSuccess) break;
+    if ((e = odw_wf_interact(&q, mc, sorted ? pool_c : cur, hits, nxt, cap, bound, n, ctr, bounce, st)) != cudaSuccess) break;
     if (launches) *launches += 2;
     if ((e = cudaMemcpyAsync(host_n, ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;

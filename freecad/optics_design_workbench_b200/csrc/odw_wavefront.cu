@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 #define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
 #endif
 __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
-                                                      unsigned int n, unsigned int* fetch_counter, const unsigned int* __restrict__ order) {
+                                                      unsigned int n, unsigned int* fetch_counter, const unsigned int* __restrict__ order,
+                                                      WfPool ordered) {
   const unsigned int lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;
   unsigned int slot = 0;
@@ -208,9 +209,14 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
       if (!have) {
         slot = base + __popc(need & ((1u << lane) - 1u));
         if (slot < n) {
-          if (order) slot = __ldg(order + slot);            // k-th ray in coherence order; results stay in pool order
-          const double2 a0 = pool.a0[slot], a1 = pool.a1[slot], a2 = pool.a2[slot];
-          const ulonglong2 a4 = pool.a4[slot];
+          const unsigned int src = order ? __ldg(order + slot) : slot;      // the k-th ray in coherence order
+          const double2 a0 = pool.a0[src], a1 = pool.a1[src], a2 = pool.a2[src];
+          const ulonglong2 a4 = pool.a4[src];
+          if (order) {
+            // the ray moves to slot k of the ordered pool (neighbouring lanes hold neighbouring k: coalesced stores), where the
+            // interaction kernel finds it next to its result without chasing the order a second time
+            ordered.a0[slot] = a0; ordered.a1[slot] = a1; ordered.a2[slot] = a2; ordered.a3[slot] = pool.a3[src]; ordered.a4[slot] = a4;
+          }
           s[0] = a0.x; s[1] = a0.y; s[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
           medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
           bvh_begin(tr, p, s, dn);
@@ -241,8 +247,7 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
 // surface interaction of every ray of pool_in with its hit; survivors are appended to pool_out
 template <bool MC>
 __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ TraceParams p, WfPool pool_in, const double2* __restrict__ hits,
-                                                   WfPool pool_out, unsigned int n, unsigned int* n_next, int bounce,
-                                                   const unsigned int* __restrict__ order) {
+                                                   WfPool pool_out, unsigned int n, unsigned int* n_next, int bounce) {
   __shared__ unsigned int s_cnt[CNT_N];
   if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -252,11 +257,9 @@ __global__ void __launch_bounds__(256) wf_interact(const __grid_constant__ Trace
   int medium = -1, seq_index = 0, n_isect = bounce + 1, skip_shell = -1;   // every ray of this wave has done `bounce` segments before
   unsigned long long i = 0;
   if (idx < n) {
-    // in coherence order when there is one: the survivors then land in the next pool roughly ordered already
-    const unsigned int src = order ? __ldg(order + idx) : idx;
-    const double2 a0 = pool_in.a0[src], a1 = pool_in.a1[src], a2 = pool_in.a2[src], a3 = pool_in.a3[src];
-    const ulonglong2 a4 = pool_in.a4[src];
-    const double2 h = hits[src];
+    const double2 a0 = pool_in.a0[idx], a1 = pool_in.a1[idx], a2 = pool_in.a2[idx], a3 = pool_in.a3[idx];
+    const ulonglong2 a4 = pool_in.a4[idx];
+    const double2 h = hits[idx];
     point[0] = a0.x; point[1] = a0.y; point[2] = a1.x; dn[0] = a1.y; dn[1] = a2.x; dn[2] = a2.y;
     power = a3.x; dscale = a3.y; i = a4.x;
     medium = (int)(unsigned int)a4.y; seq_index = (int)(unsigned int)(a4.y >> 32);
@@ -334,18 +337,19 @@ extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool
 }
 
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
-                                       unsigned int* fetch_counter, const unsigned int* order, int blocks, cudaStream_t st) {
+                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int blocks, cudaStream_t st) {
   const unsigned int want = (n + 255u)/256u;
-  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter, order);
+  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter,
+                                                                                          order, make_pool(order ? pool_ordered : pool, cap));
   return cudaGetLastError();
 }
 
 extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap, float bound,
-                                       unsigned int n, unsigned int* n_next, int bounce, const unsigned int* order, cudaStream_t st) {
+                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st) {
   const unsigned int blocks = (n + 255u)/256u;
   const WfPool pi = make_pool(pool_in, cap, bound), po = make_pool(pool_out, cap, bound);
-  if (mc) wf_interact<true><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce, order);
-  else wf_interact<false><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce, order);
+  if (mc) wf_interact<true><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
+  else wf_interact<false><<<blocks, 256, 0, st>>>(*p, pi, static_cast<const double2*>(hits), po, n, n_next, bounce);
   return cudaGetLastError();
 }
 
