@@ -22,7 +22,7 @@ extern "C" int odw_trace_threads(void);
 extern "C" size_t odw_wf_pool_bytes_per_ray(void);
 extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool, size_t cap, float bound, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
-                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int blocks, cudaStream_t st);
+                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int need, int blocks, cudaStream_t st);
 extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap, float bound,
                                        unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st);
 extern "C" cudaError_t odw_wf_iota(unsigned int* v, unsigned int n, cudaStream_t st);
@@ -93,7 +93,7 @@ struct odw_scene {
   size_t smem = 0;
   int n_groups = 0;
   double extent = 0;                    // max |coordinate| over all face boxes
-  bool ext_optics = false;              // a grating, a stochastic surface model or a finite absorption length somewhere (FEAT_EXT)
+  bool ext_optics = false;              // a grating, a stochastic surface model, a finite absorption length or an even-asphere face somewhere (FEAT_EXT)
   std::vector<BvhNode2> bvh_host;       // un-widened device nodes (boxes rounded outward)
   std::vector<BvhNode2> bvh_staging;    // widened copy being uploaded
   BvhNode2* bvh_dev = nullptr;
@@ -399,13 +399,17 @@ bool shell_is_convex(const odw_scene_desc* sd, int face_first, int face_count) {
 // (emitting faces of a surface source are only evaluated / trim-tested, never intersected: no fast paths there).
 static void fill_dface(const odw_face& f, const odw_trimseg* segs, bool fast_paths, DFace& d) {
     memset(&d, 0, sizeof d);
-    for (int k = 0; k < 3; ++k) { d.o[k] = f.origin[k]; d.x[k] = f.xdir[k]; d.y[k] = f.ydir[k]; d.z[k] = f.zdir[k];
-                                  d.bmin[k] = f.aabb_min[k]; d.bmax[k] = f.aabb_max[k];
-                                  }
+    for (int k = 0; k < 3; ++k) { d.o[k] = f.origin[k]; d.x[k] = f.xdir[k]; d.y[k] = f.ydir[k]; d.z[k] = f.zdir[k]; }
     d.p0 = f.p0; d.p1 = f.p1;
     d.umin = f.uv_min[0]; d.umax = f.uv_max[0]; d.vmin = f.uv_min[1]; d.vmax = f.uv_max[1];
     d.kind = f.kind; d.trim = f.trim_kind; d.nsign = f.nsign; d.group = f.group;
     d.seg_first = f.seg_first; d.seg_count = f.seg_count; d.face_id = f.face_id;
+    if (f.kind == ODW_SURF_CONICOID && f.seg_count > 0 && segs && segs[f.seg_first].kind == ODW_SEG_ASPHERE) {
+      // the auxiliary record moves into the face record; the kernels see only boundary pieces in the segment range
+      for (int k = 0; k < 5; ++k) d.aux[k] = segs[f.seg_first].a[k];
+      d.aux[5] = 1.0;
+      d.seg_first = f.seg_first + 1; d.seg_count = f.seg_count - 1;
+    }
     d.flags = (f.kind != ODW_SURF_PLANE && std::fabs((f.uv_max[0] - f.uv_min[0]) - ODW_TWO_PI) < 1e-9) ? DFACE_FULL_U : 0;
     {
       auto dot = [](const double* a, const double* b) { return a[0]*b[0] + a[1]*b[1] + a[2]*b[2]; };
@@ -446,8 +450,12 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     if (f.kind < ODW_SURF_PLANE || f.kind > ODW_SURF_CONICOID) return fail(ODW_EINVAL, "face " + std::to_string(i) + ": unknown surface kind");
     if (f.kind == ODW_SURF_CONICOID && !(f.p0 != 0 && std::isfinite(f.p0) && std::isfinite(f.p1)))
       return fail(ODW_EINVAL, "face " + std::to_string(i) + ": a conicoid needs a finite non-zero vertex curvature (p0) and a finite conic constant (p1)");
-    if (f.trim_kind == ODW_TRIM_LOOPS && (f.seg_first < 0 || f.seg_first + f.seg_count > sd->n_segs))
+    if ((f.trim_kind == ODW_TRIM_LOOPS || (f.kind == ODW_SURF_CONICOID && f.seg_count > 0)) &&
+        (f.seg_first < 0 || f.seg_count < 0 || f.seg_first + f.seg_count > sd->n_segs))
       return fail(ODW_EINVAL, "face " + std::to_string(i) + ": trim segment range out of bounds");
+    for (int k = 0; k < ((f.trim_kind == ODW_TRIM_LOOPS || f.kind == ODW_SURF_CONICOID) ? f.seg_count : 0); ++k)
+      if (sd->segs[f.seg_first + k].kind == ODW_SEG_ASPHERE && (k != 0 || f.kind != ODW_SURF_CONICOID))
+        return fail(ODW_EINVAL, "face " + std::to_string(i) + ": an asphere record must be the first segment of a conicoid face");
     DFace& d = faces[(size_t)i];
     fill_dface(f, sd->segs, true, d);
     for (int k = 0; k < 3; ++k) { boxes[(size_t)i].lo[k] = f.aabb_min[k]; boxes[(size_t)i].hi[k] = f.aabb_max[k]; }
@@ -511,6 +519,7 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   }
   odw_scene* sc = new odw_scene();
   sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
+  for (const DFace& f : faces) if (f.aux[5] != 0.0) sc->ext_optics = true;      // even-asphere faces need the FEAT_EXT instances
   for (const DGroup& g : groups)
     if (g.type == ODW_OPT_GRATING || g.scat_main >= 0 || g.scat_modify >= 0 || std::isfinite(g.absorption_length)) sc->ext_optics = true;
   int rc;
@@ -777,7 +786,7 @@ static int set_ignore(TraceParams& p, const int32_t* ign, int n) {
 // One wave of the wavefront formulation (BVH scenes, see odw_wavefront.cu): generate, then per bounce traverse + interact
 // with the survivor count read back after every bounce (it sizes the next launches and ends the loop); once fewer than
 // `tail` rays are left they finish in one launch.
-static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, float bound, uint64_t* launches) {
+static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, float bound, int need, uint64_t* launches) {
   const unsigned int n0 = (unsigned int)q.n_rays;
   if (n0 == 0) return ODW_OK;
   const size_t cap = n0;
@@ -820,7 +829,7 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
     const bool sorted = bounce < sort_bounces && n >= sort_min;
     if (sorted) { if ((e = odw_wf_sort(sort_temp, &temp_bytes, cur, cap, keys_out, iota, order, n, st)) != cudaSuccess) break; }
     // sorted: the traversal moves every ray to its place in the ordered pool (pool_c) and the interaction reads that one
-    if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, pool_c, blocks, st)) != cudaSuccess) break;
+    if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, pool_c, need, blocks, st)) != cudaSuccess) break;
     if ((e = odw_wf_interact(&q, mc, sorted ? pool_c : cur, hits, nxt, cap, bound, n, ctr, bounce, st)) != cudaSuccess) break;
     if (launches) *launches += 2;
     if ((e = cudaMemcpyAsync(host_n, ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
@@ -882,7 +891,7 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
       if (p.out_final_medium) q.out_final_medium = p.out_final_medium + off;
     }
     if (sc->use_bvh && sc->wavefront) {
-      int rc = run_wavefront_wave(eng, q, mc, (float)std::max(1e-3, std::max(sc->extent, (double)q.origin_bound)), launches);
+      int rc = run_wavefront_wave(eng, q, mc, (float)std::max(1e-3, std::max(sc->extent, (double)q.origin_bound)), need, launches);
       if (rc) return rc;
       continue;
     }

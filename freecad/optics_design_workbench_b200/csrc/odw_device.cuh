@@ -16,7 +16,7 @@ struct DFace {
   double o[3], x[3], y[3], z[3];
   double p0, p1;
   double umin, umax, vmin, vmax;
-  double bmin[3], bmax[3];
+  double aux[6];                   // conicoid with an ODW_SEG_ASPHERE record: aux[0..4] = coefficients of rho^4 .. rho^12, aux[5] = 1
   int32_t kind, trim, nsign, group;
   int32_t seg_first, seg_count, face_id, flags;
   unsigned long long seqmask[2];   // bit s set <=> the face's group is in SequentialModeElements step s
@@ -343,6 +343,39 @@ __device__ __noinline__ int line_torus(const DFace& f, const double* w, const do
   return n;
 }
 
+// ---- even asphere on top of a conic of revolution (ODW_SEG_ASPHERE, include/odw.h); same arithmetic as the oracle ----
+// sag as a function of u = rho^2:  S(u) = c u / (1 + sqrt(1 - (1+k) c^2 u)) + u^2 (a0 + a1 u + a2 u^2 + a3 u^3 + a4 u^4)
+__device__ __forceinline__ bool asphere_sag(double c, double k, const double* a, double u, double& S, double& dSdu) {
+  const double q2 = 1.0 - (1.0 + k)*c*c*u;
+  if (!(q2 > 1e-14)) return false;                         // beyond (or on) the equator of the base conic
+  const double q = sqrt(q2);
+  S = c*u/(1.0 + q) + u*u*(a[0] + u*(a[1] + u*(a[2] + u*(a[3] + u*a[4]))));
+  dSdu = c/(2.0*q) + u*(2*a[0] + u*(3*a[1] + u*(4*a[2] + u*(5*a[3] + u*6*a[4]))));
+  return true;
+}
+
+// Newton on g(t) = z(t) - S(u(t)) with the ray reduced to the two coordinates the surface depends on:
+// z(t) = wz + t dz (axial), u(t) = rho^2 = U0 + 2 U1 t + U2 t^2.  Few live values: this runs below the bounce loop in the
+// call graph and every register it needs is one the loop cannot keep.  true = converged onto the surface.
+__device__ __forceinline__ bool asphere_newton(const DFace& f, double U0, double U1, double U2, double wz, double dz, double t0, double& t_out) {
+  double t = t0;
+  for (int it = 0; it < 40; ++it) {
+    double z = wz + t*dz, u = fmax(0.0, U0 + t*(2*U1 + U2*t)), S, dS;
+    if (!asphere_sag(f.p0, f.p1, f.aux, u, S, dS)) return false;
+    const double gp = dz - dS*2*(U1 + U2*t);
+    if (gp == 0 || !isfinite(gp)) return false;
+    const double dt = (z - S)/gp;
+    t -= dt;
+    if (fabs(dt) <= 1e-15*fmax(1.0, fabs(t))) {
+      z = wz + t*dz; u = fmax(0.0, U0 + t*(2*U1 + U2*t));
+      if (!asphere_sag(f.p0, f.p1, f.aux, u, S, dS)) return false;
+      if (fabs(z - S) > 1e-10*(1.0 + fabs(z))) return false;
+      t_out = t; return true;
+    }
+  }
+  return false;
+}
+
 __device__ __noinline__ int line_surface(const DFace& f, const double* s, const double* d, double* t) {
   double w[3] = { s[0]-f.o[0], s[1]-f.o[1], s[2]-f.o[2] };
   switch (f.kind) {
@@ -381,6 +414,32 @@ __device__ __noinline__ int line_surface(const DFace& f, const double* s, const 
     }
   }
   return 0;
+}
+
+// Conicoid with even-asphere terms: crossings of the base conic (or the vertex plane when it has none) refined by Newton.
+// A SIBLING of line_surface in the call graph, not a callee: the register needs of the deepest call chain squeeze the
+// bounce loop of the trace kernel (measured: as a callee of line_surface this cost the headline scene 17 %).
+__device__ __noinline__ int line_asphere(const DFace& f, const double* s, const double* d, double* t) {
+  double U0, U1, U2, wz, dz;
+  {
+    const double w[3] = { s[0]-f.o[0], s[1]-f.o[1], s[2]-f.o[2] };
+    wz = dot3(w, f.z); dz = dot3(d, f.z);
+    U2 = 1.0 - dz*dz; U1 = dot3(w, d) - wz*dz; U0 = dot3(w, w) - wz*wz;
+  }
+  const double c = f.p0, k1 = 1.0 + f.p1;
+  double r[2];
+  const int n = solve_quadratic(c*(U2 + k1*dz*dz), 2*(c*(U1 + k1*wz*dz) - dz), c*(U0 + k1*wz*wz) - 2*wz, r);
+  int ns = 0;
+  for (int i = 0; i < n; ++i) if (1.0 - k1*c*(wz + r[i]*dz) >= 0) r[ns++] = r[i];
+  if (ns == 0 && dz != 0) { r[0] = -wz/dz; ns = 1; }
+  int m = 0;
+  for (int i = 0; i < ns; ++i) {
+    double tt;
+    if (!asphere_newton(f, U0, U1, U2, wz, dz, r[i], tt)) continue;
+    if (m == 1 && fabs(tt - t[0]) <= 1e-9*fmax(1.0, fabs(tt))) continue;     // both starts found the same crossing
+    t[m++] = tt;
+  }
+  return m;
 }
 
 // ---- point on trimmed face (ray.py:426, distToShape(face) < distTol) in (u,v) space ---------
@@ -458,7 +517,9 @@ __device__ __noinline__ bool on_trimmed_face(const DFace& f, const odw_trimseg* 
     case ODW_SURF_CONICOID: {   // v = rho; meridian arc length per unit rho = sqrt(1 + z'^2), z' = c rho / q
       v = sqrt(x*x + y*y);
       const double q2 = fmax(1e-12, 1.0 - (1.0 + f.p1)*f.p0*f.p0*v*v);
-      su = v; sv = sqrt(1.0 + f.p0*f.p0*v*v/q2); u = 0; break;
+      double slope = f.p0*v/sqrt(q2);
+      if (f.aux[5] != 0.0) { const double u2 = v*v; slope += 2*v*u2*(2*f.aux[0] + u2*(3*f.aux[1] + u2*(4*f.aux[2] + u2*(5*f.aux[3] + u2*6*f.aux[4])))); }
+      su = v; sv = sqrt(1.0 + slope*slope); u = 0; break;
     }
     default: {   // torus
       double rho = sqrt(x*x + y*y);
@@ -502,8 +563,19 @@ __device__ __forceinline__ void outward_normal_general(const DFace& f, const dou
       g[0] = ca*rx/rho - sg*sa*f.z[0]; g[1] = ca*ry/rho - sg*sa*f.z[1]; g[2] = ca*rz/rho - sg*sa*f.z[2]; break;
     }
     case ODW_SURF_CONICOID: {   // du x dv ~ c rho_vec - q Z, q = 1 - (1+k) c z
-      const double z = dot3(w, f.z), q = 1.0 - (1.0 + f.p1)*f.p0*z;
-      g[0] = f.p0*(w[0]-z*f.z[0]) - q*f.z[0]; g[1] = f.p0*(w[1]-z*f.z[1]) - q*f.z[1]; g[2] = f.p0*(w[2]-z*f.z[2]) - q*f.z[2]; break;
+      const double z = dot3(w, f.z);
+      const double rx = w[0]-z*f.z[0], ry = w[1]-z*f.z[1], rz = w[2]-z*f.z[2];
+      double m = f.p0, zc = z;
+      if (f.aux[5] != 0.0) {
+        // even-asphere terms P(u), u = rho^2: the point minus P lies on the base conic at the same rho, which gives q without a
+        // square root; slope = c rho / q + dP/drho  =>  direction (c + 2 q dP/du) rho_vec - q Z
+        const double u = rx*rx + ry*ry + rz*rz;
+        zc = z - u*u*(f.aux[0] + u*(f.aux[1] + u*(f.aux[2] + u*(f.aux[3] + u*f.aux[4]))));
+        m = u*(2*f.aux[0] + u*(3*f.aux[1] + u*(4*f.aux[2] + u*(5*f.aux[3] + u*6*f.aux[4]))));
+      }
+      const double q = 1.0 - (1.0 + f.p1)*f.p0*zc;
+      if (f.aux[5] != 0.0) m = f.p0 + 2*q*m;
+      g[0] = m*rx - q*f.z[0]; g[1] = m*ry - q*f.z[1]; g[2] = m*rz - q*f.z[2]; break;
     }
     default: {
       double z = dot3(w, f.z);

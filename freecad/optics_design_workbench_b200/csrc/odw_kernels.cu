@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
       else {
         ++n_isect;
         double t;
-        const int fi = BVH ? find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t)
+        const int fi = BVH ? find_nearest_bvh<FEAT>(p, point, dn, medium, seq_index, p.max_len, t)
                            : find_nearest_smem<FEAT>(sshells, sfaces, p, point, dn, medium, seq_index, skip_shell, p.max_len, t);
         done = interact<MC, FEAT>(p, BVH ? p.scene.faces : sfaces, BVH ? nullptr : sshells, groups, fi, t, i, r, s_cnt);
       }

@@ -14,7 +14,7 @@ namespace cg = cooperative_groups;
 // Scene / launch features a kernel instance is compiled for.  The trace kernel is one big state machine; code for features
 // the scene does not use still costs registers (spills) and instruction-cache room in the bounce loop, so the host picks
 // the leanest instance that covers the launch (odw_api.cu launch_features): measured +12 % on lensesAndMirrors.
-enum { FEAT_EXT = 1,        // gratings, stochastic surface models, finite absorption lengths
+enum { FEAT_EXT = 1,        // gratings, stochastic surface models, finite absorption lengths, even-asphere faces
        FEAT_SURFSRC = 2,    // surface light source (init_ray_surface)
        FEAT_SEQ = 4,        // SequentialMode filtering
        FEAT_BIN = 8,        // detector binning on the device
@@ -52,6 +52,7 @@ struct NearestHit {
 // called BY VALUE: a pointer to the caller's ray state would force that state into local memory for the whole
 // kernel.  Returns the smallest t in (tol, lim) whose point lies on the trimmed face, or +inf.  (All hits of one face
 // share its group, so only the nearest one can win either slot of NearestHit.)
+template <int FEAT>
 __device__ __noinline__ double general_nearest(const DFace* fp, const odw_trimseg* __restrict__ segs, double tol,
                                                double sx, double sy, double sz, double dx, double dy, double dz, double lim) {
   const DFace& f = *fp;
@@ -77,7 +78,9 @@ __device__ __noinline__ double general_nearest(const DFace* fp, const odw_trimse
     if ((A*tv + 2*B)*tv + C > outer*outer) return 1e300;
   }
   double ts[4];
-  int nt = line_surface(f, s, dn, ts);
+  // even-asphere faces only in instances with FEAT_EXT: the Newton solver below this call would squeeze the registers of the
+  // bounce loop of every instance that can reach it (measured: -17 % on the headline scene, which has no such face)
+  int nt = ((FEAT & FEAT_EXT) && f.kind == ODW_SURF_CONICOID && f.aux[5] != 0.0) ? line_asphere(f, s, dn, ts) : line_surface(f, s, dn, ts);
   double best = 1e300;
   for (int k = 0; k < nt; ++k) {
     double t = ts[k];
@@ -98,7 +101,7 @@ __device__ __forceinline__ void accept_hit(double t, int idx, int group, int med
 // One face against the line start + t*dn (ray.py:407-432).  tmax = maxRayLength + distTol.
 // Fast paths (inline, no division / inverse trigonometry): rectangle on a plane, whole sphere or spherical cap/zone
 // with full azimuth, cylinder band with full azimuth.  Everything else goes through test_face_general.
-template <bool CHECK_GROUP>
+template <bool CHECK_GROUP, int FEAT>
 __device__ __forceinline__ void test_face(const DFace& f, int idx, const TraceParams& p, const double* s, const double* dn,
                                           int medium, int seq_index, double tmax, NearestHit& h) {
   if (CHECK_GROUP) {   // the shared-memory path filters whole shells instead
@@ -107,7 +110,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
   }
   const double tol = p.tol;
   if (!(f.flags & DFACE_FAST)) {
-    const double t = general_nearest(&f, p.scene.segs, tol, s[0], s[1], s[2], dn[0], dn[1], dn[2], h.lim);
+    const double t = general_nearest<FEAT>(&f, p.scene.segs, tol, s[0], s[1], s[2], dn[0], dn[1], dn[2], h.lim);
     if (t < 1e299) accept_hit(t, idx, f.group, medium, tol, h);
     return;
   }
@@ -190,7 +193,7 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
     // miss, entirely behind the start, or beyond what can still matter
     if (t0 > t1 || t1 < 0.0f || t0 > limf) continue;
     const int f1 = sh.face_first + sh.face_count;
-    for (int i = sh.face_first; i < f1; ++i) test_face<false>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
+    for (int i = sh.face_first; i < f1; ++i) test_face<false, FEAT>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
     limf = (float)h.lim*1.000002f;
   }
   if (h.fA < 0) return -1;
@@ -202,6 +205,7 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
 // Conservative fp32 slab tests on boxes widened by the culling margin; near child first, the far child is pushed with
 // its entry distance and dropped at pop time if a closer hit has been accepted meanwhile.
 #define ODW_BVH_STACK 64
+template <int FEAT>
 __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const double* s, const double* dn,
                                                 int medium, int seq_index, double max_len, double& t_out) {
   const double tol = p.tol;
@@ -235,7 +239,7 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
     if (hit0 && d.z > 0) {                                             // leaf: exact fp64 tests
       for (int k = 0; k < d.z; ++k) {
         const int fi = __ldg(p.scene.bvh_prims + d.x + k);
-        test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
+        test_face<true, FEAT>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
       }
       limf = (float)h.lim*1.000002f;
       hit0 = false;
@@ -244,7 +248,7 @@ __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const doub
     if (hit1 && d.w > 0) {
       for (int k = 0; k < d.w; ++k) {
         const int fi = __ldg(p.scene.bvh_prims + d.y + k);
-        test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
+        test_face<true, FEAT>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, h);
       }
       limf = (float)h.lim*1.000002f;
       hit1 = false;

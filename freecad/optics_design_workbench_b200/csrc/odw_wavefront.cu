@@ -139,12 +139,13 @@ __device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const BvhStack& st, 
 }
 
 // cur is a leaf: exact fp64 tests of its faces
+template <int FEAT>
 __device__ __forceinline__ void bvh_leaf_step(BvhTrav& tr, const BvhStack& st, const TraceParams& p, const double* s, const double* dn, int medium, int seq_index) {
   const int packed = -2 - tr.cur, first = packed >> 4, count = packed & 15;
   const double tmax = p.max_len + p.tol;
   for (int k = 0; k < count; ++k) {
     const int fi = __ldg(p.scene.bvh_prims + first + k);
-    test_face<true>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, tr.h);
+    test_face<true, FEAT>(p.scene.faces[fi], fi, p, s, dn, medium, seq_index, tmax, tr.h);
   }
   tr.limf = (float)tr.h.lim*1.000002f;
   tr.cur = bvh_pop(tr, st);
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 #ifndef ODW_WF_BLOCKS
 #define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
 #endif
+template <int FEAT>
 __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
                                                       unsigned int n, unsigned int* fetch_counter, const unsigned int* __restrict__ order,
                                                       WfPool ordered) {
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
       if (have && tr.cur >= 0) bvh_inner_step(tr, st, p);
     }
     // leaves: exact face tests, all lanes that hold one together
-    if (have && tr.cur < TRAV_DONE) bvh_leaf_step(tr, st, p, s, dn, medium, seq_index);
+    if (have && tr.cur < TRAV_DONE) bvh_leaf_step<FEAT>(tr, st, p, s, dn, medium, seq_index);
     if (have && tr.cur == TRAV_DONE) {
       const double tol = p.tol;
       double t = 0; int fi = -1;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(256) wf_tail(const __grid_constant__ TracePara
       if (n_isect >= p.max_isect) { atomicAdd(&s_cnt[CNT_DEPTH], 1u); break; }
       ++n_isect;
       double t;
-      const int fi = find_nearest_bvh(p, point, dn, medium, seq_index, p.max_len, t);
+      const int fi = find_nearest_bvh<FEAT_ALL>(p, point, dn, medium, seq_index, p.max_len, t);
       if (interact<MC, FEAT_ALL>(p, p.scene.faces, nullptr, p.scene.groups, fi, t, i, r, s_cnt)) break;
     }
     finish_ray<MC>(p, i, r, s_cnt);
@@ -337,10 +339,12 @@ extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool
 }
 
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
-                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int blocks, cudaStream_t st) {
-  const unsigned int want = (n + 255u)/256u;
-  wf_traverse<<<(unsigned int)blocks < want ? (unsigned int)blocks : want, 256, 0, st>>>(*p, make_pool(pool, cap), static_cast<double2*>(hits), n, fetch_counter,
-                                                                                          order, make_pool(order ? pool_ordered : pool, cap));
+                                       unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int need, int blocks, cudaStream_t st) {
+  const unsigned int want = (n + 255u)/256u, grid = (unsigned int)blocks < want ? (unsigned int)blocks : want;
+  const WfPool pl = make_pool(pool, cap), po = make_pool(order ? pool_ordered : pool, cap);
+  // need: FEAT_* bits of the launch; only FEAT_EXT (even-asphere faces) concerns the traversal
+  if (need & FEAT_EXT) wf_traverse<FEAT_ALL><<<grid, 256, 0, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po);
+  else wf_traverse<0><<<grid, 256, 0, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po);
   return cudaGetLastError();
 }
 
@@ -378,6 +382,6 @@ extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, s
 
 extern "C" int odw_wf_traverse_occupancy(void) {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_traverse, 256, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_traverse<0>, 256, 0);
   return nb;
 }

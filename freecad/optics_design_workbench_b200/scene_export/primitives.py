@@ -118,17 +118,21 @@ def plano_convex_lens(R, aperture_radius, edge_thickness=0.0):
   return faces
 
 
-def conicoid_surface(c, k, vertex=(0, 0, 0)):
-  'conic of revolution about +z with its vertex at `vertex`: sag c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2)) (include/odw.h)'
-  return Surface('conicoid', p=np.asarray(vertex, float), n=_Z.copy(), dx=_X.copy(), dy=_Y.copy(), c=float(c), k=float(k))
+def conicoid_surface(c, k, vertex=(0, 0, 0), poly=None):
+  '''
+  conic of revolution about +z with its vertex at `vertex`: sag c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2)) (include/odw.h);
+  poly = even-asphere coefficients of rho^4, rho^6, ... rho^12 added to it (the lens-catalogue form of an asphere)
+  '''
+  return Surface('conicoid', p=np.asarray(vertex, float), n=_Z.copy(), dx=_X.copy(), dy=_Y.copy(), c=float(c), k=float(k),
+                 poly=None if poly is None else [float(x) for x in poly])
 
 
-def conic_dish(c, k, aperture_radius, inner_radius=0.0, reversed_=False):
+def conic_dish(c, k, aperture_radius, inner_radius=0.0, reversed_=False, poly=None):
   '''
   Open single-face shell: the conic of revolution z = sag(rho) for inner_radius <= rho <= aperture_radius (a parabolic
   mirror for k = -1: focal length 1/(2c), focus at z = 1/(2c)).  Geometric normal c rho - q z: away from the focus side.
   '''
-  return [_face(conicoid_surface(c, k), [_rect_loop(0, TWO_PI, inner_radius, aperture_radius)], reversed_=reversed_, shell_key=None)]
+  return [_face(conicoid_surface(c, k, poly=poly), [_rect_loop(0, TWO_PI, inner_radius, aperture_radius)], reversed_=reversed_, shell_key=None)]
 
 
 def revolved_parabola_dish(focal, aperture_radius):

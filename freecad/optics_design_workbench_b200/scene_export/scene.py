@@ -12,7 +12,7 @@ import numpy as np
 
 SURF_PLANE, SURF_CYLINDER, SURF_CONE, SURF_SPHERE, SURF_TORUS, SURF_CONICOID = 1, 2, 3, 4, 5, 6
 TRIM_NONE, TRIM_UVBOX, TRIM_LOOPS = 0, 1, 2
-SEG_LINE, SEG_ARC = 1, 2
+SEG_LINE, SEG_ARC, SEG_ASPHERE = 1, 2, 3
 OPT_MIRROR, OPT_LENS, OPT_GRATING, OPT_ABSORBER, OPT_VACUUM = 0, 1, 2, 3, 4
 OPTICAL_TYPES = ('Mirror', 'Lens', 'Grating', 'Absorber', 'Vacuum')
 GRATING_TYPES = ('Reflection', 'Transmission')
@@ -168,10 +168,18 @@ def _rigid(transform):
   return R, transform[:3, 3]
 
 
-def conic_sag(c, k, rho):
-  'optical sag of a conic of revolution: z = c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2))'
+def conic_sag(c, k, rho, poly=None):
+  '''
+  optical sag of a conic of revolution, z = c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2)), plus the even-asphere terms
+  poly[j] rho^(2j+4), j = 0..4 (include/odw.h ODW_SEG_ASPHERE)
+  '''
   rho = np.asarray(rho, dtype=float)
-  return c*rho*rho/(1+np.sqrt(np.maximum(0.0, 1-(1+k)*c*c*rho*rho)))
+  u = rho*rho
+  z = c*u/(1+np.sqrt(np.maximum(0.0, 1-(1+k)*c*c*u)))
+  if poly is not None:
+    a = list(poly)+[0.0]*(5-len(poly))
+    z = z + u*u*(a[0] + u*(a[1] + u*(a[2] + u*(a[3] + u*a[4]))))
+  return z
 
 
 def _revolved_conic(surf):
@@ -229,6 +237,11 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
       raise UnsupportedGeometry('conicoid needs a finite non-zero vertex curvature and a finite conic constant')
     f['p0'], f['p1'] = surf.c, surf.k
   f['group'], f['shell'], f['face_id'] = group, shell, face_id
+  poly = [float(x) for x in (getattr(surf, 'poly', None) or [])] if surf.kind == 'conicoid' else []
+  if len(poly) > 5 or not all(np.isfinite(poly)):
+    raise ValueError('a conicoid takes up to five finite even-asphere coefficients (rho^4 .. rho^12)')
+  if not any(poly):
+    poly = []
 
   segs = []
   for loop in fi.loops:
@@ -258,15 +271,18 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
         trim = TRIM_NONE
   f['trim_kind'] = trim
   f['uv_min'], f['uv_max'] = lo, hi
-  if trim == TRIM_LOOPS:
-    f['seg_first'], f['seg_count'] = len(segs_out), len(segs)
-    segs_out.extend(segs)
-  f['aabb_min'], f['aabb_max'] = _face_aabb(f)
+  aux = [(SEG_ASPHERE, poly+[0.0]*(5-len(poly)))] if poly else []       # auxiliary record first, boundary pieces after it
+  if trim == TRIM_LOOPS or aux:
+    f['seg_first'], f['seg_count'] = len(segs_out), len(aux)+(len(segs) if trim == TRIM_LOOPS else 0)
+    segs_out.extend(aux)
+    if trim == TRIM_LOOPS:
+      segs_out.extend(segs)
+  f['aabb_min'], f['aabb_max'] = _face_aabb(f, poly=poly or None)
   return f
 
 
-def eval_face(f, u, v):
-  'world point(s) of FACE_DTYPE row f at parameters u, v'
+def eval_face(f, u, v, poly=None):
+  'world point(s) of FACE_DTYPE row f at parameters u, v (poly: even-asphere coefficients of a conicoid face)'
   u = np.asarray(u, dtype=float)[..., None]
   v = np.asarray(v, dtype=float)[..., None]
   O, X, Y, Z = f['origin'], f['xdir'], f['ydir'], f['zdir']
@@ -283,11 +299,11 @@ def eval_face(f, u, v):
   if k == SURF_TORUS:
     return O + (f['p0']+f['p1']*np.cos(v))*er + f['p1']*np.sin(v)*Z
   if k == SURF_CONICOID:
-    return O + v*er + conic_sag(float(f['p0']), float(f['p1']), v)*Z
+    return O + v*er + conic_sag(float(f['p0']), float(f['p1']), v, poly)*Z
   raise ValueError(k)
 
 
-def _face_aabb(f, n=65):
+def _face_aabb(f, n=65, poly=None):
   lo, hi = f['uv_min'], f['uv_max']
   k = int(f['kind'])
   if k == SURF_PLANE:
@@ -295,7 +311,7 @@ def _face_aabb(f, n=65):
     pts = eval_face(f, uu, vv).reshape(-1, 3)
     return pts.min(axis=0), pts.max(axis=0)
   uu, vv = np.meshgrid(np.linspace(lo[0], hi[0], n), np.linspace(lo[1], hi[1], n))
-  pts = eval_face(f, uu, vv).reshape(-1, 3)
+  pts = eval_face(f, uu, vv, poly).reshape(-1, 3)
   # sagitta of the sampling: a point between samples can stick out by R(1-cos(h/2))
   hu = (hi[0]-lo[0])/(n-1)
   rmax = {SURF_CYLINDER: f['p0'], SURF_SPHERE: f['p0'], SURF_TORUS: f['p0']+f['p1'],
@@ -307,6 +323,10 @@ def _face_aabb(f, n=65):
     hv = (hi[1]-lo[1])/(n-1)
     q = np.sqrt(max(1e-12, 1-(1+float(f['p1']))*float(f['p0'])**2*hi[1]**2))
     pad += hv*hv/8*abs(float(f['p0']))/q**3
+    if poly is not None:                     # second derivative of the polynomial part, bounded on a fine grid
+      r = np.linspace(lo[1], hi[1], 1025)
+      z = conic_sag(0.0, 0.0, r, poly)
+      pad += hv*hv/8*1.5*np.abs(np.gradient(np.gradient(z, r), r)).max()
   if k in (SURF_SPHERE, SURF_TORUS):
     hv = (hi[1]-lo[1])/(n-1)
     rv = f['p0'] if k == SURF_SPHERE else f['p1']

@@ -61,6 +61,9 @@ extern "C" {
 /* trim segment kinds (pcurves of the face boundary in (u,v) space) */
 #define ODW_SEG_LINE 1       /* a = {u0, v0, u1, v1} */
 #define ODW_SEG_ARC  2       /* a = {cu, cv, radius, angle0, span}: angles in [angle0, angle0+span], span in (0, 2pi] */
+#define ODW_SEG_ASPHERE 3    /* not a boundary piece: auxiliary record of a conicoid face, a = even-asphere coefficients of
+                              * rho^4, rho^6, rho^8, rho^10, rho^12 added to the conic sag.  Must be the face's FIRST segment
+                              * (seg_first; counted in seg_count, also when trim_kind is not ODW_TRIM_LOOPS) */
 
 /* optical types, order of the reference's OpticalType enumeration (optical_group.py:29-96) */
 #define ODW_OPT_MIRROR   0
@@ -86,7 +89,8 @@ extern "C" {
  * the axis >= 0, c = vertex curvature (p0), k = conic constant (p1): k = -1 paraboloid of focal length 1/(2c) (what OCC
  * writes as the surface of revolution of a Geom_Parabola about its own axis), -1 < k < 0 prolate / k > 0 oblate
  * ellipsoid, k < -1 hyperboloid sheet, k = 0 sphere.  n_geom of a conicoid = du x dv / |du x dv| ~ c rho_vec - q Z,
- * q = 1 - (1+k) c z (the side the vertex bulges towards for c > 0).
+ * q = 1 - (1+k) c z (the side the vertex bulges towards for c > 0).  With an ODW_SEG_ASPHERE record the sag gains
+ * a4 v^4 + ... + a12 v^12 (standard even asphere); the ray crossing is then found by Newton from the crossings of the base conic.
  * Outward normal n_out = nsign * n_geom, n_geom = the radial-outward normal written with (X,Y,Z)
  * (plane: Z); nsign folds the face orientation (TopAbs_REVERSED) and the handedness of the frame. */
 typedef struct odw_face {

@@ -298,8 +298,46 @@ static int solve_quartic_depressed(double B, double C, double D, double lo, doub
   return n;
 }
 
+/* ---- even asphere on top of a conic of revolution (ODW_SURF_CONICOID with an ODW_SEG_ASPHERE record, odw.h) ----
+ * sag as a function of u = rho^2:  S(u) = c u / (1 + sqrt(1 - (1+k) c^2 u)) + u^2 (a0 + a1 u + a2 u^2 + a3 u^3 + a4 u^4) */
+static const double* asphere_coeffs(const odw_face* f, const odw_trimseg* segs) {
+  if (f->kind != ODW_SURF_CONICOID || f->seg_count < 1 || !segs) return NULL;
+  return segs[f->seg_first].kind == ODW_SEG_ASPHERE ? segs[f->seg_first].a : NULL;
+}
+
+static int asphere_sag(double c, double k, const double* a, double u, double* S, double* dSdu) {
+  double q2 = 1.0 - (1.0 + k)*c*c*u;
+  if (!(q2 > 1e-14)) return 0;                              /* beyond (or on) the equator of the base conic */
+  double q = sqrt(q2);
+  *S = c*u/(1.0 + q) + u*u*(a[0] + u*(a[1] + u*(a[2] + u*(a[3] + u*a[4]))));
+  *dSdu = c/(2.0*q) + u*(2*a[0] + u*(3*a[1] + u*(4*a[2] + u*(5*a[3] + u*6*a[4]))));
+  return 1;
+}
+
+/* Newton on g(t) = z(t) - S(u(t)) along w + t d (d unit), started at t0; 1 = converged onto the surface */
+static int asphere_newton(double c, double k, const double* a, const double* w, const double* d, double wz, double dz,
+                          double t0, double* t_out) {
+  double wd = dot3(w, d), ww = dot3(w, w), t = t0;
+  for (int it = 0; it < 40; ++it) {
+    double z = wz + t*dz, u = ww + t*(2*wd + t) - z*z, S, dS;
+    if (u < 0) u = 0;
+    if (!asphere_sag(c, k, a, u, &S, &dS)) return 0;
+    double g = z - S, gp = dz - dS*2*((wd + t) - z*dz);
+    if (gp == 0 || !isfinite(gp)) return 0;
+    double dt = g/gp;
+    t -= dt;
+    if (fabs(dt) <= 1e-15*fmax(1.0, fabs(t))) {
+      z = wz + t*dz; u = ww + t*(2*wd + t) - z*z; if (u < 0) u = 0;
+      if (!asphere_sag(c, k, a, u, &S, &dS)) return 0;
+      if (fabs(z - S) > 1e-10*(1.0 + fabs(z))) return 0;
+      *t_out = t; return 1;
+    }
+  }
+  return 0;
+}
+
 /* all parameters t with start + t*d on the untrimmed surface; d must be unit.  returns count (<=4) */
-static int line_surface(const odw_face* f, const double* s, const double* d, double* t) {
+static int line_surface(const odw_face* f, const odw_trimseg* segs, const double* s, const double* d, double* t) {
   double w[3] = { s[0]-f->origin[0], s[1]-f->origin[1], s[2]-f->origin[2] };
   switch (f->kind) {
     case ODW_SURF_PLANE: {
@@ -354,6 +392,20 @@ static int line_surface(const odw_face* f, const double* s, const double* d, dou
       int n = solve_quadratic(A, B, C, r), m = 0;
       /* the sheet of the quadric that the sag formula describes: q = 1 - (1+k) c z >= 0 */
       for (int i = 0; i < n; ++i) if (1.0 - (1.0 + k)*c*(wz + r[i]*dz) >= 0) t[m++] = r[i];
+      const double* a = asphere_coeffs(f, segs);
+      if (a) {
+        /* polynomial terms: Newton from every crossing of the base conic (from the vertex plane when it has none) */
+        double start[2]; int ns = m;
+        for (int i = 0; i < m; ++i) start[i] = t[i];
+        if (ns == 0 && dz != 0) { start[0] = -wz/dz; ns = 1; }
+        m = 0;
+        for (int i = 0; i < ns; ++i) {
+          double tt;
+          if (!asphere_newton(c, k, a, w, d, wz, dz, start[i], &tt)) continue;
+          if (m == 1 && fabs(tt - t[0]) <= 1e-9*fmax(1.0, fabs(tt))) continue;    /* both starts found the same crossing */
+          t[m++] = tt;
+        }
+      }
       return m;
     }
   }
@@ -363,7 +415,7 @@ static int line_surface(const odw_face* f, const double* s, const double* d, dou
 /* ------------------------------------------------------------------------------------------ */
 /* (u, v) of a point on the surface and the outward normal  (ray.py:463-465 Surface.parameter + normalAt) */
 
-static void surface_uv_normal(const odw_face* f, const double* P, double* uv, double* n_out) {
+static void surface_uv_normal(const odw_face* f, const odw_trimseg* segs, const double* P, double* uv, double* n_out) {
   double w[3] = { P[0]-f->origin[0], P[1]-f->origin[1], P[2]-f->origin[2] };
   double x = dot3(w, f->xdir), y = dot3(w, f->ydir), z = dot3(w, f->zdir);
   double ng[3];
@@ -411,6 +463,13 @@ static void surface_uv_normal(const odw_face* f, const double* P, double* uv, do
       /* v = rho; du x dv is along c rho_vec - q Z, q = 1 - (1+k) c z (= the square root of the sag formula) */
       double q = 1.0 - (1.0 + f->p1)*f->p0*z;
       uv[0] = atan2(y, x); uv[1] = sqrt(x*x + y*y);
+      const double* a = asphere_coeffs(f, segs);
+      if (a) {       /* S_rho e_r - Z with S_rho = 2 rho dS/du: the same direction as c rho_vec - q Z when the polynomial vanishes */
+        double S, dS;
+        if (!asphere_sag(f->p0, f->p1, a, x*x + y*y, &S, &dS)) { S = 0; dS = 0; }
+        for (int i = 0; i < 3; ++i) ng[i] = 2*dS*(x*f->xdir[i] + y*f->ydir[i]) - f->zdir[i];
+        break;
+      }
       for (int i = 0; i < 3; ++i) ng[i] = f->p0*(x*f->xdir[i] + y*f->ydir[i]) - q*f->zdir[i];
       break;
     }
@@ -453,7 +512,10 @@ static int trim_contains(const odw_face* f, const odw_trimseg* segs, double* uv,
     case ODW_SURF_CONICOID: {   /* meridian arc length per unit rho: sqrt(1 + z'^2), z' = c rho / q */
       double q2 = 1.0 - (1.0 + f->p1)*f->p0*f->p0*v*v;
       if (q2 < 1e-12) q2 = 1e-12;
-      su = v; sv = sqrt(1.0 + f->p0*f->p0*v*v/q2); uper = 1; break;
+      double slope = f->p0*v/sqrt(q2);
+      const double* a = asphere_coeffs(f, segs);
+      if (a) { double u2 = v*v; slope += 2*v*u2*(2*a[0] + u2*(3*a[1] + u2*(4*a[2] + u2*(5*a[3] + u2*6*a[4])))); }
+      su = v; sv = sqrt(1.0 + slope*slope); uper = 1; break;
     }
   }
   if (su < 1e-12) su = 1e-12;
@@ -468,6 +530,7 @@ static int trim_contains(const odw_face* f, const odw_trimseg* segs, double* uv,
   for (int i = 0; i < f->seg_count; ++i) {
     const odw_trimseg* s = &segs[f->seg_first + i];
     const double* a = s->a;
+    if (s->kind == ODW_SEG_ASPHERE) continue;          /* auxiliary record, not a boundary piece */
     if (s->kind == ODW_SEG_LINE) {
       if ((a[1] > v) != (a[3] > v)) {
         double ux = a[0] + (v - a[1])*(a[2] - a[0])/(a[3] - a[1]);
@@ -580,13 +643,13 @@ static void surface_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t r
     surface_eval(f, u, v, P, du, dv);
     if (!ok) continue;
     double uv[2], n_tmp[3];
-    surface_uv_normal(f, P, uv, n_tmp);
+    surface_uv_normal(f, s->emit_segs, P, uv, n_tmp);
     if (trim_contains(f, s->emit_segs, uv, s->dist_tol)) break;   /* :399-408 keep rolling until the point is on the face */
   }
   double theta = interp_cdf(a[1], s->first_cdf, s->n_first, s->first_lo, s->first_hi);
   double phi = b[0]*TWO_PI;                                        /* :544 */
   double uv[2], n[3];
-  surface_uv_normal(f, P, uv, n);
+  surface_uv_normal(f, s->emit_segs, P, uv, n);
   /* :549 faceTangent = du if du.Length > 10 distTol else the longer of du, dv */
   double lu = len3(du), lv = len3(dv);
   const double* t = (lu > 10*s->dist_tol || lu >= lv) ? du : dv;
@@ -711,7 +774,7 @@ static int find_nearest(const odw_scene_desc* sc, const odw_trace_cfg* cfg, cons
       if (!(face_c[fi].dist < max_len)) continue;                                 /* :410 */
       const odw_face* f = &sc->faces[face_c[fi].index];
       double ts[4];
-      int nt = line_surface(f, start, dn, ts);                                    /* :411 */
+      int nt = line_surface(f, sc->segs, start, dn, ts);                                    /* :411 */
       for (int k = 0; k < nt; ++k) {
         double t = ts[k];
         double P[3] = { start[0]+t*dn[0], start[1]+t*dn[1], start[2]+t*dn[2] };
@@ -720,7 +783,7 @@ static int find_nearest(const odw_scene_desc* sc, const odw_trace_cfg* cfg, cons
         double dseg = t < 0 ? -t : (t > max_len ? t - max_len : 0);               /* :425 distance to the finite segment */
         if (!(dseg < tol)) continue;
         double uv[2], nrm[3];
-        surface_uv_normal(f, P, uv, nrm);
+        surface_uv_normal(f, sc->segs, P, uv, nrm);
         if (!trim_contains(f, sc->segs, uv, tol)) continue;                       /* :426 */
         if (nh < 64) { hits[nh].face = face_c[fi].index; hits[nh].t = dist; memcpy(hits[nh].P, P, sizeof P); hits[nh].order = nh; ++nh; }
         max_len = dist + 5*tol;                                                   /* :432 */
@@ -887,7 +950,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
     }
     /* getNormal (:455-480): outward normal, flipped to point along propagation; isEntering */
     double uv[2], n_out[3], nrm[3];
-    surface_uv_normal(f, point, uv, n_out);
+    surface_uv_normal(f, sc->segs, point, uv, n_out);
     double dray[3] = { point[0]-prev[0], point[1]-prev[1], point[2]-prev[2] };
     double cosang = dot3(dray, n_out)/(len3(dray)*len3(n_out));
     int entering = cosang < 0;
@@ -1065,7 +1128,7 @@ int oracle_find_nearest(const odw_scene_desc* sc, const odw_trace_cfg* cfg, cons
 /* Surface.parameter + Face.normalAt (ray.py:463-466): (u, v) and the orientation-aware unit normal of a face at P */
 int oracle_face_normal(const odw_scene_desc* sc, int32_t face, const double* P, double* uv_out, double* normal_out) {
   if (face < 0 || face >= sc->n_faces) return ODW_EINVAL;
-  surface_uv_normal(&sc->faces[face], P, uv_out, normal_out);
+  surface_uv_normal(&sc->faces[face], sc->segs, P, uv_out, normal_out);
   return 0;
 }
 

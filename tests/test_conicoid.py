@@ -178,6 +178,84 @@ def test_parabolic_lens_surface_and_trim(oracle):
   assert np.abs(h['points'][(h['ray_index'] == 3) & (h['bounce'] == 2)][0]-[0, 0, 60]).max() < 1e-12
 
 
+def test_even_asphere_terms_known_answers(oracle):
+  '''
+  ODW_SEG_ASPHERE: sag = conic + a4 rho^4 + a6 rho^6.  Axis-parallel rays meet the surface at their own rho (z = sag(rho)
+  exactly), oblique rays satisfy the implicit equation, the normal is the analytic gradient, and with all coefficients
+  zero nothing changes against the plain conicoid.
+  '''
+  c, k, poly, R = 1/30.0, -0.6, [2.0e-5, -3.0e-8], 12.0
+  from freecad.optics_design_workbench_b200.scene_export.scene import conic_sag
+  asph = dish_and_screen(prim.conic_dish(c, k, R, poly=poly), screen_z=80.0)
+  assert int(asph.faces[0]['seg_count']) == 1 and int(asph.segs[asph.faces[0]['seg_first']]['kind']) == sc_mod.SEG_ASPHERE
+  o, d = grid_rays(R)
+  r = trace(oracle, asph, o, d)
+  h = r['hits']
+  P1 = h['points'][h['bounce'] == 0]
+  rho = np.hypot(o[:, 0], o[:, 1])
+  assert len(P1) == len(o) and np.abs(P1[:, 2]-conic_sag(c, k, rho, poly)).max() < 1e-13
+  # reflected direction from the analytic normal S'(rho) e_r - z
+  u = rho*rho
+  q = np.sqrt(1-(1+k)*c*c*u)
+  slope = c*rho/q + 4*poly[0]*rho**3 + 6*poly[1]*rho**5
+  n = np.column_stack([slope*o[:, 0]/rho, slope*o[:, 1]/rho, -np.ones_like(rho)])
+  n /= np.linalg.norm(n, axis=1)[:, None]
+  expect = d-2*np.sum(d*n, axis=1)[:, None]*n
+  D2 = h['directions'][h['bounce'] == 1]
+  assert np.abs(D2-expect).max() < 1e-12
+  # oblique rays: the hit satisfies z = sag(rho) and lies inside the aperture
+  rng = np.random.default_rng(4)
+  oo = np.column_stack([rng.uniform(-9, 9, 500), rng.uniform(-9, 9, 500), np.full(500, 40.0)])
+  dd = np.column_stack([rng.normal(0, 0.15, 500), rng.normal(0, 0.15, 500), -np.ones(500)])
+  r = trace(oracle, asph, oo, dd, max_intersections=1)
+  P = r['hits']['points'][r['hits']['group'] == 0]
+  assert len(P) > 300
+  rr = np.hypot(P[:, 0], P[:, 1])
+  assert rr.max() < R+1e-6 and np.abs(P[:, 2]-conic_sag(c, k, rr, poly)).max() < 1e-12
+  # a departure of 2e-5 rho^4 is visible: the plain conic puts the same rays elsewhere
+  plain = dish_and_screen(prim.conic_dish(c, k, R), screen_z=80.0)
+  r0 = trace(oracle, plain, oo, dd, max_intersections=1)
+  assert np.abs(r0['hits']['points'][:50]-r['hits']['points'][:50]).max() > 1e-3
+  # all-zero coefficients: no auxiliary record, identical results
+  zero = dish_and_screen(prim.conic_dish(c, k, R, poly=[0.0, 0.0]), screen_z=80.0)
+  assert int(zero.faces[0]['seg_count']) == 0
+  rz = trace(oracle, zero, oo, dd, max_intersections=1)
+  assert np.array_equal(rz['hits']['points'], r0['hits']['points'])
+
+
+def test_asphere_corrects_spherical_aberration(oracle):
+  '''
+  A plano-convex singlet whose curved face is the hyperboloid with k = -n^2 focuses a collimated beam entering through the
+  flat side to one point (the Cartesian-oval result for this configuration); the spherical face of the same curvature does not.
+  Checks refraction through a conicoid face end to end.
+  '''
+  n, Rc, ap, thick = 1.5, 20.0, 8.0, 6.0
+  def singlet(k):
+    b = SceneBuilder()
+    g = b.add_group('L', 'L', optical_type='Lens', refractive_index=n)
+    # curved face bulging towards +z: the conicoid frame is flipped (vertex at z = thick, opening towards -z)
+    faces = prim.conic_dish(1/Rc, k, ap) + [prim._face(prim.plane_surface((0, 0, 0), (1, 0, 0), (0, 1, 0)), [prim._circle_loop(ap)], reversed_=True, shell_key=None)]
+    flip = prim.translation(0, 0, thick) @ prim.rotation((1, 0, 0), np.pi)
+    faces[0].transform = flip
+    for f in faces:
+      f.shell_key = 1
+    b.add_shape(g, faces, np.eye(4))
+    a = b.add_group('A', 'A', optical_type='Absorber', record_hits=True)
+    b.add_shape(a, prim.disc(50.0), prim.translation(0, 0, thick + Rc/(n-1)))       # paraxial focus: f = R/(n-1) behind the vertex
+    return b.build()
+  rho = np.linspace(0.5, 6.5, 13)
+  o = np.column_stack([rho, np.zeros_like(rho), np.full_like(rho, -5.0)])
+  d = np.tile([0, 0, 1.0], (len(rho), 1))
+  spot = {}
+  for k in (0.0, -n*n):
+    r = trace(oracle, singlet(k), o, d)
+    h = r['hits']
+    assert np.all(r['n_segments'] == 3)
+    spot[k] = np.abs(h['points'][h['group'] == 1][:, 0])
+  assert spot[-n*n].max() < 1e-9            # stigmatic
+  assert spot[0.0].max() > 0.05             # the sphere's marginal rays miss the paraxial focus by far more
+
+
 def test_conicoid_validation():
   b = SceneBuilder()
   g = b.add_group('M', 'M', optical_type='Mirror')
@@ -193,11 +271,12 @@ def test_gpu_conicoid_parity_with_oracle(gpu_engine, oracle):
   'paraboloid + ellipsoid + hyperboloid mirrors, a parabolic lens and a screen: same sequences, points to 1e-9 mm'
   b = SceneBuilder()
   m = b.add_group('M', 'M', optical_type='Mirror', reflectivity=0.9)
-  b.add_shape(m, prim.conic_dish(1/25.0, -1.0, 20.0), np.eye(4))
+  b.add_shape(m, prim.conic_dish(1/25.0, -1.0, 20.0, poly=[1.0e-6]), np.eye(4))
   b.add_shape(m, prim.conic_dish(30.0/18.0**2, -(1-18.0**2/30.0**2), 15.0), prim.translation(45, 0, 0))
   b.add_shape(m, prim.conic_dish(10.0/(26.0**2-100.0), -(2.6**2), 15.0, inner_radius=2.0), prim.translation(-45, 0, 0) @ prim.rotation((1, 0, 0), 0.2))
   l = b.add_group('L', 'L', optical_type='Lens', refractive_index=1.5)
-  lens = prim.conic_dish(1/40.0, -1.0, 8.0) + [prim._face(prim.plane_surface((0, 0, 0.8), (1, 0, 0), (0, 1, 0)), [prim._circle_loop(8.0)], shell_key=None)]
+  # the lens carries even-asphere terms on top of its paraboloid (ODW_SEG_ASPHERE): Newton from the conic crossing
+  lens = prim.conic_dish(1/40.0, -1.0, 8.0, poly=[-1.5e-5, 4.0e-8]) + [prim._face(prim.plane_surface((0, 0, 0.8-1.5e-5*8.0**4+4.0e-8*8.0**6), (1, 0, 0), (0, 1, 0)), [prim._circle_loop(8.0)], shell_key=None)]
   for f in lens:
     f.shell_key = 1
   b.add_shape(l, lens, prim.translation(0, 0, 30))
@@ -205,6 +284,7 @@ def test_gpu_conicoid_parity_with_oracle(gpu_engine, oracle):
   b.add_shape(a, prim.disc(300.0), prim.translation(0, 0, 90))
   scene = b.build()
   assert sum(int(f['kind']) == sc_mod.SURF_CONICOID for f in scene.faces) == 4
+  assert sum(int(k) == sc_mod.SEG_ASPHERE for k in scene.segs['kind']) == 2
   rng = np.random.default_rng(21)
   n = 20000
   o = np.column_stack([rng.uniform(-60, 60, n), rng.uniform(-18, 18, n), np.full(n, 80.0)])
