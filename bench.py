@@ -179,11 +179,30 @@ def run_reference(args, rank, world):
               cpu_baseline=dict(value=value, unit=UNIT, cores=ncores, kind='port', sample=sample),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
               gpu_launches=0)
-  print(json.dumps(line), flush=True)
+  emit(line)
+
+
+_RESULT_OUT = None
+
+def claim_stdout():
+  '''
+  The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+  image sets NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the whole run and the result line goes
+  to a private duplicate of the original stdout.
+  '''
+  global _RESULT_OUT
+  if _RESULT_OUT is None:
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+def emit(line):
+  print(json.dumps(line), file=_RESULT_OUT or sys.stdout, flush=True)
 
 
 def main():
   args = parse_args()
+  claim_stdout()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -201,7 +220,6 @@ def main():
   torch.cuda.set_device(local_rank)
   distributed = world > 1
   if distributed:
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # NCCL's version banner must not share stdout with the JSON line
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
   n_rays = int(args.rays)
@@ -329,7 +347,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:      # reported at N=1 only (rank 0)
       cb, _, _ = cpu_baseline(sim, 1, args.cpu_sample_rays, 'scalar C restatement (oracle/odw_oracle.c), 1 thread')
       line['cpu_baseline'] = cb
-    print(json.dumps(line), flush=True)
+    emit(line)
   if distributed:
     dist.barrier()
     dist.destroy_process_group()
