@@ -250,6 +250,41 @@ def test_edge_cases_empty_overflow_and_errors(gpu_engine, sims):
     engine.Engine(99)
 
 
+def test_kernel_instances_agree(gpu_engine, sims):
+  '''
+  The Monte-Carlo kernel exists in several feature sets (FEAT_* in csrc/odw_trace.cuh: none / sequential / all) and the
+  host picks the leanest that covers a launch.  Same rays through the lean and the full instance (forced by asking for a
+  device histogram, FEAT_BIN) must give the same hit list bit for bit; likewise sequential scene vs the same scene
+  with a histogram.  Also covers dynamic ray claiming: one request, different launch sizes and stream counts.
+  '''
+  n = 300000
+  ref = {}
+  for name in ('lensesAndMirrors', 'lensesAndMirrorsSequential'):
+    sim = sims(name)
+    absorber = len(sim.scene.groups)-1
+    spec = dict(group=absorber, nu=8, nv=8, origin=(-68.86, 0, 73), uaxis=(1, 0, 0), vaxis=(0, 1, 0), u_range=(-1, 1), v_range=(-1, 1))
+    ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+    with ds.trace_mc(dsrc, sim.cfg(record_all_hits=True, hit_capacity=9*n), SEED, 123, n) as res:
+      lean, c0 = res.hits(sort=True), res.counts
+    with ds.trace_mc(dsrc, sim.cfg(record_all_hits=True, hit_capacity=9*n, binnings=[spec]), SEED, 123, n) as res:
+      full, c1 = res.hits(sort=True), res.counts
+    assert c0['segments'] == c1['segments'] and c0['hits'] == c1['hits'] > 6*n
+    for key in lean:
+      assert np.array_equal(lean[key], full[key]), (name, key)
+    ref[name] = full
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  for wave, streams in (('4096', '1'), ('65536', '3'), ('1000003', '8')):
+    os.environ['ODW_RAYS_PER_LAUNCH'], os.environ['ODW_STREAMS'] = wave, streams
+    try:
+      with ds.trace_mc(dsrc, sim.cfg(record_all_hits=True, hit_capacity=9*n), SEED, 123, n) as res:
+        h = res.hits(sort=True)
+    finally:
+      del os.environ['ODW_RAYS_PER_LAUNCH'], os.environ['ODW_STREAMS']
+    for key in h:
+      assert np.array_equal(h[key], ref['lensesAndMirrors'][key]), (wave, key)
+
+
 def test_count_only_and_histogram_modes(gpu_engine, oracle, sims):
   'device binning == numpy.histogram2d of the stored hit list (reference jupyter_utils/histogram.py:54 semantics)'
   sim = sims('lensesAndMirrors')
