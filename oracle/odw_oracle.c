@@ -17,12 +17,13 @@
  *              the reference delegates them to FreeCAD/OpenCASCADE (unpinned "system FreeCAD / latest AppImage",
  *              benchmark files written by FreeCAD 1.1R20260725), absent here, and its tests hold no golden vector for
  *              a single ray.  They are anchored on hand-derived known answers for the benchmark scenes
- *              (tests/test_oracle_known_answers.py) and on the reference's statistical assertions.
+ *              (tests/test_oracle_known_answers.py), on the focal properties of the conics of
+ *              revolution (tests/test_conicoid.py) and on the reference's statistical assertions.
  *
  * Each function cites the reference code it follows (paths relative to
  * /root/reference/freecad/optics_design_workbench/).  Where the reference calls OCC
  * (Curve.intersect(Surface), distToShape, normalAt) the closed-form equivalent for
- * plane / cylinder / cone / sphere / torus is written out.
+ * plane / cylinder / cone / sphere / torus / conic of revolution (+ even-asphere terms) is written out.
  *
  * Plain scalar C, one ray at a time, same loop structure as the reference:
  * groups -> shells (bbox cull, sorted) -> faces (bbox cull, sorted) -> all line/surface points ->
