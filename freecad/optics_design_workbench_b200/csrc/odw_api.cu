@@ -29,7 +29,7 @@ extern "C" cudaError_t odw_wf_iota(unsigned int* v, unsigned int n, cudaStream_t
 extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, size_t cap, unsigned int* keys_out, const unsigned int* iota,
                                    unsigned int* order, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_tail(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, int bounce, cudaStream_t st);
-extern "C" int odw_wf_traverse_occupancy(void);
+extern "C" int odw_wf_traverse_occupancy(int n_nodes);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -243,9 +243,18 @@ struct BvhBuilder {
 
   // Inner nodes in device layout: both child boxes in the parent (see BvhNode2).
   std::vector<BvhNode2> wide() const {
+    // inner nodes are numbered breadth-first: the first k device nodes are the top of the tree, which is what the wavefront
+    // traversal stages in shared memory when the whole tree does not fit
     std::vector<int> index(nodes.size(), -1);
     int n_inner = 0;
-    for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].count == 0) index[i] = n_inner++;
+    if (!nodes.empty() && nodes[0].count == 0) {
+      std::vector<int> queue(1, 0);
+      for (size_t h = 0; h < queue.size(); ++h) {
+        const int i = queue[h];
+        index[(size_t)i] = n_inner++;
+        for (int k = 0; k < 2; ++k) if (nodes[(size_t)nodes[(size_t)i].left + k].count == 0) queue.push_back(nodes[(size_t)i].left + k);
+      }
+    }
     std::vector<BvhNode2> out((size_t)std::max(n_inner, 1));
     auto set_child = [&](BvhNode2& w, int k, const BvhNode* c) {
       float* lo = k ? w.lo1 : w.lo0; float* hi = k ? w.hi1 : w.hi0;
@@ -816,7 +825,7 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
   } else sort_bounces = 0;
   unsigned int tail = 8192;
   if (const char* w = getenv("ODW_WAVEFRONT_TAIL")) { long long v = atoll(w); if (v >= 0) tail = (unsigned int)v; }
-  const int blocks = eng->sm_count*std::max(1, odw_wf_traverse_occupancy());
+  const int blocks = eng->sm_count*std::max(1, odw_wf_traverse_occupancy(q.scene.n_bvh_nodes));
   cudaStream_t st = eng->stream;
   unsigned int* host_n = reinterpret_cast<unsigned int*>(&eng->pinned_counters[0]);     // page-locked scratch
   cudaError_t e = odw_wf_generate(&q, mc, pool_a, cap, bound, n0, st);

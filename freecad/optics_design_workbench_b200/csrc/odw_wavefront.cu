@@ -108,11 +108,26 @@ __device__ __forceinline__ int bvh_pop(BvhTrav& tr, const BvhStack& st) {
 }
 
 // cur is an inner node: test both children, go to the nearer one, stack the other
-__device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const BvhStack& st, const TraceParams& p) {
+// Nodes staged in shared memory: node n = 16-byte words 4n .. 4n+3.  Lanes of a warp read the SAME word of DIFFERENT nodes, and a
+// 64-byte record offers only two bank positions per word, so the words are swizzled: word w lives in row w / 8 at position
+// (w % 8) ^ (row % 8), which spreads the lanes over all eight 16-byte bank groups.
+__device__ __forceinline__ int staged_word(int node, int k) {
+  const int row = node >> 1, q = ((node & 1) << 2) | k;
+  return (row << 3) | (q ^ (row & 7));
+}
+
+__device__ __forceinline__ void bvh_inner_step(BvhTrav& tr, const BvhStack& st, const TraceParams& p, const float4* s_nodes, int n_staged) {
   const float sx = tr.sx, sy = tr.sy, sz = tr.sz, ix = tr.ix, iy = tr.iy, iz = tr.iz;
-  const float4* q = reinterpret_cast<const float4*>(p.scene.bvh + tr.cur);
-  const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-  const int4 d = __ldg(reinterpret_cast<const int4*>(q + 3));
+  float4 a, b, c; int4 d;
+  if (tr.cur < n_staged) {
+    a = s_nodes[staged_word(tr.cur, 0)]; b = s_nodes[staged_word(tr.cur, 1)]; c = s_nodes[staged_word(tr.cur, 2)];
+    const float4 dd = s_nodes[staged_word(tr.cur, 3)];
+    d = make_int4(__float_as_int(dd.x), __float_as_int(dd.y), __float_as_int(dd.z), __float_as_int(dd.w));
+  } else {
+    const float4* q = reinterpret_cast<const float4*>(p.scene.bvh + tr.cur);
+    a = __ldg(q); b = __ldg(q + 1); c = __ldg(q + 2);
+    d = __ldg(reinterpret_cast<const int4*>(q + 3));
+  }
   // child 0: lo = (a.x, a.y, a.z), hi = (a.w, b.x, b.y);  child 1: lo = (b.z, b.w, c.x), hi = (c.y, c.z, c.w)
   float ta = (a.x - sx)*ix, tb = (a.w - sx)*ix;
   float n0 = fminf(ta, tb), f0 = fmaxf(ta, tb);
@@ -187,10 +202,21 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 #ifndef ODW_WF_BLOCKS
 #define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
 #endif
+#ifndef ODW_WF_THREADS
+#define ODW_WF_THREADS 1024     // one CTA per SM: ONE staged copy of the tree's top serves all 32 warps of the SM
+#endif
 template <int FEAT>
-__global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
+__global__ void __launch_bounds__(ODW_WF_THREADS, (ODW_WF_BLOCKS*256)/ODW_WF_THREADS) wf_traverse(const __grid_constant__ TraceParams p, WfPool pool, double2* hits,
                                                       unsigned int n, unsigned int* fetch_counter, const unsigned int* __restrict__ order,
-                                                      WfPool ordered) {
+                                                      WfPool ordered, int n_staged) {
+  // the first n_staged nodes (breadth-first order: the top of the tree, all of it for hugeArray) live in shared memory: an inner
+  // step then waits for a shared-memory read instead of an L1 / L2 round trip, which is what this kernel spends its time on
+  extern __shared__ __align__(16) float4 s_nodes[];
+  {
+    const float4* g = reinterpret_cast<const float4*>(p.scene.bvh);
+    for (int w = threadIdx.x; w < 4*n_staged; w += blockDim.x) s_nodes[staged_word(w >> 2, w & 3)] = __ldg(g + w);
+    __syncthreads();
+  }
   const unsigned int lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;
   unsigned int slot = 0;
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(256, ODW_WF_BLOCKS) wf_traverse(const __grid_c
     if (!__any_sync(0xffffffffu, have)) break;
     // descend: every lane walks inner nodes until it holds a leaf or has finished
     while (__any_sync(0xffffffffu, have && tr.cur >= 0)) {
-      if (have && tr.cur >= 0) bvh_inner_step(tr, st, p);
+      if (have && tr.cur >= 0) bvh_inner_step(tr, st, p, s_nodes, n_staged);
     }
     // leaves: exact face tests, all lanes that hold one together
     if (have && tr.cur < TRAV_DONE) bvh_leaf_step<FEAT>(tr, st, p, s, dn, medium, seq_index);
@@ -338,13 +364,30 @@ extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool
   return cudaGetLastError();
 }
 
+// nodes of the tree that fit the shared memory one CTA may use (the rest is read through L1 / L2)
+static int wf_staged_nodes(int n_nodes) {
+  // shared memory and L1 share 256 KB per SM: 96 KB of nodes (1536, all of hugeArray's 1499) leave the L1 enough room for the
+  // traversal stacks and the face records
+  const int per_cta = ODW_WF_THREADS >= 1024 ? 96*1024 : (ODW_WF_THREADS >= 512 ? 96*1024 : 48*1024);
+  int n = per_cta/(int)sizeof(BvhNode2);
+  n = n < n_nodes ? n : n_nodes;
+  return n & ~1;                       // whole rows of the swizzle (two nodes per 128-byte row)
+}
+
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
                                        unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int need, int blocks, cudaStream_t st) {
-  const unsigned int want = (n + 255u)/256u, grid = (unsigned int)blocks < want ? (unsigned int)blocks : want;
+  const unsigned int want = (n + ODW_WF_THREADS - 1u)/ODW_WF_THREADS, grid = (unsigned int)blocks < want ? (unsigned int)blocks : want;
   const WfPool pl = make_pool(pool, cap), po = make_pool(order ? pool_ordered : pool, cap);
+  const int n_staged = wf_staged_nodes(p->scene.n_bvh_nodes);
+  const size_t smem = (size_t)n_staged*sizeof(BvhNode2);
   // need: FEAT_* bits of the launch; only FEAT_EXT (even-asphere faces) concerns the traversal
-  if (need & FEAT_EXT) wf_traverse<FEAT_ALL><<<grid, 256, 0, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po);
-  else wf_traverse<0><<<grid, 256, 0, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po);
+  if (need & FEAT_EXT) {
+    cudaFuncSetAttribute(wf_traverse<FEAT_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wf_traverse<FEAT_ALL><<<grid, ODW_WF_THREADS, smem, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po, n_staged);
+  } else {
+    cudaFuncSetAttribute(wf_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wf_traverse<0><<<grid, ODW_WF_THREADS, smem, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po, n_staged);
+  }
   return cudaGetLastError();
 }
 
@@ -380,8 +423,10 @@ extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, s
   return cub::DeviceRadixSort::SortPairs(temp, *temp_bytes, (const unsigned int*)pl.key, keys_out, iota, order, (int)n, 0, ODW_SORT_KEY_BITS, st);
 }
 
-extern "C" int odw_wf_traverse_occupancy(void) {
+extern "C" int odw_wf_traverse_occupancy(int n_nodes) {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_traverse<0>, 256, 0);
+  const size_t smem = (size_t)wf_staged_nodes(n_nodes)*sizeof(BvhNode2);
+  cudaFuncSetAttribute(wf_traverse<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wf_traverse<0>, ODW_WF_THREADS, smem);
   return nb;
 }
