@@ -68,3 +68,23 @@ def test_product_package_does_not_import_oracle():
         text = open(os.path.join(dirpath, f)).read()
         assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f'{f} imports oracle'
         assert 'odw_oracle' not in text, f'{f} references the oracle library'
+
+
+def test_kernel_instance_selection():
+  '''
+  Which instance of the trace kernel a launch gets (csrc/odw_kernels.cu pick_feat; FEAT_* bits: 1 gratings / scatter / absorption /
+  aspheres, 2 surface source, 4 sequential mode, 8 device binning): the lean one only when nothing is needed, the sequential
+  one for sequential mode alone, the full one otherwise and for explicit ray lists and BVH scenes.  Host logic, no GPU call.
+  '''
+  import ctypes as C
+  from freecad.optics_design_workbench_b200 import engine
+  L = engine.load_library()
+  L.odw_trace_instance.restype = C.c_int
+  L.odw_trace_instance.argtypes = [C.c_bool, C.c_bool, C.c_int]
+  assert L.odw_trace_instance(True, False, 0) == 0
+  assert L.odw_trace_instance(True, False, 4) == 4
+  for need in (1, 2, 8, 5, 6, 12, 15):
+    assert L.odw_trace_instance(True, False, need) == 15, need
+  for need in (0, 4, 15):
+    assert L.odw_trace_instance(False, False, need) == 15       # explicit ray lists
+    assert L.odw_trace_instance(True, True, need) == 15         # BVH scenes
