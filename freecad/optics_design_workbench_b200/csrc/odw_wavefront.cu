@@ -202,6 +202,9 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Trace
 #ifndef ODW_WF_BLOCKS
 #define ODW_WF_BLOCKS 4          // 64 registers, 32 warps per SM: the traversal is bound by node-fetch latency (measured 2, 3, 4, 5: 2.03, 2.09, 2.19, 2.03e9 segments/s)
 #endif
+#ifndef ODW_WF_FETCH_MIN
+#define ODW_WF_FETCH_MIN 16       // measured 1 / 4 / 8 / 16 / 24 / 32: 3.41 / 3.44 / 3.48 / 3.53 / 3.47 / 2.90e9 segments/s on hugeArray
+#endif
 #ifndef ODW_WF_THREADS
 #define ODW_WF_THREADS 1024     // one CTA per SM: ONE staged copy of the tree's top serves all 32 warps of the SM
 #endif
@@ -228,7 +231,8 @@ __global__ void __launch_bounds__(ODW_WF_THREADS, (ODW_WF_BLOCKS*256)/ODW_WF_THR
   const BvhStack st = { stack_ref, stack_t };
   for (;;) {
     const unsigned int need = __ballot_sync(0xffffffffu, !have);
-    if (need && !exhausted) {
+    // A fetch stalls the whole warp for a trip to the pool, so it waits until ODW_WF_FETCH_MIN lanes are free (or none has work)
+    if (!exhausted && (__popc(need) >= ODW_WF_FETCH_MIN || need == 0xffffffffu)) {
       // lanes without a ray take the next pool slots: one atomic per warp
       const int leader = __ffs(need) - 1;
       unsigned int base = 0;
