@@ -50,7 +50,7 @@ struct odw_engine {
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_WAVE_STREAMS] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_trace[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-  Counters* pinned_counters = nullptr;  // [2], page-locked
+  Counters* pinned_counters = nullptr;  // [3], page-locked: [0], [1] chunk counters of odw_trace_mc_host, [2] scratch of the wavefront loop
   std::string name;
   // size-keyed pool so that per-call result buffers are not re-allocated every step
   std::multimap<size_t, void*> pool;
@@ -155,8 +155,9 @@ extern "C" int odw_engine_create(int device_id, odw_engine** out) {
   CU(cudaEventCreate(&eng->ev0));
   CU(cudaEventCreate(&eng->ev1));
   for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&eng->ev_trace[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&eng->ev_copy[i], cudaEventDisableTiming)); }
-  CU(cudaHostAlloc((void**)&eng->pinned_counters, 2*sizeof(Counters), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&eng->pinned_counters, 3*sizeof(Counters), cudaHostAllocDefault));
   CU(cudaMalloc((void**)&eng->wave_counters, odw_engine::MAX_WAVES*sizeof(unsigned long long)));
+  CU(cudaMemset(eng->wave_counters, 0, odw_engine::MAX_WAVES*sizeof(unsigned long long)));
   *out = eng;
   return ODW_OK;
 }
@@ -827,7 +828,7 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
   if (const char* w = getenv("ODW_WAVEFRONT_TAIL")) { long long v = atoll(w); if (v >= 0) tail = (unsigned int)v; }
   const int blocks = eng->sm_count*std::max(1, odw_wf_traverse_occupancy(q.scene.n_bvh_nodes));
   cudaStream_t st = eng->stream;
-  unsigned int* host_n = reinterpret_cast<unsigned int*>(&eng->pinned_counters[0]);     // page-locked scratch
+  unsigned int* host_n = reinterpret_cast<unsigned int*>(&eng->pinned_counters[2]);     // page-locked scratch of its own: [0], [1] hold chunk counters the host may not have read yet
   cudaError_t e = odw_wf_generate(&q, mc, pool_a, cap, bound, n0, st);
   if (launches) ++*launches;
   unsigned int n = q.max_isect > 0 ? n0 : 0;
@@ -879,12 +880,14 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   int n_streams = odw_engine::DEFAULT_WAVE_STREAMS;
   if (const char* w = getenv("ODW_STREAMS")) n_streams = std::max(1, std::min(odw_engine::MAX_WAVE_STREAMS, atoi(w)));
   if ((sc->use_bvh && sc->wavefront) || p.n_rays <= wave) n_streams = 1;
+  // The claim counters are zeroed on the engine stream BEFORE the fork event is recorded, so every wave stream is
+  // ordered after the memset (and, through the join of the previous request, after every kernel that used the counters).
+  if (!(sc->use_bvh && sc->wavefront) && p.n_rays > 0)
+    CU(cudaMemsetAsync(eng->wave_counters, 0, ((p.n_rays + wave - 1)/wave)*sizeof(unsigned long long), eng->stream));
   if (n_streams > 1) {
     CU(cudaEventRecord(eng->ev_fork, eng->stream));
     for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
   }
-  if (!(sc->use_bvh && sc->wavefront) && p.n_rays > 0)      // before the fork: every wave stream sees its counter zeroed
-    CU(cudaMemsetAsync(eng->wave_counters, 0, ((p.n_rays + wave - 1)/wave)*sizeof(unsigned long long), eng->stream));
   uint64_t wave_index = 0;
   for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
@@ -968,9 +971,17 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
   uint64_t chunk = 1ull << 23;
   if (const char* w = getenv("ODW_HOST_CHUNK")) { long long v = atoll(w); if (v > 0) chunk = (uint64_t)v; }
   chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(n_rays, 1));
+  // cfg->hit_capacity = rows the caller expects for the WHOLE range (0: two per ray); the per-chunk device lists get the
+  // same rows-per-ray ratio, so a caller that repeats the call with a larger capacity after ODW_EOVERFLOW (scenes that
+  // record more than two hits per ray: transparent detectors, record_all_hits) also gets larger device lists.  The chunk
+  // shrinks when that would take more than 2^27 rows per list (81 B per row, two lists).
+  uint64_t rows_per_ray = 2;
+  if (cfg->hit_capacity && n_rays) rows_per_ray = std::max<uint64_t>(1, (cfg->hit_capacity + n_rays - 1)/n_rays);
+  if (cfg->max_intersections > 0) rows_per_ray = std::min<uint64_t>(rows_per_ray, (uint64_t)cfg->max_intersections*std::max(1.0, src->max_intersections_scale) + 1);
+  while (chunk > (1ull << 16) && chunk*rows_per_ray > (1ull << 27)) chunk >>= 1;
   odw_trace_cfg ccfg = *cfg;
   ccfg.store_hits = 1;
-  ccfg.hit_capacity = std::max<uint64_t>(1024, 2*chunk);
+  ccfg.hit_capacity = std::max<uint64_t>(1024, rows_per_ray*chunk);
   odw_result* r[2] = {nullptr, nullptr};
   TraceParams p[2];
   auto cleanup = [&]() { odw_result_destroy(r[0]); odw_result_destroy(r[1]); };

@@ -285,6 +285,20 @@ class Engine:
       setattr(view, name, ptr.value)
     return arrays, view
 
+  def free_pinned(self, view):
+    'give the page-locked columns behind `view` (from pinned_hit_arrays) back; the numpy arrays over them die with it'
+    for name in ('points', 'directions', 'powers', 'is_entering', 'ray_index', 'group', 'bounce', 'face_id', 'medium'):
+      ptr = getattr(view, name)
+      ptr = ptr if isinstance(ptr, int) else getattr(ptr, 'value', None)
+      if not ptr:
+        continue
+      for k, have in enumerate(self._pinned):
+        if have.value == ptr:
+          load_library().odw_host_free(self._h, have)
+          del self._pinned[k]
+          break
+      setattr(view, name, None)
+
   def scene(self, scene):
     return DeviceScene(self, scene)
 

@@ -229,14 +229,19 @@ class GenericSourceProxy:
     keys = ctx.sim.settings.get('store_hit_keys', [])
     columns = ['points', 'directions', 'powers', 'is_entering'] + (['group'] if len(recording) != 1 else []) + (['ray_index'] if keys else [])
     capacity = max(1024, 2*n)
+    # a ray records at most one hit per intersection: that bounds the retries below
+    ceiling = max(1024, n*(int(float(ctx.sim.settings['MaxIntersections'])*float(obj.get('MaxIntersectionsScale', 1.0)))+1))
     while True:
       arrays, view = ctx.pinned_hits(capacity, tuple(columns))
-      counts, got = ctx.device_scene.trace_mc_host(dsrc, ctx.cfg(obj, store_hits=True), ctx.seed, first, n, view)
+      # hit_capacity = rows expected for the whole range: the engine sizes its per-chunk device lists by the same ratio
+      counts, got = ctx.device_scene.trace_mc_host(dsrc, ctx.cfg(obj, store_hits=True, hit_capacity=capacity), ctx.seed, first, n, view)
       if not counts['hits_dropped']:
         break
+      if capacity >= ceiling:
+        raise RuntimeError(f"{counts['hits_dropped']} hits dropped although the hit buffers hold one row per possible intersection")
       # more recorded hits than rows (transparent detectors record two hits per pass): the same ray range again with
       # room for all of them — the Philox stream makes the repeat identical
-      capacity = max(4*capacity, int(counts['hits'])+1024)
+      capacity = min(ceiling, max(4*capacity, int(counts['hits'])+1024))
     hits = {k: v[:got] for k, v in arrays.items()}
     if 'group' not in hits:
       hits['group'] = np.full(got, int(recording[0]), dtype=np.int32)

@@ -88,6 +88,9 @@ class SimulationContext:
     'page-locked hit arrays of at least `capacity` rows with these columns, reused from call to call'
     have = self._pinned.get(columns)
     if have is None or have[2] < capacity:
+      if have is not None and hasattr(self.engine, 'free_pinned'):
+        self.engine.free_pinned(have[1])                 # the superseded, smaller buffers go back to the driver
+        del self._pinned[columns]
       if hasattr(self.engine, 'pinned_hit_arrays'):
         arrays, view = self.engine.pinned_hit_arrays(capacity, columns)
       else:                                              # engines without page-locked memory (the CPU test double)

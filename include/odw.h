@@ -307,7 +307,9 @@ int  odw_trace_mc(odw_scene*, odw_source*, const odw_trace_cfg*, uint64_t seed,
 
 /* Monte-Carlo trace with the hit list delivered straight into HOST arrays (page-locked memory recommended): the
  * range is traced in chunks and the device->host copy of chunk c overlaps the trace of chunk c+1.  Rows are appended
- * in chunk order (unsorted inside a chunk).  *n_hits_out = rows written; counts_out may be NULL. */
+ * in chunk order (unsorted inside a chunk).  *n_hits_out = rows written; counts_out may be NULL.
+ * cfg->hit_capacity = rows expected for the whole range (0 = two per ray): the per-chunk device hit lists are sized by
+ * the same rows-per-ray ratio; hits that fit neither them nor host->capacity are counted in hits_dropped (ODW_EOVERFLOW). */
 int  odw_trace_mc_host(odw_scene*, odw_source*, const odw_trace_cfg*, uint64_t seed, uint64_t first_ray, uint64_t n_rays,
                        const odw_hits_view* host, uint64_t* n_hits_out, odw_counts* counts_out);
 

@@ -329,6 +329,66 @@ def test_host_delivery_equals_device_hit_list(gpu_engine, sims):
   assert got == 1000 and counts['hits_dropped'] == c['hits']-1000
 
 
+def test_host_delivery_many_waves_on_many_streams(gpu_engine, sims, monkeypatch):
+  """
+  Several chunks of several launch waves rotating over 4 streams: the per-wave claim counters are zeroed on the engine
+  stream BEFORE the fork, so no wave stream can read the stale counters of the previous chunk (which would skip or
+  repeat a whole wave).  Repeated, because the failure was a race.
+  """
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n = 300000
+  with ds.trace_mc(dsrc, sim.cfg(hit_capacity=2*n), SEED, 7, n) as res:
+    dev, c = res.hits(sort=True), res.counts
+  monkeypatch.setenv('ODW_HOST_CHUNK', '65536')
+  monkeypatch.setenv('ODW_RAYS_PER_LAUNCH', '8192')
+  monkeypatch.setenv('ODW_STREAMS', '4')
+  arrays = _abi.HitArrays(n+16)
+  for _ in range(5):
+    counts, got = ds.trace_mc_host(dsrc, sim.cfg(), SEED, 7, n, arrays.view)
+    assert counts['waves'] >= 4*8 + 4
+    assert got == c['hits'] and counts['segments'] == c['segments'] and counts['escaped'] == c['escaped']
+    host = arrays.trimmed(got, sort=True)
+    for key in dev:
+      assert np.array_equal(host[key], dev[key]), key
+
+
+def test_host_delivery_wavefront_chunks_keep_their_counters(gpu_engine, sims, monkeypatch):
+  'BVH / wavefront scenes: the per-bounce survivor count has its own pinned word, the chunk counters stay intact'
+  monkeypatch.setenv('ODW_BVH', '1')
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n = 200000
+  with ds.trace_mc(dsrc, sim.cfg(hit_capacity=2*n), SEED, 0, n) as res:
+    dev, c = res.hits(sort=True), res.counts
+  monkeypatch.setenv('ODW_HOST_CHUNK', '50000')
+  arrays = _abi.HitArrays(n+16)
+  counts, got = ds.trace_mc_host(dsrc, sim.cfg(), SEED, 0, n, arrays.view)
+  assert counts['segments'] == c['segments'] and got == c['hits'] and counts['escaped'] == c['escaped']
+  host = arrays.trimmed(got, sort=True)
+  for key in dev:
+    assert np.array_equal(host[key], dev[key]), key
+
+
+def test_host_delivery_more_than_two_hits_per_ray(gpu_engine, sims, monkeypatch):
+  'hit_capacity sizes the per-chunk device lists too: a scene recording ~7 hits per ray is delivered complete'
+  sim = sims('lensesAndMirrors')
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  n = 100000
+  with ds.trace_mc(dsrc, sim.cfg(hit_capacity=8*n, record_all_hits=True), SEED, 0, n) as res:
+    dev, c = res.hits(sort=True), res.counts
+  assert c['hits'] > 6*n and c['hits_dropped'] == 0
+  monkeypatch.setenv('ODW_HOST_CHUNK', '30000')
+  arrays = _abi.HitArrays(8*n)
+  counts, got = ds.trace_mc_host(dsrc, sim.cfg(record_all_hits=True), SEED, 0, n, arrays.view)       # default: two rows per ray
+  assert counts['hits_dropped'] > 0 and counts['hits'] == c['hits']
+  counts, got = ds.trace_mc_host(dsrc, sim.cfg(record_all_hits=True, hit_capacity=8*n), SEED, 0, n, arrays.view)
+  assert counts['hits_dropped'] == 0 and got == c['hits']
+  host = arrays.trimmed(got, sort=True)
+  for key in dev:
+    assert np.array_equal(host[key], dev[key]), key
+
+
 def test_range_splitting_is_invariant(gpu_engine, sims):
   'Philox counter = global ray index: tracing [0,n) equals tracing [0,k) and [k,n) (GPU-count invariance, SURVEY §8e)'
   sim = sims('lensesAndMirrors')
