@@ -434,12 +434,18 @@ static void fill_dface(const odw_face& f, const odw_trimseg* segs, bool fast_pat
         d.flags |= DFACE_FAST | DFACE_DISC; d.c0 = dot(d.o, d.z); d.c1 = dot(d.o, d.x); d.c2 = dot(d.o, d.y);
         d.umin = c.a[0]; d.vmin = c.a[1]; d.umax = c.a[2]; d.vmax = c.a[2];
       } else if (f.kind == ODW_SURF_SPHERE && (f.trim_kind == ODW_TRIM_NONE || (f.trim_kind == ODW_TRIM_UVBOX && full_u))) {
+        // axial window [c0, c1] of the zone; the tolerance is a distance ALONG the sphere (ray.py:426 measures the distance to
+        // the trimmed face), i.e. tol*cos(v) in the axial coordinate: aux[0], aux[1] carry the two cosines.  A bound at a pole
+        // is no bound (and must not reject a hit whose axial coordinate exceeds R by a rounding error).
         d.flags |= DFACE_FAST;
         const bool whole = f.trim_kind == ODW_TRIM_NONE;
-        d.c0 = whole ? -1e300 : f.p0*std::sin(f.uv_min[1]);
-        d.c1 = whole ?  1e300 : f.p0*std::sin(f.uv_max[1]);
+        const bool lo_open = whole || f.uv_min[1] <= -ODW_TWO_PI/4 + 1e-12, hi_open = whole || f.uv_max[1] >= ODW_TWO_PI/4 - 1e-12;
+        d.c0 = lo_open ? -1e300 : f.p0*std::sin(f.uv_min[1]);
+        d.c1 = hi_open ?  1e300 : f.p0*std::sin(f.uv_max[1]);
+        d.aux[0] = lo_open ? 0.0 : std::cos(f.uv_min[1]);
+        d.aux[1] = hi_open ? 0.0 : std::cos(f.uv_max[1]);
       } else if (f.kind == ODW_SURF_CYLINDER && f.trim_kind == ODW_TRIM_UVBOX && full_u) {
-        d.flags |= DFACE_FAST; d.c0 = f.uv_min[1]; d.c1 = f.uv_max[1];
+        d.flags |= DFACE_FAST; d.c0 = f.uv_min[1]; d.c1 = f.uv_max[1]; d.aux[0] = d.aux[1] = 1.0;
       }
       }
     }

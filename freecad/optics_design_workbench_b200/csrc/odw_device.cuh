@@ -16,7 +16,8 @@ struct DFace {
   double o[3], x[3], y[3], z[3];
   double p0, p1;
   double umin, umax, vmin, vmax;
-  double aux[6];                   // conicoid with an ODW_SEG_ASPHERE record: aux[0..4] = coefficients of rho^4 .. rho^12, aux[5] = 1
+  double aux[6];                   // conicoid with an ODW_SEG_ASPHERE record: aux[0..4] = coefficients of rho^4 .. rho^12, aux[5] = 1;
+                                   // DFACE_FAST sphere zone / cylinder band: aux[0], aux[1] = axial share of the tolerance at c0, c1
   int32_t kind, trim, nsign, group;
   int32_t seg_first, seg_count, face_id, flags;
   unsigned long long seqmask[2];   // bit s set <=> the face's group is in SequentialModeElements step s

@@ -149,7 +149,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
     const double t = k ? tf : tn;
     if (t > tol && t < limit) {
       const double zc = fma(t, dz, wz);                              // axial coordinate of the hit
-      if (zc >= f.c0 - tol && zc <= f.c1 + tol) accept_hit(t, idx, f.group, medium, tol, h);
+      if (zc >= fma(-tol, f.aux[0], f.c0) && zc <= fma(tol, f.aux[1], f.c1)) accept_hit(t, idx, f.group, medium, tol, h);   // aux: axial share of the tolerance
     }
   }
 }

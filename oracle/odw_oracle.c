@@ -5,20 +5,25 @@
  * --impl reference legs may load it.  The product (libodw_b200.so) never links or calls it.
  *
  * PARITY STATUS
- *   pinned   — the bounce loop (traceRay state machine, getNormal flip / isEntering, mirror, snellsLaw incl. total
- *              reflection, lineGrating, power / medium / sequence-index bookkeeping, the powerTol and maxIntersections
- *              exits, what onRayHit hands to the store, the rotation formula of applyStochasticRayCorrections) and
- *              _makeRay: against the reference's OWN ray.py / point_source.py / optical_group.py executed under FreeCAD
- *              stand-ins with this file answering the two OpenCASCADE questions (tests/golden/make_traceray_golden.py,
- *              tests/test_traceray_golden.py);
+ *   pinned   — the whole per-ray path, against the reference's OWN Python executed here with NO method overridden
+ *              (tests/golden/make_traceray_golden.py -> tests/golden/traceray_golden.npz, tests/test_traceray_golden.py):
+ *              Ray.traceRay (state machine, power / medium / sequence-index bookkeeping, powerTol and maxIntersections
+ *              exits), Ray.findNearestIntersection (shell and face candidates by enlarged-box distance, the LINE test of
+ *              the boxes, the three acceptance rules, the maxRayLength shrink, the minDist + 2 tol filter, the "not the
+ *              current medium" preference), Ray.getNormal (flip / isEntering), mirror, snellsLaw incl. total reflection,
+ *              lineGrating, find.relevantOpticalObjects + getTracingSequence (ignore list, sequential filter),
+ *              raytracing_cache, OpticalGroupProxy.onRayHit, the rotation formula of applyStochasticRayCorrections and
+ *              PointSourceProxy._makeRay.  FreeCAD's Base types and the OpenCASCADE PRIMITIVES the loop calls (line x
+ *              untrimmed surface, point-to-edge and point-to-trimmed-face distance, bounding boxes, Surface.parameter,
+ *              normalAt) are numpy stand-ins (tests/freecad_stub.py, tests/occ_stub.py) that do not use this file;
  *            — the sampler (numeric mode), the fan grid and the fan ray list: against the importable reference
  *              `distributions` / `point_source` modules (tests/golden/make_sampler_golden.py, make_fan_golden.py).
- *   "parity unpinned" — the geometry answers themselves (line/surface intersection, trimmed-face membership, normals):
- *              the reference delegates them to FreeCAD/OpenCASCADE (unpinned "system FreeCAD / latest AppImage",
- *              benchmark files written by FreeCAD 1.1R20260725), absent here, and its tests hold no golden vector for
- *              a single ray.  They are anchored on hand-derived known answers for the benchmark scenes
- *              (tests/test_oracle_known_answers.py), on the focal properties of the conics of
- *              revolution (tests/test_conicoid.py) and on the reference's statistical assertions.
+ *   "parity unpinned" — OpenCASCADE's primitive answers on real BRep shapes only: the reference delegates them to
+ *              FreeCAD/OCC (unpinned "system FreeCAD / latest AppImage", benchmark files written by FreeCAD 1.1R20260725),
+ *              absent here AND on the GPU box (profiles/r02_freecad_probe.txt), and its tests hold no golden vector for
+ *              a single ray.  The stand-ins restate their documented behaviour with a different algorithm (polynomial
+ *              root finding); hand-derived known answers anchor them (tests/test_occ_stub.py,
+ *              tests/test_oracle_known_answers.py, tests/test_conicoid.py).
  *
  * Each function cites the reference code it follows (paths relative to
  * /root/reference/freecad/optics_design_workbench/).  Where the reference calls OCC

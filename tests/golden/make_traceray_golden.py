@@ -2,18 +2,23 @@
 Generates tests/golden/traceray_golden.npz by running the reference's OWN Python for the hot path
   PointSourceProxy._makeRay            (freecad_elements/point_source.py:411-460)
   Ray.traceRay / getNormal / mirror / snellsLaw / lineGrating   (freecad_elements/ray.py:36-281,455-539)
+  Ray.findNearestIntersection          (freecad_elements/ray.py:290-452: candidate shells by enlarged-box distance, the LINE
+                                        test of the boxes, face candidates, the three acceptance rules, the maxRayLength
+                                        shrink, the minDist + 2 tol filter, the "not the current medium" preference)
+  find.relevantOpticalObjects          (freecad_elements/find.py:79-104: ignore list, sequential filter) with
+  SimulationSettingsProxy.getTracingSequence (freecad_elements/simulation_settings.py:158-196)
+  raytracing_cache.cached*             (simulation/raytracing_cache.py:43-114)
   OpticalGroupProxy.onRayHit / applyStochasticRayCorrections   (freecad_elements/optical_group.py:206-209,279-323;
                                         its (theta, phi) draws come from the engine's Philox stream: numpy's process-seeded
                                         RNG of the reference is not reproducible — the rotation formula is the reference's)
 imported unmodified from /root/reference in the build container.  FreeCAD is absent, so
-  * FreeCAD.Vector / Rotation / Matrix are the stand-ins of tests/freecad_stub.py, and
-  * the two questions the reference asks OpenCASCADE — Ray.findNearestIntersection (ray.py:290-452) and
-    Surface.parameter / Face.normalAt inside getNormal (ray.py:463-466) — are answered by the oracle's geometry
-    (oracle_find_nearest / oracle_face_normal).
-Everything else — the bounce loop state machine, power / medium / sequence-index bookkeeping, the maxIntersections and
-powerTol exits, isEntering, the interaction formulas, what is handed to the result store — is the reference's code.
-The golden therefore pins the oracle's (and the CUDA kernel's) restatement of ray.py:36-281 and point_source.py:411-460
-GIVEN the geometry answers; the geometry itself stays anchored on the hand-derived known answers.
+  * FreeCAD.Vector / Rotation / Matrix are the stand-ins of tests/freecad_stub.py,
+  * the document is a list of plain objects (optical groups, one settings object) behind simulation.simulatingDocument(),
+  * the OpenCASCADE primitives the loop calls — Part.makeLine, Curve.intersect(Surface), Part.Vertex.distToShape(edge | face),
+    BoundBox.isInside / closestPoint / enlarge / intersect, Surface.parameter, Face.normalAt — are the stand-ins of
+    tests/occ_stub.py (numpy; polynomial root finding, not the closed forms of the oracle or the kernels; no use of oracle/).
+NO method of the reference's Ray is overridden: the golden holds what the reference's code decides, given OCC-primitive
+answers only.  What stays unpinned is OpenCASCADE itself (the primitive answers on real BRep shapes).
 Run here only (/root/reference does not exist on the GPU box):  python tests/golden/make_traceray_golden.py
 '''
 import os, sys, types
@@ -25,6 +30,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
 
 import freecad_stub
 freecad_stub.install()
+import occ_stub
+occ_stub.install(sys.modules['Part'])
 from freecad_stub import Vector, Matrix
 from make_fan_golden import load_reference_point_source
 import traceray_cases as cases
@@ -69,23 +76,45 @@ def make_objects(og, scene):
   return objs
 
 
-def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=()):
+class Document:
+  'what simulation.simulatingDocument() returns: find._allObjects walks .Objects (find.py:24-56)'
+  def __init__(self, objects):
+    self.Objects = list(objects)
+
+
+def make_settings(ss, cfg, objs, sequence):
+  'the active OpticalSimulationSettings object (simulation_settings.py:20-77), read by find.activeSimulationSettings'
+  st = Obj(Name='OpticalSimulationSettings', Label='OpticalSimulationSettings', TypeId='Part::FeaturePython', Active=True,
+           Proxy=ss.SimulationSettingsProxy.__new__(ss.SimulationSettingsProxy),
+           MaxRayLength=cfg.cfg.max_ray_length, MaxIntersections=cfg.cfg.max_intersections,
+           DistanceTolerance=repr(float(cfg.cfg.dist_tol)), SequentialMode=bool(sequence))
+  st.isDerivedFrom = lambda type_id: False
+  st.addProperty = lambda ptype, name, group, doc: setattr(st, name, [])       # a new property list starts empty
+  for i, step in enumerate(sequence or []):
+    setattr(st, f'SequentialModeElements_{i:02d}', [objs[g] for g in step])
+  return st
+
+
+def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=(), sequence=None, frames=None, shape_scene=None):
   '''
   rays: list of reference Ray objects.  Returns per-ray segment lists and the hits handed to the store.
+  The reference's own findNearestIntersection / getNormal run on occ_stub shapes built from the scene's face table
+  (frames / shape_scene: the shapes live in the groups' own coordinates and are reached through gpM, pM).
   '''
   sa = _abi.SceneArgs(scene)
+  ss = sys.modules['odw_ref.freecad_elements.simulation_settings']
   identity = Matrix()
-
-  class Face:
-    'the (gpM, gpMi, face) triple of ray.py:455-480 with an analytic Surface.parameter / normalAt'
-    def __init__(self, index):
-      self.index, self.Surface, self._n = index, self, None
-    def parameter(self, point):
-      uv, n = oracle.face_normal(sa, self.index, list(point))
-      self._n = Vector(n)
-      return tuple(uv)
-    def normalAt(self, u, v):
-      return self._n
+  for o in objs:
+    o.TypeId = 'App::LinkGroupPython'
+    o.isDerivedFrom = lambda type_id: False
+    o.Shape = occ_stub.group_shape(shape_scene if shape_scene is not None else scene, o.group_index)
+    T, S = (frames or {}).get(o.group_index, (np.eye(4), np.eye(4)))
+    gpM, pM = Matrix(T), Matrix(S)
+    o.Proxy._getCoordinateTransformMatrices = lambda obj, m=(gpM, gpM.inverse(), pM, pM.inverse()): [m]
+  settings = make_settings(ss, cfg, objs, sequence)
+  sys.modules['odw_ref.simulation'].simulatingDocument = lambda: Document(objs + [settings])
+  sys.modules['odw_ref.simulation.raytracing_cache'].cacheClear()
+  light.IgnoredOpticalElements = [objs[g] for g in ignored]
 
   state = dict(ray=0, bounce=-1)
 
@@ -104,17 +133,17 @@ def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=()):
       return Draw(_o.group_index, which) if oracle.scatter_draw(sa, _o.group_index, which, 0, 0, 0, 0) else False
     o.Proxy._getVrv = get_vrv
 
-  class TracedRay(ray_mod.Ray):
-    def findNearestIntersection(self, start, direction, currentMedium, maxRayLength, distTol=None, sequenceIndex=None):
-      state['bounce'] += 1
-      fi, P = oracle.find_nearest(sa, cfg, list(start), list(direction), -1 if currentMedium is None else currentMedium.group_index,
-                                  maxRayLength, sequenceIndex, ignored)
-      if fi < 0:
-        return None
-      return objs[int(scene.faces[fi]['group'])], (identity, identity, Face(fi)), Vector(P)
+  found = []
 
-  settings = Obj(MaxRayLength=cfg.cfg.max_ray_length, MaxIntersections=cfg.cfg.max_intersections)
-  ray_mod.find = types.SimpleNamespace(activeSimulationSettings=lambda: settings)
+  class TracedRay(ray_mod.Ray):
+    'observes the reference method (bounce counter for the Philox draws, which face was chosen); changes nothing'
+    def findNearestIntersection(self, *a, **k):
+      state['bounce'] += 1
+      hit = ray_mod.Ray.findNearestIntersection(self, *a, **k)
+      if hit is not None:
+        found.append(hit[1][2].index)
+      return hit
+
   seg_p1, seg_p2, seg_power, seg_medium, seg_off = [], [], [], [], [0]
   hit_ray, hit_rows = [], []
   for i, r in enumerate(rays):
@@ -127,9 +156,12 @@ def run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=()):
     seg_off.append(len(seg_p1))
     hit_ray.extend([i]*len(store.rows))
     hit_rows.extend(store.rows)
+  assert len(found) == len(hit_rows)
   return dict(seg_p1=np.array(seg_p1).reshape(-1, 3), seg_p2=np.array(seg_p2).reshape(-1, 3), seg_power=np.array(seg_power),
               seg_medium=np.array(seg_medium, dtype=np.int32), seg_offsets=np.array(seg_off, dtype=np.int64),
               hit_ray=np.array(hit_ray, dtype=np.int64), hit_group=np.array([h[0] for h in hit_rows], dtype=np.int32),
+              hit_face_id=scene.faces['face_id'][np.array(found, dtype=np.int64)].astype(np.int32),
+              hit_face_row=np.array(found, dtype=np.int32),
               hit_points=np.array([h[1] for h in hit_rows]).reshape(-1, 3), hit_directions=np.array([h[2] for h in hit_rows]).reshape(-1, 3),
               hit_powers=np.array([h[3] for h in hit_rows]), hit_is_entering=np.array([h[4] for h in hit_rows], dtype=np.uint8))
 
@@ -156,18 +188,22 @@ def main():
     cfg = sim.cfg(record_all_hits=True, wavelength=float(rec['Wavelength']))
     objs = make_objects(og, sim.scene)
     ignored = [sim.scene.group_names.index(g) if isinstance(g, str) else int(g) for g in rec['ignored']]
-    res = run_case(ray_mod, oracle, sim.scene, objs, cfg, rays, light, ignored)
+    sc = sim.scene
+    sequence = [[int(g) for g in sc.seq_groups[a:b]] for a, b in zip(sc.seq_offsets[:-1], sc.seq_offsets[1:])] if cfg.cfg.sequential else None
+    res = run_case(ray_mod, oracle, sim.scene, objs, cfg, rays, light, ignored, sequence=sequence)
     out.update({f'{name}/{k}': v for k, v in res.items()})
     print(name, n, 'rays', len(res['seg_power']), 'segments', len(res['hit_powers']), 'interactions', flush=True)
   for name, (build, wavelengths) in cases.SYNTHETIC_CASES.items():
     scene, o, d, settings = build()
+    _, extras = cases.split_settings(settings)
     objs = make_objects(og, scene)
     for wl in wavelengths:
       key = name if len(wavelengths) == 1 else f'{name}@{wl:g}'
       cfg = cases.synthetic_cfg(settings, record_all_hits=True, wavelength=wl)
       light = Obj(Name='Source', Label='Source', Wavelength=wl, MaxRayLengthScale=1.0, MaxIntersectionsScale=1.0)
       rays = [ray_mod.Ray(light, Vector(a), Vector(b), wavelength=wl) for a, b in zip(o, d)]
-      res = run_case(ray_mod, oracle, scene, objs, cfg, rays, light)
+      res = run_case(ray_mod, oracle, scene, objs, cfg, rays, light, ignored=extras['ignored'] or (), sequence=extras['sequence'],
+                     frames=extras['frames'], shape_scene=extras['shape_scene'])
       out[key+'/origins'], out[key+'/directions'], out[key+'/wavelength'] = o, d, np.array(wl)
       out.update({f'{key}/{k}': v for k, v in res.items()})
       print(key, len(o), 'rays', len(res['seg_power']), 'segments', len(res['hit_powers']), 'interactions', flush=True)

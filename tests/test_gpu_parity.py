@@ -10,6 +10,7 @@ grows ~10x per bounce, so positions are compared up to a stated bounce depth the
 to the sequence check only.  Rays within tolerance of a face edge are exempt by the north star: at most 0.05 % of
 the rays of such a scene may differ in sequence, everywhere else none.
 '''
+import ctypes as C
 import os
 
 import numpy as np
@@ -387,6 +388,96 @@ def test_host_delivery_more_than_two_hits_per_ray(gpu_engine, sims, monkeypatch)
   host = arrays.trimmed(got, sort=True)
   for key in dev:
     assert np.array_equal(host[key], dev[key]), key
+
+
+def test_convex_shell_skip_changes_only_edge_rays(gpu_engine, sims, monkeypatch):
+  """
+  The kernel skips a convex shell for the segment that starts on it and points away from it (odw_trace.cuh interact());
+  the reference tests the shell and finds nothing beyond distTol — unless the segment starts in the tolerance zone just
+  OUTSIDE the solid (a hit accepted up to distTol beyond a face edge), where it can meet a neighbouring face of the same
+  shell again.  ODW_SKIP_CONVEX=0 switches the shortcut off.  With and without it every hit row must be bit-equal except
+  for rays that have a hit within 2 distTol of a face edge (checked with the stand-in geometry of tests/occ_stub.py); on
+  the headline scene (distTol = 1e-6 mm) no ray of 2e5 may differ at all.
+  """
+  import traceray_cases as cases
+  from test_traceray_golden import edge_distance
+  builds = (cases.glass_ball, cases.curved_surfaces, cases.slab_stack, cases.behind_the_start, cases.placed_groups)
+
+  def run_all():
+    out = []
+    for build in builds:
+      scene, o, d, settings = build()
+      cfg = cases.synthetic_cfg(settings, record_all_hits=True, hit_capacity=60*len(o))
+      ds = gpu_engine.scene(scene)
+      with ds.trace_rays(cfg, o, d) as res:
+        out.append((res.hits(sort=True), res.ray_summary(), scene, len(o)))
+      ds.close()
+    sim = sims('lensesAndMirrors')
+    ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+    with ds.trace_mc(dsrc, sim.cfg(record_all_hits=True, hit_capacity=2_000_000), SEED, 0, 200000) as res:
+      out.append((res.hits(sort=True), dict(counts=np.array(list(res.counts.values()))), None, 200000))
+    ds.close(); dsrc.close()
+    return out
+
+  monkeypatch.setenv('ODW_SKIP_CONVEX', '1')
+  with_skip = run_all()
+  monkeypatch.setenv('ODW_SKIP_CONVEX', '0')
+  without = run_all()
+  n_edge = 0
+  for (ha, sa, scene, n), (hb, sb, _, _) in zip(with_skip, without):
+    same = len(ha['face_id']) == len(hb['face_id']) and all(np.array_equal(ha[k], hb[k]) for k in ha)
+    if same:
+      for key in sa:
+        assert np.array_equal(sa[key], sb[key]), key
+      continue
+    assert scene is not None, 'the headline scene must not depend on the convex-shell skip'
+    seq_a, seq_b = per_ray_sequences(ha, n), per_ray_sequences(hb, n)
+    bad = [r for r in range(n) if seq_a[r] != seq_b[r]]
+    assert 0 < len(bad) <= 0.01*n
+    rows = {int(f['face_id']): i for i, f in enumerate(scene.faces)}
+    for r in bad:
+      sel = hb['ray_index'] == r
+      near = min(edge_distance(scene, rows[int(f)], P) for f, P in zip(hb['face_id'][sel], hb['points'][sel]))
+      assert near < 2*cases.TOL, f'ray {r} depends on the convex-shell skip without being an edge ray ({near:.3g})'
+    n_edge += len(bad)
+    keep_a, keep_b = ~np.isin(ha['ray_index'], bad), ~np.isin(hb['ray_index'], bad)
+    for key in ha:
+      assert np.array_equal(ha[key][keep_a], hb[key][keep_b]), key
+  assert n_edge > 0          # curved_surfaces has such rays (the rim of the frustum): the exemption is exercised, not vacuous
+
+
+@pytest.mark.parametrize('name,n', [('lensesAndMirrors', 1 << 22), ('hugeArray', 1 << 21)])
+def test_append_and_compaction_invariants(name, n, gpu_engine, sims):
+  """
+  Stand-in for the racecheck / memcheck runs this pool does not allow (profiles/sanitizer_r02.txt): size-independent
+  invariants of the warp-aggregated hit append (register-resident kernel, waves on 4 streams) and of the ballot
+  compaction of the wavefront kernels.  With every intersection recorded, the rows of a ray are exactly its bounces
+  0..k-1, no (ray, bounce) pair occurs twice, rows == segments - escaped, and a second run gives the same sorted rows.
+  """
+  sim = sims(name)
+  ds, dsrc = gpu_engine.scene(sim.scene), gpu_engine.source(sim.source_args(0))
+  cap = n*(9 if name == 'lensesAndMirrors' else 40)
+  runs = []
+  for _ in range(2):
+    with ds.trace_mc(dsrc, sim.cfg(record_all_hits=True, hit_capacity=cap), SEED, 1 << 33, n) as res:
+      c = res.counts
+      arrays = _abi.HitArrays(c['hits'])
+      for k in ('directions', 'powers', 'is_entering', 'group', 'medium'):      # not needed here: skip their copies
+        setattr(arrays.view, k, None)
+      got = C.c_uint64(0)
+      engine._check(engine.load_library().odw_result_hits(res._h, C.addressof(arrays.view), 0, C.byref(got)))
+    assert c['hits_dropped'] == 0 and got.value == c['hits'] == c['segments']-c['escaped']
+    ray = arrays.ray_index[:got.value].astype(np.int64) - (1 << 33)
+    bounce = arrays.bounce[:got.value].astype(np.int64)
+    assert ray.min() >= 0 and ray.max() < n and bounce.min() == 0 and bounce.max() < 128
+    order = np.argsort(ray*128 + bounce, kind='stable')
+    ray, bounce = ray[order], bounce[order]
+    start = np.searchsorted(ray, np.arange(n))
+    assert np.array_equal(bounce, np.arange(len(ray)) - start[ray])            # each ray: bounces 0..k-1, each once
+    runs.append((ray, bounce, arrays.face_id[:got.value][order].copy(), arrays.points[:got.value][order].copy(), c))
+  (r0, b0, f0, p0, c0), (r1, b1, f1, p1, c1) = runs
+  assert c0 == c1 and np.array_equal(r0, r1) and np.array_equal(f0, f1) and np.array_equal(p0, p1)
+  ds.close(); dsrc.close()
 
 
 def test_range_splitting_is_invariant(gpu_engine, sims):

@@ -1,11 +1,14 @@
 '''
-The reference's OWN bounce loop as the judge of the restatement: tests/golden/traceray_golden.npz holds what
-PointSourceProxy._makeRay + Ray.traceRay + OpticalGroupProxy.onRayHit of the reference (imported unmodified, executed
-under tests/freecad_stub.py with the oracle answering the two OpenCASCADE questions) produce for the rays of the
-benchmark scenes and of synthetic scenes that reach the remaining branches of ray.py:36-281 (generator:
-tests/golden/make_traceray_golden.py).  Compared here: the oracle's complete trace (CPU) and the CUDA path through the
-C ABI (GPU) — segment counts, every interaction (object, point, incoming direction, power, isEntering, traversed
-medium), final points; for the fixture scenes also the initial rays (the reference's _makeRay vs the engine's).
+The reference's OWN code as the judge of the restatement: tests/golden/traceray_golden.npz holds what
+PointSourceProxy._makeRay + Ray.traceRay + Ray.findNearestIntersection + Ray.getNormal + find.relevantOpticalObjects +
+OpticalGroupProxy.onRayHit of the reference (imported unmodified, NO method overridden) produce for the rays of the
+benchmark scenes and of synthetic scenes that reach the remaining branches of ray.py:36-452, executed under stand-ins
+for FreeCAD's Base types (tests/freecad_stub.py) and for the OpenCASCADE primitives the loop calls (tests/occ_stub.py:
+line x untrimmed surface, point-to-edge and point-to-trimmed-face distances, bounding boxes, Surface.parameter, normalAt;
+numpy only, independent of oracle/).  Generator: tests/golden/make_traceray_golden.py.  Compared here: the oracle's
+complete trace (CPU) and the CUDA path through the C ABI (GPU) — segment counts, every interaction (object, the very
+face, point, incoming direction, power, isEntering, traversed medium), final points; for the fixture scenes also the
+initial rays (the reference's _makeRay vs the engine's).
 '''
 import os
 
@@ -17,6 +20,9 @@ import traceray_cases as cases
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'traceray_golden.npz')
 POS_TOL = 1e-9          # mm, on intersection points (same bar as tests/test_gpu_parity.py)
 DIR_TOL = 1e-12
+# the stand-in finds torus / cone crossings as roots of the substituted polynomial (numpy.roots + Newton): near-grazing
+# crossings of the curved-surface case carry ~1e-12 of conditioning error on the GOLDEN side
+DIR_TOL_CASE = dict(curved_surfaces=1e-10)
 POWER_TOL = 1e-12
 
 
@@ -48,10 +54,65 @@ def setup_case(key, g):
     return sim.scene, sim.cfg(record_all_hits=True, wavelength=wl, hit_capacity=n_hits+16), ignored, sim.source_args(0)
   build, _ = cases.SYNTHETIC_CASES[key.split('@')[0]]
   scene, _, _, settings = build()
-  return scene, cases.synthetic_cfg(settings, record_all_hits=True, wavelength=wl, hit_capacity=len(g['hit_powers'])+16), [], None
+  _, extras = cases.split_settings(settings)
+  cfg = cases.synthetic_cfg(settings, record_all_hits=True, wavelength=wl, hit_capacity=len(g['hit_powers'])+16)
+  return scene, cfg, list(extras['ignored'] or []), None
 
 
-def check_against_golden(g, hits, n_segments, final_points):
+def edge_distance(scene, face_row, point, _cache={}):
+  'distance of a hit point to the boundary curves of its face (numpy stand-in geometry of tests/occ_stub.py); inf = closed surface'
+  import occ_stub
+  key = (id(scene), int(face_row))
+  if key not in _cache:
+    _cache[key] = occ_stub.Face(scene.faces[int(face_row)], scene.segs, int(face_row))
+  face = _cache[key]
+  if not face._boundary_curves():
+    return np.inf
+  return face.boundary_distance(np.asarray(point, dtype=np.float64))
+
+
+def drop_edge_rays(g, hits, n_segments, final_points, scene, tol, max_fraction=0.01):
+  '''
+  The north star exempts rays within tolerance of a face edge.  The kernels differ from the reference there in one
+  documented way: a segment that starts on a convex shell and points away from it skips that shell, while
+  the reference can meet the shell again when the start point lies in the tolerance zone just outside the solid.  Rays
+  whose sequence differs from the golden must have a golden hit within 2 tol of the boundary of its face — checked, not
+  assumed — and there may be only a few; they are removed from both sides before the strict comparison.
+  '''
+  n_rays = len(g['origins'])
+  want_segments = np.diff(g['seg_offsets'])
+  first_g = np.searchsorted(g['hit_ray'], np.arange(n_rays+1))
+  ray_h = hits['ray_index'].astype(np.int64)
+  first_h = np.searchsorted(ray_h, np.arange(n_rays+1))
+  bad = [r for r in range(n_rays)
+         if n_segments[r] != want_segments[r]
+         or not np.array_equal(hits['face_id'][first_h[r]:first_h[r+1]], g['hit_face_id'][first_g[r]:first_g[r+1]])]
+  if not bad:
+    return g, hits, n_segments, final_points, 0
+  assert len(bad) <= max_fraction*n_rays, f'{len(bad)} of {n_rays} rays differ from the reference'
+  for r in bad:
+    rows = range(first_g[r], first_g[r+1])
+    near = min((edge_distance(scene, g['hit_face_row'][k], g['hit_points'][k]) for k in rows), default=np.inf)
+    assert near < 2*tol, f'ray {r} differs from the reference although no hit of it is within 2 tol of a face edge ({near:.3g})'
+  keep_ray = np.ones(n_rays, dtype=bool); keep_ray[bad] = False
+  new_index = np.cumsum(keep_ray)-1
+  kg, kh = keep_ray[g['hit_ray']], keep_ray[ray_h]
+  g2 = dict(g)
+  for k in list(g):
+    if k.startswith('hit_'):
+      g2[k] = g[k][kg]
+  g2['hit_ray'] = new_index[g['hit_ray'][kg]]
+  seg_keep = np.repeat(keep_ray, want_segments)
+  for k in ('seg_p1', 'seg_p2', 'seg_power', 'seg_medium'):
+    g2[k] = g[k][seg_keep]
+  g2['seg_offsets'] = np.concatenate([[0], np.cumsum(want_segments[keep_ray])])
+  g2['origins'], g2['directions'] = g['origins'][keep_ray], g['directions'][keep_ray]
+  h2 = {k: v[kh] for k, v in hits.items()}
+  h2['ray_index'] = new_index[ray_h[kh]].astype(hits['ray_index'].dtype)
+  return g2, h2, n_segments[keep_ray], final_points[keep_ray], len(bad)
+
+
+def check_against_golden(g, hits, n_segments, final_points, dir_tol=DIR_TOL):
   n_rays = len(g['origins'])
   want_segments = np.diff(g['seg_offsets'])
   assert np.array_equal(n_segments, want_segments)
@@ -61,9 +122,10 @@ def check_against_golden(g, hits, n_segments, final_points):
   first = np.searchsorted(g['hit_ray'], np.arange(n_rays))
   assert np.array_equal(hits['bounce'], np.arange(len(g['hit_ray'])) - first[g['hit_ray']])
   assert np.array_equal(hits['group'], g['hit_group'])
+  assert np.array_equal(hits['face_id'], g['hit_face_id'])         # the very face the reference's selection returned
   assert np.array_equal(hits['is_entering'], g['hit_is_entering'])
   assert np.abs(hits['points']-g['hit_points']).max() < POS_TOL
-  assert np.abs(hits['directions']-g['hit_directions']).max() < DIR_TOL
+  assert np.abs(hits['directions']-g['hit_directions']).max() < dir_tol
   assert np.abs(hits['powers']-g['hit_powers']).max() < POWER_TOL
   # medium of the segment that ends in the interaction (yield ..., prevMedium, ray.py:117)
   seg_of_hit = g['seg_offsets'][g['hit_ray']] + hits['bounce']
@@ -90,6 +152,38 @@ def test_golden_covers_the_branches(golden):
   assert np.array_equal(seq['hit_group'][:7], golden['lensesAndMirrors']['hit_group'][:7])
 
 
+def test_golden_covers_the_selection_rules(golden):
+  'the cases for ray.py:290-452 / find.py:79-104 reach the decisive branches'
+  tol = cases.TOL
+  g = golden['slab_stack']
+  first = g['hit_ray'] == 0                                  # a perpendicular ray: the gaps are met at exactly their width
+  z, grp, ent = g['hit_points'][first][:, 2], g['hit_group'][first], g['hit_is_entering'][first]
+  # gaps of 0, 0.5 and 1.5 tolerances: the exit face of the current medium and the entry face of the next slab are both
+  # inside minDist + 2 tol -> the reference returns the one that is NOT the current medium, the exit is never reported
+  assert list(grp[:4]) == [0, 1, 2, 3] and ent[:4].all()
+  assert np.allclose(z[:4], [10, 14, 18+0.5*tol, 22+2*tol], atol=1e-9)
+  # a gap of 2.5 tolerances: the entry face is found (inside maxRayLength + 5 tol) but dropped by the 2 tol filter
+  assert grp[4] == 3 and ent[4] == 0 and grp[5] == 4 and ent[5] == 1 and abs((z[5]-z[4])-2.5*tol) < 1e-9
+  g = golden['end_of_the_ray']
+  dist = np.linalg.norm(g['hit_points']-g['origins'][g['hit_ray']], axis=1)
+  assert (dist > 50.0).sum() > 20 and dist.max() < 50.0+tol          # accepted up to one tolerance beyond maxRayLength ...
+  missed = np.setdiff1d(np.arange(len(g['origins'])), g['hit_ray'])
+  k = np.where(missed < 120, 1.0-g['origins'][missed, 2], -g['origins'][missed, 2])/tol
+  assert len(missed) > 40 and k.min() > 1.0 and k.min() < 1.1         # ... and not beyond
+  g = golden['behind_the_start']
+  assert set(g['hit_group'][g['hit_ray'] < 100]) == {3, 4}             # nothing on the backward half of the line is ever hit
+  g = golden['sequence_and_ignore_list']
+  assert 3 not in set(g['hit_group'])                                  # the ignored blocker
+  per_ray = np.diff(g['seg_offsets'])
+  assert set(per_ray) >= {7, 9, 10}                                    # ball missed / last mirror missed / the whole list, then nothing
+  full = np.nonzero(per_ray == 10)[0][0]
+  assert list(g['hit_group'][g['hit_ray'] == full]) == [2, 2, 0, 2, 2, 4, 4, 1, 0]
+  g = golden['placed_groups']
+  assert (g['hit_group'] == 0).sum() > 100 and (g['hit_group'] == 1).sum() > 50
+  g = golden['curved_surfaces']
+  assert set(g['hit_group']) == {0, 1, 2, 3, 4}
+
+
 @pytest.mark.parametrize('key', all_cases())
 def test_oracle_matches_reference_traceray(key, golden, oracle):
   g = golden[key]
@@ -101,7 +195,7 @@ def test_oracle_matches_reference_traceray(key, golden, oracle):
     assert np.abs(s['directions']-g['directions']).max() < 1e-14
   r = oracle.trace_rays(scene, cfg, g['origins'], g['directions'], ignored=ignored, hit_capacity=len(g['hit_powers'])+16)
   assert r['rc'] == 0
-  check_against_golden(g, r['hits'], r['n_segments'], r['final_points'])
+  check_against_golden(g, r['hits'], r['n_segments'], r['final_points'], DIR_TOL_CASE.get(key, DIR_TOL))
 
 
 @pytest.mark.gpu
@@ -121,4 +215,5 @@ def test_gpu_matches_reference_traceray(key, golden, gpu_engine):
       hits, summary = res.hits(sort=True), res.ray_summary()
   finally:
     ds.close()
-  check_against_golden(g, hits, summary['n_segments'], summary['final_points'])
+  g, hits, n_segments, final_points, n_edge = drop_edge_rays(g, hits, summary['n_segments'], summary['final_points'], scene, cfg.cfg.dist_tol)
+  check_against_golden(g, hits, n_segments, final_points, DIR_TOL_CASE.get(key, DIR_TOL))
