@@ -126,17 +126,28 @@ class GenericSourceProxy:
     return counts
 
   # -- engine calls -----------------------------------------------------------------------------------
-  def _store_hits(self, obj, hits, store, metadata_of):
-    'append the hit arrays to the store, one entry per optical group (file per (source, object))'
+  def _store_hits(self, obj, hits, store, metadata_of, borrowed=False):
+    '''
+    append the hit arrays to the store, one entry per optical group (file per (source, object)).  borrowed: the arrays
+    are views of the engine's page-locked delivery buffers (valid until the next engine call); hits of a single group
+    are handed over as they are, without selecting or copying.
+    '''
     scene = self.context.sim.scene
     group = hits['group']
     keys = self.context.sim.settings.get('store_hit_keys', [])
-    for gi in np.unique(group):
-      sel = np.nonzero(group == gi)[0]
+    if not len(group):
+      return
+    present = np.flatnonzero(np.bincount(group, minlength=len(scene.group_names)))
+    for gi in present:
+      if len(present) == 1:
+        sel = slice(None)
+      else:
+        sel = np.flatnonzero(group == gi)
       md = metadata_of(hits['ray_index'][sel], keys) if keys else {}
       store.addRayHits(results_store.named((obj['name'], obj['label'])),
                        results_store.named((scene.group_names[gi], scene.group_labels[gi])),
-                       hits['points'][sel], hits['directions'][sel], hits['powers'][sel], hits['is_entering'][sel], md)
+                       hits['points'][sel], hits['directions'][sel], hits['powers'][sel], hits['is_entering'][sel], md,
+                       borrowed=borrowed and len(present) == 1)
 
   def _ray_dicts(self, obj, batch, hits, summary):
     '''
@@ -244,9 +255,9 @@ class GenericSourceProxy:
       capacity = min(ceiling, max(4*capacity, int(counts['hits'])+1024))
     hits = {k: v[:got] for k, v in arrays.items()}
     if 'group' not in hits:
-      hits['group'] = np.full(got, int(recording[0]), dtype=np.int32)
+      hits['group'] = np.broadcast_to(np.int32(recording[0]), (got,))         # one recording group: no column, no memory
     if 'ray_index' not in hits:
-      hits['ray_index'] = np.zeros(got, dtype=np.uint64)
+      hits['ray_index'] = np.broadcast_to(np.uint64(0), (got,))
     if store:
       def metadata_of(ray_index, keys):
         s = dsrc.sample(ctx.seed, first, n)               # same Philox stream -> the rays' initial conditions
@@ -262,6 +273,6 @@ class GenericSourceProxy:
           elif name == 'initPhi': md[name] = s['phi'][idx]
           elif name == 'initTheta': md[name] = s['first'][idx] if finite else np.full(len(idx), np.nan)
         return md
-      self._store_hits(obj, hits, store, metadata_of)
+      self._store_hits(obj, hits, store, metadata_of, borrowed=True)          # views of the page-locked delivery buffers
       store.incrementRayCount(n)
     return counts

@@ -165,15 +165,29 @@ class SimulationResults:
     self.totalIterations += int(n)
 
   # -- hits ---------------------------------------------------------------------------------------
-  def addRayHits(self, source, obj, points, directions, powers, isEntering, metadata=None):
+  # batches of at least this many bytes that the caller only LENDS (views of page-locked engine buffers that the next
+  # engine call overwrites) are written to their hit files at once instead of being copied into the buffer first
+  DIRECT_WRITE_BYTES = 32 << 20
+  ROWS_PER_FILE = 1 << 23            # a lent batch is cut into files of at most this many hits, written by parallel threads
+
+  def addRayHits(self, source, obj, points, directions, powers, isEntering, metadata=None, borrowed=False):
     '''
     Batch form of addRayHit (results_store.py:641-648): N hits of light source `source` on optical group `obj`.
     metadata: dict key -> array of N values (or (N,3)); only the keys enabled by StoreHit* should be passed.
+    borrowed: the arrays are only valid during this call (views of the engine's page-locked delivery buffers): a large
+    batch goes straight into hit files (the loader concatenates any number of *-hits.pkl per (source, object),
+    results_store.py:74-181), a small one is copied into the buffer.
     '''
     self._raiseIfCleanedUp()
     n = len(powers)
     if n == 0:
       return
+    if borrowed:
+      if n*57 >= self.DIRECT_WRITE_BYTES:
+        self._writeHitsDirect(named(source), named(obj), points, directions, powers, isEntering, metadata or {})
+        return
+      points, directions, powers = np.array(points, dtype=np.float64), np.array(directions, dtype=np.float64), np.array(powers, dtype=np.float64)
+      metadata = {k: np.array(v) for k, v in (metadata or {}).items()}
     entry = dict(points=np.asarray(points, dtype=np.float64).reshape(n, 3),
                  directions=np.asarray(directions, dtype=np.float64).reshape(n, 3),
                  powers=np.asarray(powers, dtype=np.float64).reshape(n),
@@ -185,6 +199,38 @@ class SimulationResults:
     self.hits.append((named(source), named(obj), entry))
     self._bufferedHits += n
     self.writeDiskIfNeeded()
+
+  def _writeHitsDirect(self, source, obj, points, directions, powers, isEntering, metadata):
+    'hit files of one lent batch, written from the caller\'s arrays without an intermediate copy (pickle protocol 5), in parallel slices'
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(powers)
+    points = np.asarray(points, dtype=np.float64).reshape(n, 3)
+    directions = np.asarray(directions, dtype=np.float64).reshape(n, 3)
+    powers = np.asarray(powers, dtype=np.float64).reshape(n)
+    isEntering = np.asarray(isEntering).reshape(n)
+    slices = [(a, min(n, a+self.ROWS_PER_FILE)) for a in range(0, n, self.ROWS_PER_FILE)]
+    names = []
+    for _ in slices:
+      self._fingerprint(fresh=True)
+      names.append(self._makeFilename(kind='hits', source=source, obj=obj))
+
+    def write(job):
+      (a, b), fname = job
+      res = dict(source=source.Name, obj=obj.Name, points=points[a:b], directions=directions[a:b], powers=powers[a:b],
+                 isEntering=isEntering[a:b].astype(np.int64))
+      for k, v in metadata.items():
+        res[k] = np.asarray(v)[a:b]
+      with open(fname, 'wb') as f:
+        pickle.dump(res, f, protocol=5)           # large array payloads go from the array's memory to the file, no bytes copy
+      return fname
+
+    if len(slices) == 1:
+      done = [write((slices[0], names[0]))]
+    else:
+      with ThreadPoolExecutor(max_workers=min(8, len(slices), os.cpu_count() or 1)) as pool:
+        done = list(pool.map(write, zip(slices, names)))
+    self.writtenFiles.extend(done)
+    self.totalRecordedHits += n
 
   def addRays(self, source, rays):
     '''
@@ -238,9 +284,9 @@ class SimulationResults:
             else:                                   # NaN padding like the reference's metadata handling
               shape = next(x[k].shape[1:] for x in entries if k in x)
               parts.append(np.full((n,)+shape, np.nan))
-          res[k] = np.concatenate(parts, axis=0)
+          res[k] = parts[0] if len(parts) == 1 else np.concatenate(parts, axis=0)
         with open(fname, 'wb') as f:
-          pickle.dump(res, f)
+          pickle.dump(res, f, protocol=5)         # array payloads are written from the arrays' memory (no bytes copy)
         self.writtenFiles.append(fname)
       self.totalRecordedHits += self._bufferedHits
       self.hits, self._bufferedHits = None, 0
