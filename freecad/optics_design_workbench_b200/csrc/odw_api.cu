@@ -521,7 +521,8 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     d.n = g.refractive_index; d.reflectivity = g.reflectivity; d.absorption_length = g.absorption_length;
     d.lpm = g.grating_lines_per_mm; d.order = g.grating_order;
     for (int k = 0; k < 3; ++k) d.gdir[k] = g.grating_orientation[k];
-    d.type = g.optical_type; d.record = g.record_hits; d.gtype = g.grating_type; d.pad = 0;
+    d.type = g.optical_type; d.record = g.record_hits; d.gtype = g.grating_type;
+    d.fresnel = (g.fresnel && g.optical_type == ODW_OPT_LENS) ? 1 : 0;
     d.scat_main = d.scat_modify = -1; d.pad1 = d.pad2 = 0;
     if (sd->n_scatters > 0 && sd->group_scatter && (g.optical_type == ODW_OPT_MIRROR || g.optical_type == ODW_OPT_LENS)) {
       d.scat_main = sd->group_scatter[2*i]; d.scat_modify = sd->group_scatter[2*i+1];
@@ -537,7 +538,7 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
   sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
   for (const DFace& f : faces) if (f.aux[5] != 0.0) sc->ext_optics = true;      // even-asphere faces need the FEAT_EXT instances
   for (const DGroup& g : groups)
-    if (g.type == ODW_OPT_GRATING || g.scat_main >= 0 || g.scat_modify >= 0 || std::isfinite(g.absorption_length)) sc->ext_optics = true;
+    if (g.type == ODW_OPT_GRATING || g.scat_main >= 0 || g.scat_modify >= 0 || std::isfinite(g.absorption_length) || g.fresnel) sc->ext_optics = true;
   int rc;
   if ((rc = upload(eng, sc->owned, faces.data(), faces.size(), &sc->d.faces))) { odw_scene_destroy(sc); return rc; }
   if ((rc = upload(eng, sc->owned, shells.data(), shells.size(), &sc->d.shells))) { odw_scene_destroy(sc); return rc; }

@@ -42,7 +42,7 @@ struct DShell {                    // 64 B
 
 struct DGroup {
   double n, reflectivity, absorption_length, lpm, order, gdir[3];
-  int32_t type, record, gtype, pad;
+  int32_t type, record, gtype, fresnel;         // fresnel: opt-in Fresnel reflection at the faces of a Lens group (odw.h)
   int32_t scat_main, scat_modify, pad1, pad2;   // stochastic surface model: indices into DScene::scatters, -1 = ideal
 };
 
@@ -685,6 +685,17 @@ __device__ __forceinline__ bool snell(const double* ray, double n1, double n2, c
   out[1] = mu*(ray[1]*nn - n[1]*nr) + n[1]*s;
   out[2] = mu*(ray[2]*nn - n[2]*nr) + n[2]*s;
   return false;
+}
+
+// unpolarised Fresnel reflectance of the interface n1 -> n2 (unit direction, unit normal with d.n >= 0); 1 beyond the critical
+// angle.  Opt-in extension (odw_group.fresnel): the reference has no Fresnel split.  Same arithmetic as the oracle.
+__device__ __forceinline__ double fresnel_reflectance(const double* d, const double* n, double n1, double n2) {
+  const double ci = fmin(1.0, fabs(dot3(d, n)));
+  const double s2 = (n1/n2)*(n1/n2)*(1 - ci*ci);
+  if (s2 >= 1) return 1.0;
+  const double ct = sqrt(1 - s2);
+  const double rs = (n1*ci - n2*ct)/(n1*ci + n2*ct), rp = (n1*ct - n2*ci)/(n1*ct + n2*ci);
+  return 0.5*(rs*rs + rp*rp);
 }
 
 struct Vec3 { double x, y, z; };

@@ -481,7 +481,13 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
     }
     case ODW_OPT_LENS: {                                                         // ray.py:165-211
       double n1 = r.medium >= 0 ? groups[r.medium].n : 1.0, n2 = 1.0;
-      if (entering) { r.medium = fgroup; n2 = g.n; }
+      if (entering) n2 = g.n;
+      if ((FEAT & FEAT_EXT) && g.fresnel) {                                      // opt-in extension (odw.h odw_group.fresnel): not in the reference
+        double u0, u1;
+        philox_uniform2(p.seed, (uint32_t)p.src.source_id, p.first_ray + i, 0x20000u + (uint32_t)(r.n_isect-1), u0, u1);
+        if (u0 < fresnel_reflectance(dn, nrm, n1, n2)) { mirror_dir(dn, nrm, o); oscale = 1.0; break; }   // reflected: medium and sequence index stay
+      }
+      if (entering) r.medium = fgroup;
       bool tir = snell(dn, n1, n2, nrm, o);
       oscale = 1.0;                                                              // snellsLaw works on the unit direction
       if ((FEAT & FEAT_EXT) && p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {   // ray.py:197-201

@@ -375,6 +375,7 @@ def build_scene(doc):
       reflectivity=float(g.get('Reflectivity', 1.0)),
       absorption_length=_float(g.get('AbsorptionLength', 'inf'), np.inf),
       record_hits=bool(g.get('RecordHits', False)),
+      fresnel=bool(g.get('FresnelReflection', False)),       # additional property of this engine (default off = reference behaviour)
       grating_type=g.get('GratingType', 'Reflection') if g.get('GratingType') in ('Reflection', 'Transmission') else 'Reflection',
       grating_lines_per_mm=float(g.get('GratingLinesPerMillimeter', 1000.0)),
       grating_order=float(g.get('GratingDiffractionOrder', 1.0)),

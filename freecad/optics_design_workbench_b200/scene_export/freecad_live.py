@@ -56,6 +56,7 @@ def build_scene(optical_groups, placements_of, sequence=None):
       g.Name, g.Label, otype,
       refractive_index=float(_prop(g, 'RefractiveIndex', 2.0)), reflectivity=float(_prop(g, 'Reflectivity', 1.0)),
       absorption_length=float(_prop(g, 'AbsorptionLength', 'inf')), record_hits=bool(_prop(g, 'RecordHits', False)),
+      fresnel=bool(_prop(g, 'FresnelReflection', False)),
       grating_type=_prop(g, 'GratingType', 'Reflection'), grating_lines_per_mm=float(_prop(g, 'GratingLinesPerMillimeter', 1000.0)),
       grating_order=float(_prop(g, 'GratingDiffractionOrder', 1.0)), grating_orientation=orient,
       scatter_density=(_prop(g, 'ReflectedProbabilityDensity', '') if otype == 'Mirror'

@@ -37,7 +37,7 @@ SHELL_DTYPE = np.dtype([
 GROUP_DTYPE = np.dtype([
   ('refractive_index', '<f8'), ('reflectivity', '<f8'), ('absorption_length', '<f8'),
   ('grating_lines_per_mm', '<f8'), ('grating_order', '<f8'), ('grating_orientation', '<f8', 3),
-  ('optical_type', '<i4'), ('record_hits', '<i4'), ('grating_type', '<i4'), ('pad', '<i4'),
+  ('optical_type', '<i4'), ('record_hits', '<i4'), ('grating_type', '<i4'), ('fresnel', '<i4'),
 ], align=True)
 
 assert FACE_DTYPE.itemsize == 224 and SEG_DTYPE.itemsize == 48
@@ -385,8 +385,10 @@ class SceneBuilder:
                 grating_lines_per_mm=1000.0, grating_order=1.0, grating_orientation=(0, 0, 1),
                 scatter_density='', power_theta_domain='-pi/2, pi/2', power_phi_domain='0, 2*pi',
                 modify_density='', modify_theta_domain='-pi/2, pi/2', modify_phi_domain='0, 2*pi',
-                scatter_resolution=None):
+                scatter_resolution=None, fresnel=False):
     '''
+    fresnel = opt-in Fresnel reflection at the faces of a Lens group (include/odw.h odw_group.fresnel; the reference has
+    none, so the default reproduces it).
     scatter_density = ReflectedProbabilityDensity (Mirror) / RefractedProbabilityDensity (Lens); modify_density =
     RayModificationProbabilityDensity (optical_group.py:29-96); empty = ideal surface.
     '''
@@ -396,6 +398,7 @@ class SceneBuilder:
     g['refractive_index'], g['reflectivity'] = refractive_index, reflectivity
     g['absorption_length'] = absorption_length
     g['record_hits'] = int(bool(record_hits))
+    g['fresnel'] = int(bool(fresnel))
     g['grating_type'] = (GRATING_TYPES.index(grating_type) if isinstance(grating_type, str)
                          else grating_type)
     g['grating_lines_per_mm'], g['grating_order'] = grating_lines_per_mm, grating_order

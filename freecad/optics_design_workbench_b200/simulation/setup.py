@@ -45,7 +45,11 @@ class PreparedSimulation:
       from ..distributions import SamplerTables
       d = meta['scatter_domains'][i]
       scatters.append(SamplerTables(z[f'scatter_phi_{i}'], z[f'scatter_first_{i}'], d[0], d[1], 'theta'))
-    scene = Scene(z['faces'], z['segs'], z['shells'], z['groups'], meta['group_names'], meta['group_labels'],
+    from ..scene_export.scene import GROUP_DTYPE
+    groups = z['groups']
+    if groups.dtype != GROUP_DTYPE and groups.dtype.itemsize == GROUP_DTYPE.itemsize:
+      groups = groups.view(GROUP_DTYPE)                      # fixtures written before a field of the same size was renamed
+    scene = Scene(z['faces'], z['segs'], z['shells'], groups, meta['group_names'], meta['group_labels'],
                   z['seq_offsets'], z['seq_groups'], scatters=scatters,
                   group_scatter=z['group_scatter'] if 'group_scatter' in z.files else None)
     records = meta['source_records']

@@ -141,7 +141,12 @@ typedef struct odw_group {
   int32_t optical_type;          /* ODW_OPT_* */
   int32_t record_hits;           /* RecordHits */
   int32_t grating_type;          /* ODW_GRATING_* */
-  int32_t pad;
+  int32_t fresnel;               /* OPT-IN EXTENSION, 0 = the reference's behaviour (ray.py:165-211 refracts every ray at a Lens
+                                  * face without loss: no Fresnel split).  1: at every face of this Lens group the
+                                  * ray is REFLECTED with the unpolarised Fresnel reflectance R = (Rs + Rp)/2 of the interface
+                                  * n1 -> n2 and refracted otherwise (one ray in, one ray out: a stochastic choice driven by the
+                                  * ray's Philox stream, purpose 0x20000 + bounce; power is not split).  A reflected ray keeps its
+                                  * medium and its sequence index, like a totally reflected one. */
 } odw_group;
 
 /* Tabulated (theta, phi) density of an optical group's stochastic surface model (optical_group.py:212-323:

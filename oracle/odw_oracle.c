@@ -832,6 +832,18 @@ static int snell(const double* ray, double n1, double n2, const double* n, doubl
   return 0;
 }
 
+/* unpolarised Fresnel reflectance of the interface n1 -> n2 for unit direction d and unit normal n (d.n >= 0); 1 beyond the
+ * critical angle.  Not in the reference (no Fresnel split there): opt-in extension, see odw_group.fresnel in odw.h */
+static double fresnel_reflectance(const double* d, const double* n, double n1, double n2) {
+  double ci = fabs(dot3(d, n));
+  if (ci > 1) ci = 1;
+  double s2 = (n1/n2)*(n1/n2)*(1 - ci*ci);
+  if (s2 >= 1) return 1.0;
+  double ct = sqrt(1 - s2);
+  double rs = (n1*ci - n2*ct)/(n1*ci + n2*ct), rp = (n1*ct - n2*ci)/(n1*ct + n2*ci);
+  return 0.5*(rs*rs + rp*rp);
+}
+
 static void line_grating(const double* ray_in, double n1, double n2, const double* normal, const odw_group* g,
                          double wavelength_nm, int transmission, double* out) {
   double wl = wavelength_nm/1000.0;
@@ -986,6 +998,16 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
           n2 = 1.0;                                                         /* quirk Q2 */
         }
         double o[3];
+        if (g->fresnel) {                                                   /* opt-in extension (odw.h odw_group.fresnel): not in the reference */
+          double u[2];
+          oracle_philox(seed, source_id, ray_index, 0x20000u + (uint32_t)(n_isect-1), u);
+          if (u[0] < fresnel_reflectance(dnrm, nrm, n1, n2)) {
+            if (entering) medium = prev_medium;                             /* the ray never got in */
+            mirror(dnrm, nrm, o);
+            memcpy(dir, o, sizeof o);
+            break;
+          }
+        }
         int tir = snell(dnrm, n1, n2, nrm, o);
         apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, o);   /* :197-201 */
         memcpy(dir, o, sizeof o);
