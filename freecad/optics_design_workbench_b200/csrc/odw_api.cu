@@ -601,6 +601,22 @@ static std::vector<uint32_t> build_guide(const double* cdf, int n) {
 
 extern "C" void odw_source_destroy(odw_source* s);
 
+// A plane face trimmed to exactly one triangle (three chained straight pcurves): what the tessellation of a free-form emitter
+// consists of.  tri = (u, v) of the three corners.  Same rule as the oracle's emit_triangle.
+static bool emit_triangle(const odw_face& f, const odw_trimseg* segs, double* tri) {
+  if (f.kind != ODW_SURF_PLANE || f.trim_kind != ODW_TRIM_LOOPS || f.seg_count != 3 || !segs) return false;
+  const odw_trimseg* g = segs + f.seg_first;
+  double scale = 0;
+  for (int k = 0; k < 3; ++k) { if (g[k].kind != ODW_SEG_LINE) return false; for (int j = 0; j < 4; ++j) scale = std::max(scale, std::fabs(g[k].a[j])); }
+  const double eps = 1e-9*std::max(scale, 1e-300);
+  for (int k = 0; k < 3; ++k) {
+    const odw_trimseg& a = g[k]; const odw_trimseg& b = g[(k + 1) % 3];
+    if (std::fabs(a.a[2] - b.a[0]) > eps || std::fabs(a.a[3] - b.a[1]) > eps) return false;
+    tri[2*k] = a.a[0]; tri[2*k + 1] = a.a[1];
+  }
+  return true;
+}
+
 // ODW_SRC_SURFACE (reference freecad_elements/surface_source.py): emitting faces, area CDF and the theta table
 static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw_source** out) {
   if (sd->n_emit <= 0 || !sd->emit_faces || !sd->emit_cdf) return fail(ODW_EINVAL, "surface source without emitting faces");
@@ -621,12 +637,26 @@ static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw
   double bound = 0;
   for (int i = 0; i < sd->n_emit; ++i) {
     fill_dface(sd->emit_faces[i], sd->emit_segs, false, faces[(size_t)i]);
+    double tri[6];
+    if (emit_triangle(sd->emit_faces[i], sd->emit_segs, tri)) {      // tessellated emitters: sampled without rejection (odw_trace.cuh init_ray_surface)
+      faces[(size_t)i].flags |= DFACE_TRI;
+      for (int k = 0; k < 6; ++k) faces[(size_t)i].aux[k] = tri[k];
+    }
     for (int k = 0; k < 3; ++k) bound = std::max(bound, std::max(std::fabs(sd->emit_faces[i].aabb_min[k]), std::fabs(sd->emit_faces[i].aabb_max[k])));
   }
   int rc;
   if ((rc = upload(eng, s->owned, faces.data(), faces.size(), &s->d.emit_faces))) { odw_source_destroy(s); return rc; }
   if ((rc = upload(eng, s->owned, sd->emit_segs, (size_t)sd->n_emit_segs, &s->d.emit_segs))) { odw_source_destroy(s); return rc; }
   if ((rc = upload(eng, s->owned, sd->emit_cdf, (size_t)sd->n_emit, &s->d.emit_cdf))) { odw_source_destroy(s); return rc; }
+  {
+    std::vector<uint32_t> eg((size_t)ODW_EMIT_GUIDE + 1);
+    for (int k = 0; k <= ODW_EMIT_GUIDE; ++k) {                       // first face with emit_cdf > k/ODW_EMIT_GUIDE
+      const double x = (double)k/(double)ODW_EMIT_GUIDE;
+      const long j = std::upper_bound(sd->emit_cdf, sd->emit_cdf + sd->n_emit, x) - sd->emit_cdf;
+      eg[(size_t)k] = (uint32_t)std::min<long>(j, sd->n_emit - 1);
+    }
+    if ((rc = upload(eng, s->owned, eg.data(), eg.size(), &s->d.emit_guide))) { odw_source_destroy(s); return rc; }
+  }
   if ((rc = upload(eng, s->owned, sd->first_cdf, (size_t)sd->n_first, &s->d.first_cdf))) { odw_source_destroy(s); return rc; }
   std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first);
   if ((rc = upload(eng, s->owned, fg.data(), fg.size(), &s->d.first_guide))) { odw_source_destroy(s); return rc; }

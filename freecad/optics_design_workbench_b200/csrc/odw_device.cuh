@@ -27,6 +27,7 @@ struct DFace {
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
 #define DFACE_FAST   2             // plane/uvbox, plane/disc, sphere (whole or full-u cap), cylinder (full-u band): inline test
 #define DFACE_DISC   4             // plane whose only trim loop is one full circle: umin,vmin = centre, umax = radius
+#define DFACE_TRI    8             // EMITTING faces only: plane trimmed to one triangle (a tessellated emitter), aux[0..5] = its corners (u, v)
 
 // Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).  The box is fp32,
 // rounded outward; the kernel widens it by TraceParams::cull_margin (distTol + the fp32 error bound of the slab
@@ -101,8 +102,10 @@ struct DSource {
   const DFace* emit_faces;
   const odw_trimseg* emit_segs;
   const double* emit_cdf;
+  const uint32_t* emit_guide;      // [ODW_EMIT_GUIDE+1]: emit_guide[k] = first face whose cumulative weight exceeds k/ODW_EMIT_GUIDE
   double dist_tol;
 };
+#define ODW_EMIT_GUIDE 65536
 #define ODW_GUIDE 4096
 
 struct HitBuffers {

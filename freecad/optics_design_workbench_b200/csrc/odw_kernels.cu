@@ -152,13 +152,14 @@ __global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long 
 // ------------------------------------------------------------------------------------------
 // launch helpers used by odw_api.cu
 
-// Kernel instances: the Monte-Carlo kernel for scenes staged in shared memory (the hot configuration) exists in three
+// Kernel instances: the Monte-Carlo kernel for scenes staged in shared memory (the hot configuration) exists in four
 // feature sets, everything else only with all features.  pick_feat() maps the features a launch needs to the leanest
 // instance that covers them.
 static int pick_feat(bool mc, bool bvh, int need) {
   if (!mc || bvh) return FEAT_ALL;
   if (need == 0) return 0;
   if ((need & ~FEAT_SEQ) == 0) return FEAT_SEQ;
+  if (!(need & FEAT_EXT)) return FEAT_ALL & ~FEAT_EXT;      // surface sources / device binning in scenes of ideal surfaces (BASELINE configs[4])
   return FEAT_ALL;
 }
 
@@ -182,6 +183,7 @@ extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh,
   if (mc && !bvh) {
     if (feat == 0) return launch_instance<true, false, 0>(p, blocks, smem, st);
     if (feat == FEAT_SEQ) return launch_instance<true, false, FEAT_SEQ>(p, blocks, smem, st);
+    if (feat == (FEAT_ALL & ~FEAT_EXT)) return launch_instance<true, false, FEAT_ALL & ~FEAT_EXT>(p, blocks, smem, st);
     return launch_instance<true, false, FEAT_ALL>(p, blocks, smem, st);
   }
   if (mc) return launch_instance<true, true, FEAT_ALL>(p, blocks, smem, st);
@@ -203,6 +205,7 @@ extern "C" int odw_trace_occupancy(bool mc, bool bvh, int need, size_t smem) {
   if (mc && !bvh) {
     if (feat == 0) return occupancy_instance<true, false, 0>(smem);
     if (feat == FEAT_SEQ) return occupancy_instance<true, false, FEAT_SEQ>(smem);
+    if (feat == (FEAT_ALL & ~FEAT_EXT)) return occupancy_instance<true, false, FEAT_ALL & ~FEAT_EXT>(smem);
     return occupancy_instance<true, false, FEAT_ALL>(smem);
   }
   if (mc) return occupancy_instance<true, true, FEAT_ALL>(smem);

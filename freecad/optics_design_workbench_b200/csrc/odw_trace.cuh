@@ -330,10 +330,22 @@ __device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long
   double a0, a1, b0, b1;
   philox_uniform2(seed, (uint32_t)s.source_id, ray, 0u, a0, a1);
   philox_uniform2(seed, (uint32_t)s.source_id, ray, 1u, b0, b1);
-  int k = 0, hi = s.n_emit-1;                                                    // first face with a0 < emit_cdf[k]
+  // first face with a0 < emit_cdf[k]: the guide table brackets it (a tessellated emitter has 1e4..1e5 faces: a plain binary
+  // search is 17 dependent trips to L2)
+  const int cell = min(ODW_EMIT_GUIDE-1, (int)(a0*(double)ODW_EMIT_GUIDE));
+  int k = (int)__ldg(s.emit_guide + cell), hi = min(s.n_emit-1, (int)__ldg(s.emit_guide + cell + 1));
   while (k < hi) { const int m = (k + hi) >> 1; if (a0 < __ldg(s.emit_cdf + m)) hi = m; else k = m + 1; }
   const DFace& f = s.emit_faces[k];
   double P[3] = {0, 0, 0}, du[3] = {1, 0, 0}, dv[3] = {0, 1, 0};
+  if (f.flags & DFACE_TRI) {
+    // a triangle (tessellated emitter): area-uniform point from two uniforms, nothing to reject
+    double w0, w1;
+    philox_uniform2(seed, (uint32_t)s.source_id, ray, 2u, w0, w1);
+    const double sq = sqrt(w0), b1 = sq*(1.0 - w1), b2 = sq*w1, b0 = 1.0 - sq;
+    const double u = b0*f.aux[0] + b1*f.aux[2] + b2*f.aux[4], v = b0*f.aux[1] + b1*f.aux[3] + b2*f.aux[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + u*f.x[i] + v*f.y[i]; du[i] = f.x[i]; dv[i] = f.y[i]; }
+  } else
   for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {
     double w0, w1, w2, w3, u, v;
     philox_uniform2(seed, (uint32_t)s.source_id, ray, 2u + tr, w0, w1);

@@ -210,7 +210,8 @@ typedef struct odw_source_desc {
   /* ---- surface sources only (kind == ODW_SRC_SURFACE; reference freecad_elements/surface_source.py:418-555) ----
    * Per ray: pick an emitting face with probability proportional to its area (:465-466,536-537), draw a point
    * uniformly by area inside the face's (u,v) window and redraw until it lies on the trimmed face within dist_tol
-   * (:390-410), draw theta from first_cdf (one row, edges linspace(first_lo, first_hi, n_first); NO sin(theta)
+   * (:390-410; a plane face trimmed to a single triangle — the tessellation of a free-form emitter — is sampled directly,
+   * P = (1 - sqrt(w0)) A + sqrt(w0) (1 - w1) B + sqrt(w0) w1 C, nothing to redraw), draw theta from first_cdf (one row, edges linspace(first_lo, first_hi, n_first); NO sin(theta)
    * factor, :530) and phi uniform in [0, 2pi) (:544), then
    *   d = cos(theta) n + sin(theta) (cos(phi) (t x n) + sin(phi) t)        [= R(n,phi) R(t,theta) n, :85-111]
    * with n the outward face normal and t the unit u-tangent (the longer of the u/v tangents when |dP/du| <= 10 dist_tol).

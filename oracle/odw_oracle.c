@@ -631,6 +631,22 @@ static int surface_draw_uv(const odw_face* f, double w0, double w1, double w2, d
   }
 }
 
+/* a plane face trimmed to exactly one triangle (three chained straight pcurves; what a tessellated emitter consists of):
+ * tri = (u, v) of its corners.  Such a face is sampled without rejection (include/odw.h, surface sources). */
+static int emit_triangle(const odw_face* f, const odw_trimseg* segs, double* tri) {
+  if (f->kind != ODW_SURF_PLANE || f->trim_kind != ODW_TRIM_LOOPS || f->seg_count != 3 || !segs) return 0;
+  const odw_trimseg* g = segs + f->seg_first;
+  double scale = 0;
+  for (int k = 0; k < 3; ++k) { if (g[k].kind != ODW_SEG_LINE) return 0; for (int j = 0; j < 4; ++j) scale = fmax(scale, fabs(g[k].a[j])); }
+  double eps = 1e-9*fmax(scale, 1e-300);
+  for (int k = 0; k < 3; ++k) {
+    const odw_trimseg* a = &g[k]; const odw_trimseg* b = &g[(k + 1) % 3];
+    if (fabs(a->a[2] - b->a[0]) > eps || fabs(a->a[3] - b->a[1]) > eps) return 0;
+    tri[2*k] = a->a[0]; tri[2*k + 1] = a->a[1];
+  }
+  return 1;
+}
+
 #define ODW_SURFACE_MAX_TRIES 64
 static void surface_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t ray, double* theta_out, double* phi_out,
                              double* origin, double* dir) {
@@ -640,7 +656,14 @@ static void surface_make_ray(const odw_source_desc* s, uint64_t seed, uint64_t r
   int k = 0, hi = s->n_emit-1;                                   /* first face with a[0] < emit_cdf[k] (binary search) */
   while (k < hi) { int m = (k + hi) >> 1; if (a[0] < s->emit_cdf[m]) hi = m; else k = m + 1; }
   const odw_face* f = &s->emit_faces[k];
-  double P[3], du[3], dv[3], u = 0, v = 0;
+  double P[3], du[3], dv[3], u = 0, v = 0, tri[6];
+  if (emit_triangle(f, s->emit_segs, tri)) {                        /* area-uniform point of a triangle from two uniforms */
+    double w[2];
+    oracle_philox(seed, (uint32_t)s->source_id, ray, 2, w);
+    double sq = sqrt(w[0]), b1 = sq*(1.0 - w[1]), b2 = sq*w[1], b0 = 1.0 - sq;
+    u = b0*tri[0] + b1*tri[2] + b2*tri[4]; v = b0*tri[1] + b1*tri[3] + b2*tri[5];
+    surface_eval(f, u, v, P, du, dv);
+  } else
   for (uint32_t tr = 0; tr < ODW_SURFACE_MAX_TRIES; ++tr) {
     double w[2], w2[2];
     oracle_philox(seed, (uint32_t)s->source_id, ray, 2 + tr, w);
