@@ -24,12 +24,15 @@ extern "C" cudaError_t odw_wf_generate(const TraceParams* p, bool mc, void* pool
 extern "C" cudaError_t odw_wf_traverse(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n,
                                        unsigned int* fetch_counter, const unsigned int* order, void* pool_ordered, int need, int blocks, cudaStream_t st);
 extern "C" cudaError_t odw_wf_interact(const TraceParams* p, bool mc, void* pool_in, void* hits, void* pool_out, size_t cap, float bound,
-                                       unsigned int n, unsigned int* n_next, int bounce, cudaStream_t st);
+                                       unsigned int n, unsigned int* n_next, int bounce, int keys, cudaStream_t st);
 extern "C" cudaError_t odw_wf_iota(unsigned int* v, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, size_t cap, unsigned int* keys_out, const unsigned int* iota,
                                    unsigned int* order, unsigned int n, cudaStream_t st);
 extern "C" cudaError_t odw_wf_tail(const TraceParams* p, bool mc, void* pool, size_t cap, unsigned int n, int bounce, cudaStream_t st);
 extern "C" int odw_wf_traverse_occupancy(int n_nodes);
+extern "C" cudaError_t odw_wf_traverse4(const TraceParams* p, void* pool, size_t cap, void* hits, unsigned int n, unsigned int* fetch_counter,
+                                        const unsigned int* order, void* pool_ordered, int need, int regen, int blocks, cudaStream_t st);
+extern "C" cudaError_t odw_wf_generate_keys(const TraceParams* p, void* pool, size_t cap, float bound, unsigned int n, cudaStream_t st);
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -98,6 +101,8 @@ struct odw_scene {
   std::vector<BvhNode2> bvh_staging;    // widened copy being uploaded
   BvhNode2* bvh_dev = nullptr;
   float bvh_margin = -1.0f;             // margin the device copy currently carries
+  std::vector<Bvh4Node> bvh4_host, bvh4_staging;   // 4-wide tree of the wavefront traversal, same protocol
+  Bvh4Node* bvh4_dev = nullptr;
 };
 
 struct odw_source {
@@ -278,6 +283,57 @@ struct BvhBuilder {
     return out;
   }
 
+  // 4-wide tree (Bvh4Node): every inner node of the binary tree that becomes a 4-wide node adopts up to four descendants —
+  // its two children, the larger (by box area) of which is replaced by ITS children while there is room.  Nodes are numbered
+  // breadth-first (the top of the tree first).  compact_of[face] >= 0: the face has a compact record (a whole sphere) and
+  // its leaf entry is ~compact_of[face].  depth_out = levels of the 4-wide tree (bounds the traversal stack: 3 per level).
+  void wide4(const std::vector<int>& compact_of, std::vector<Bvh4Node>& out, std::vector<int32_t>& prims4, int* depth_out) const {
+    out.clear(); prims4.clear(); *depth_out = 1;
+    auto area = [&](int i) { const BvhNode& n = nodes[(size_t)i];
+                             const double d[3] = { (double)n.hi[0]-n.lo[0], (double)n.hi[1]-n.lo[1], (double)n.hi[2]-n.lo[2] };
+                             return d[0]*d[1] + d[1]*d[2] + d[2]*d[0]; };
+    auto leaf_ref = [&](const BvhNode& c) {
+      const int first = (int)prims4.size();
+      for (int k = 0; k < c.count; ++k) { const int f = prims[(size_t)c.left + k]; prims4.push_back(compact_of[(size_t)f] >= 0 ? ~compact_of[(size_t)f] : f); }
+      return -2 - ((first << 3) | (std::min(c.count, 8) - 1));      // -1 is the traversal's "done"
+    };
+    auto empty_node = [] { Bvh4Node w; memset(&w, 0, sizeof w);
+                           for (int a = 0; a < 3; ++a) for (int k = 0; k < 4; ++k) { w.b[2*a][k] = 3.0e38f; w.b[2*a+1][k] = -3.0e38f; }
+                           for (int k = 0; k < 4; ++k) w.ref[k] = -1; return w; };
+    auto set_slot = [&](Bvh4Node& w, int k, const BvhNode& c, int ref) {
+      for (int a = 0; a < 3; ++a) { w.b[2*a][k] = c.lo[a]; w.b[2*a+1][k] = c.hi[a]; }
+      w.ref[k] = ref;
+    };
+    if (prims.empty()) { out.push_back(empty_node()); return; }
+    if (nodes[0].count != 0) {                        // the root is a leaf
+      Bvh4Node w = empty_node(); set_slot(w, 0, nodes[0], leaf_ref(nodes[0])); out.push_back(w); return;
+    }
+    struct Pending { int bnode, level; };
+    std::vector<Pending> queue(1, Pending{0, 1});
+    std::vector<std::vector<int>> kids;               // binary node ids adopted by each 4-wide node
+    for (size_t h = 0; h < queue.size(); ++h) {
+      std::vector<int> c = { nodes[(size_t)queue[h].bnode].left, nodes[(size_t)queue[h].bnode].left + 1 };
+      while (c.size() < 4) {
+        int pick = -1;
+        for (size_t k = 0; k < c.size(); ++k) if (nodes[(size_t)c[k]].count == 0 && (pick < 0 || area(c[k]) > area(c[(size_t)pick]))) pick = (int)k;
+        if (pick < 0) break;
+        const int b = c[(size_t)pick];
+        c[(size_t)pick] = nodes[(size_t)b].left; c.push_back(nodes[(size_t)b].left + 1);
+      }
+      for (int b : c) if (nodes[(size_t)b].count == 0) queue.push_back(Pending{b, queue[h].level + 1});
+      *depth_out = std::max(*depth_out, queue[h].level);
+      kids.push_back(c);
+    }
+    // queue order = node numbering: the inner children of node h were appended in the order of kids[h]
+    out.assign(queue.size(), empty_node());
+    size_t next = 1;
+    for (size_t h = 0; h < queue.size(); ++h)
+      for (size_t k = 0; k < kids[h].size(); ++k) {
+        const BvhNode& c = nodes[(size_t)kids[h][k]];
+        if (c.count == 0) set_slot(out[h], (int)k, c, (int)next++); else set_slot(out[h], (int)k, c, leaf_ref(c));
+      }
+  }
+
   void recurse(int node, int first, int count, int depth) {
     Box bb; bb.reset(); Box cb; cb.reset();
     for (int i = first; i < first + count; ++i) {
@@ -285,7 +341,7 @@ struct BvhBuilder {
       for (int a = 0; a < 3; ++a) { double c = 0.5*(b.lo[a] + b.hi[a]); cb.lo[a] = std::min(cb.lo[a], c); cb.hi[a] = std::max(cb.hi[a], c); }
     }
     set_box(nodes[node], bb);
-    const int LEAF = 2, NB = 16;
+    const int LEAF = 1, NB = 16;            // one primitive per leaf: a leaf's box is the primitive's own box (tightest cull before the exact test)
     int best_axis = -1, best_split = -1; double best_cost = 1e300;
     if (count > LEAF && depth < 24) {      // deeper than 24: median splits only, so the depth stays below 24 + log2(n) < ODW_BVH_STACK
       for (int a = 0; a < 3; ++a) {
@@ -574,6 +630,40 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     if ((rc = upload(eng, sc->owned, b.prims.data(), b.prims.size(), &sc->d.bvh_prims))) { odw_scene_destroy(sc); return rc; }
     sc->d.n_bvh_nodes = (int)sc->bvh_host.size();
     sc->smem = 0;
+    // 4-wide tree + compact sphere records for the wavefront traversal (odw_wavefront.cu wf_traverse4)
+    {
+      std::vector<int> compact_of((size_t)sd->n_faces, -1);
+      std::vector<DSphere> spheres; std::vector<int2> info;
+      for (int i = 0; i < sd->n_faces; ++i) {
+        const odw_face& f = sd->faces[i];
+        if (f.kind == ODW_SURF_SPHERE && f.trim_kind == ODW_TRIM_NONE) {
+          compact_of[(size_t)i] = (int)spheres.size();
+          spheres.push_back(DSphere{ f.origin[0], f.origin[1], f.origin[2], f.p0 });
+          info.push_back(make_int2(i, f.group));
+        }
+      }
+      std::vector<int32_t> prims4; int depth4 = 1;
+      b.wide4(compact_of, sc->bvh4_host, prims4, &depth4);
+      bool use4 = 3*depth4 + 1 <= ODW_BVH_STACK;                    // the traversal stacks up to three siblings per level
+      if (const char* w = getenv("ODW_BVH4")) use4 = use4 && atoi(w) != 0;
+      if (use4) {
+        const Bvh4Node* dev4 = nullptr;
+        if ((rc = upload(eng, sc->owned, sc->bvh4_host.data(), sc->bvh4_host.size(), &dev4))) { odw_scene_destroy(sc); return rc; }
+        sc->bvh4_dev = const_cast<Bvh4Node*>(dev4); sc->d.bvh4 = dev4; sc->d.n_bvh4_nodes = (int)sc->bvh4_host.size();
+        if ((rc = upload(eng, sc->owned, prims4.data(), prims4.size(), &sc->d.bvh4_prims))) { odw_scene_destroy(sc); return rc; }
+        sc->d.n_bvh4_prims = (int)prims4.size();
+        if ((rc = upload(eng, sc->owned, spheres.data(), spheres.size(), &sc->d.spheres))) { odw_scene_destroy(sc); return rc; }
+        if ((rc = upload(eng, sc->owned, info.data(), info.size(), &sc->d.sphere_info))) { odw_scene_destroy(sc); return rc; }
+        sc->d.n_spheres = (int)spheres.size(); sc->d.bvh_depth = depth4;
+        std::vector<ulonglong2> gmask((size_t)sd->n_groups, make_ulonglong2(0ull, 0ull));
+        for (int st = 0; st < sd->n_seq_steps; ++st)
+          for (int k = sd->seq_offsets[st]; k < sd->seq_offsets[st+1]; ++k) {
+            const int g = sd->seq_groups[k];
+            if (g >= 0 && g < sd->n_groups) { if (st < 64) gmask[(size_t)g].x |= 1ull << st; else gmask[(size_t)g].y |= 1ull << (st - 64); }
+          }
+        if ((rc = upload(eng, sc->owned, gmask.data(), gmask.size(), &sc->d.group_seqmask))) { odw_scene_destroy(sc); return rc; }
+      }
+    }
   } else {
     sc->smem = std::max<size_t>(16, faces.size()*sizeof(DFace) + shells.size()*sizeof(DShell));
   }
@@ -815,7 +905,16 @@ static int ensure_bvh_margin(odw_scene* sc, float margin) {
       if (w.count[1] >= 0) { w.lo1[a] = std::nextafter(w.lo1[a] - margin, -INFINITY); w.hi1[a] = std::nextafter(w.hi1[a] + margin, INFINITY); }
     }
   CU(cudaMemcpyAsync(sc->bvh_dev, sc->bvh_staging.data(), sc->bvh_staging.size()*sizeof(BvhNode2), cudaMemcpyHostToDevice, sc->eng->stream));
-  CU(cudaStreamSynchronize(sc->eng->stream));      // the staging vector is pageable and reused
+  if (sc->bvh4_dev) {
+    sc->bvh4_staging = sc->bvh4_host;
+    for (Bvh4Node& w : sc->bvh4_staging)
+      for (int k = 0; k < 4; ++k) {
+        if (w.b[0][k] > w.b[1][k]) continue;                       // empty slot
+        for (int a = 0; a < 3; ++a) { w.b[2*a][k] = std::nextafter(w.b[2*a][k] - margin, -INFINITY); w.b[2*a+1][k] = std::nextafter(w.b[2*a+1][k] + margin, INFINITY); }
+      }
+    CU(cudaMemcpyAsync(sc->bvh4_dev, sc->bvh4_staging.data(), sc->bvh4_staging.size()*sizeof(Bvh4Node), cudaMemcpyHostToDevice, sc->eng->stream));
+  }
+  CU(cudaStreamSynchronize(sc->eng->stream));      // the staging vectors are pageable and reused
   sc->bvh_margin = margin;
   return ODW_OK;
 }
@@ -861,12 +960,17 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
         (rc = eng->alloc(&pool_c, cap*odw_wf_pool_bytes_per_ray()))) { cleanup(); return rc; }
     if ((es = odw_wf_iota(iota, n0, eng->stream)) != cudaSuccess) { cleanup(); return fail(ODW_ECUDA, std::string("wavefront sort: ") + cudaGetErrorString(es)); }
   } else sort_bounces = 0;
-  unsigned int tail = 8192;
+  unsigned int tail = 65536;             // measured on hugeArray: 2048 / 8192 / 65536 -> 4.55 / 4.83 / 4.87e9 segments/s
   if (const char* w = getenv("ODW_WAVEFRONT_TAIL")) { long long v = atoll(w); if (v >= 0) tail = (unsigned int)v; }
   const int blocks = eng->sm_count*std::max(1, odw_wf_traverse_occupancy(q.scene.n_bvh_nodes));
   cudaStream_t st = eng->stream;
   unsigned int* host_n = reinterpret_cast<unsigned int*>(&eng->pinned_counters[2]);     // page-locked scratch of its own: [0], [1] hold chunk counters the host may not have read yet
-  cudaError_t e = odw_wf_generate(&q, mc, pool_a, cap, bound, n0, st);
+  const bool wide = q.scene.bvh4 != nullptr;                                            // 4-wide traversal (wf_traverse4)
+  // Monte-Carlo rays of a sorted first bounce are drawn twice: once for their coherence key, once by the traversal in coherence
+  // order — cheaper than storing them and gathering five 16-byte columns per ray from unrelated addresses
+  bool regen = wide && mc && sort_bounces > 0 && q.max_isect > 0 && n0 > tail;
+  if (const char* w = getenv("ODW_WF_REGEN")) regen = regen && atoi(w) != 0;
+  cudaError_t e = regen ? odw_wf_generate_keys(&q, pool_a, cap, bound, n0, st) : odw_wf_generate(&q, mc, pool_a, cap, bound, n0, st);
   if (launches) ++*launches;
   unsigned int n = q.max_isect > 0 ? n0 : 0;
   void *cur = pool_a, *nxt = pool_b;
@@ -876,8 +980,12 @@ static int run_wavefront_wave(odw_engine* eng, const TraceParams& q, bool mc, fl
     const bool sorted = bounce < sort_bounces && n >= sort_min;
     if (sorted) { if ((e = odw_wf_sort(sort_temp, &temp_bytes, cur, cap, keys_out, iota, order, n, st)) != cudaSuccess) break; }
     // sorted: the traversal moves every ray to its place in the ordered pool (pool_c) and the interaction reads that one
+    if (wide) {
+      if ((e = odw_wf_traverse4(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, pool_c, need, (regen && bounce == 0 && sorted) ? 1 : 0,
+                                eng->sm_count, st)) != cudaSuccess) break;
+    } else
     if ((e = odw_wf_traverse(&q, cur, cap, hits, n, ctr + 1, sorted ? order : nullptr, pool_c, need, blocks, st)) != cudaSuccess) break;
-    if ((e = odw_wf_interact(&q, mc, sorted ? pool_c : cur, hits, nxt, cap, bound, n, ctr, bounce, st)) != cudaSuccess) break;
+    if ((e = odw_wf_interact(&q, mc, sorted ? pool_c : cur, hits, nxt, cap, bound, n, ctr, bounce, bounce + 1 < sort_bounces ? 1 : 0, st)) != cudaSuccess) break;
     if (launches) *launches += 2;
     if ((e = cudaMemcpyAsync(host_n, ctr, sizeof(unsigned int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
@@ -908,8 +1016,8 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   // 2^19 up (wave size x stream count sweep in profiles/README.md: 29.5-29.9 ms per 1e8 rays for 2^19..2^23 rays on 2-8
   // streams, 30.5 ms for one stream of 2^23-ray waves; with the earlier fixed lane -> ray stride the optimum was 2^18 rays on 4
   // streams and one stream cost 50 % more).
-  uint64_t wave = sc->use_bvh ? (1ull << 24)                   // BVH scenes: big waves amortise the per-bounce host round trip
-                              : (1ull << 21);
+  uint64_t wave = sc->use_bvh ? (1ull << 25)                   // BVH scenes: big waves amortise the per-bounce host round trip and the
+                              : (1ull << 21);                  // thin last bounces (hugeArray: 4.59e9 at 2^24, 4.83e9 at 2^25 rays per wave)
   if (const char* w = getenv("ODW_RAYS_PER_LAUNCH")) { long long v = atoll(w); if (v > 0) wave = (uint64_t)v; }
   wave = std::min<uint64_t>(wave, 1ull << 31);
   wave = std::max<uint64_t>(wave, (p.n_rays + odw_engine::MAX_WAVES - 1)/odw_engine::MAX_WAVES);   // one claim counter per wave

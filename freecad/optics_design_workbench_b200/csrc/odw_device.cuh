@@ -79,7 +79,29 @@ struct BvhNode2 {
   int32_t child[2], count[2];
 };
 
+// 4-wide node of the wavefront traversal (odw_wavefront.cu): the fp32 boxes of up to four children, axis by axis, and their
+// references.  128 B = eight 16-byte words: 0..5 = lo.x, hi.x, lo.y, hi.y, lo.z, hi.z of the four children, 6 = references,
+// 7 unused.  An empty slot has lo = +3e38, hi = -3e38 (never hit).  Reference: >= 0 inner node; <= -2: leaf, -2 - ref = first entry
+// of bvh4_prims << 3 | (entries - 1) (-1 = the traversal's "done").  A prims entry >= 0 is a face index (DScene::faces, general test); < 0 is ~index into
+// the compact table of whole spheres (DScene::spheres).  Boxes are stored rounded outward and already widened by the launch's
+// culling margin, like BvhNode2.
+struct Bvh4Node {
+  float b[6][4];                   // words 0..5: lo.x, hi.x, lo.y, hi.y, lo.z, hi.z (near / far plane of an axis = word 2a ^ (direction < 0))
+  int32_t ref[4];
+  int32_t pad[4];
+};
+
+// Whole sphere (surface kind sphere, no trim: the unit spheres of hugeArray's Draft arrays) as the traversal's compact leaf:
+// 32 B instead of the 272 B face record; face index and optical group sit in DScene::sphere_info.
+struct DSphere { double cx, cy, cz, r; };
+
 struct DScene {
+  const Bvh4Node* bvh4;            // wavefront traversal: 4-wide tree over the same face boxes (nullptr: none)
+  const int32_t* bvh4_prims;
+  const DSphere* spheres;
+  const int2* sphere_info;         // (face index, optical group) of each compact sphere
+  const ulonglong2* group_seqmask; // [n_groups]: bit s set <=> the group is in SequentialModeElements step s (the faces' seqmask, per group)
+  int32_t n_bvh4_nodes, n_bvh4_prims, n_spheres, bvh_depth;
   const DFace* faces;
   const DShell* shells;
   const odw_trimseg* segs;
@@ -107,6 +129,7 @@ struct DSource {
 };
 #define ODW_EMIT_GUIDE 65536
 #define ODW_GUIDE 4096
+#define ODW_BVH_STACK 64           // entries of a traversal stack (the builders bound the tree depth accordingly)
 
 struct HitBuffers {
   double* points; double* dirs; double* powers;

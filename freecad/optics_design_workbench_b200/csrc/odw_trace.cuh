@@ -204,7 +204,6 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
 // same rule, faces reached through a BVH over face boxes (replaces the shell/face BoundBox culls of ray.py:345-404).
 // Conservative fp32 slab tests on boxes widened by the culling margin; near child first, the far child is pushed with
 // its entry distance and dropped at pop time if a closer hit has been accepted meanwhile.
-#define ODW_BVH_STACK 64
 template <int FEAT>
 __device__ __forceinline__ int find_nearest_bvh(const TraceParams& p, const double* s, const double* dn,
                                                 int medium, int seq_index, double max_len, double& t_out) {

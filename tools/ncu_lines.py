@@ -9,7 +9,7 @@ def main():
   top = int(sys.argv[5]) if len(sys.argv) > 5 else 60
   tmp = tempfile.mkdtemp()
   subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-  cubin = [f for f in os.listdir(tmp) if f.startswith('odw_kernels.')][0]
+  cubin = [f for f in os.listdir(tmp) if f.startswith(os.environ.get('ODW_CUBIN', 'odw_kernels')+'.')][0]
   sass = subprocess.run(['nvdisasm', '-g', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split('\n')
   start = [i for i, l in enumerate(sass) if l.startswith('.text.') and kern in l][0]
   end = next((i for i in range(start+1, len(sass)) if sass[i].startswith('//--------------------- .text')), len(sass))
