@@ -555,6 +555,15 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     if (face_count > 0) { d.seqmask[0] = faces[(size_t)face_first].seqmask[0]; d.seqmask[1] = faces[(size_t)face_first].seqmask[1]; }
     return d;
   };
+  auto pair_planes = [&](int face_first, int face_count) {
+    // opposite faces of a box come as consecutive planes with the SAME normal vector (the orientation is in nsign): the first
+    // of such a pair is flagged, the shared-memory kernel then tests both with one reciprocal and one set of dot products
+    for (int f = face_first; f + 1 < face_first + face_count; ++f) {
+      DFace& a = faces[(size_t)f]; const DFace& b = faces[(size_t)f + 1];
+      const bool planes = a.kind == ODW_SURF_PLANE && b.kind == ODW_SURF_PLANE && (a.flags & DFACE_FAST) && (b.flags & DFACE_FAST);
+      if (planes && a.z[0] == b.z[0] && a.z[1] == b.z[1] && a.z[2] == b.z[2]) { a.flags |= DFACE_PAIR; ++f; }
+    }
+  };
   if (sd->n_shells > 0 && sd->shells) {
     for (int i = 0; i < sd->n_shells; ++i) {
       const odw_shell& h = sd->shells[i];
@@ -563,6 +572,7 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
       for (int f = h.face_first; f < h.face_first + h.face_count; ++f)
         if (sd->faces[f].group != h.group) return fail(ODW_EINVAL, "shell " + std::to_string(i) + ": faces of a shell must share its group");
       shells.push_back(make_shell(h.face_first, h.face_count, h.group));
+      pair_planes(h.face_first, h.face_count);
     }
     std::vector<char> covered((size_t)sd->n_faces, 0);
     for (const DShell& d : shells) for (int f = d.face_first; f < d.face_first + d.face_count; ++f) covered[(size_t)f]++;

@@ -27,6 +27,8 @@ struct DFace {
 #define DFACE_FULL_U 1             // u range spans the whole period: no azimuth test needed
 #define DFACE_FAST   2             // plane/uvbox, plane/disc, sphere (whole or full-u cap), cylinder (full-u band): inline test
 #define DFACE_DISC   4             // plane whose only trim loop is one full circle: umin,vmin = centre, umax = radius
+#define DFACE_PAIR   16            // a DFACE_FAST plane whose NEXT face (same shell) is a DFACE_FAST plane with the same normal: opposite
+                                   // faces of a box share the reciprocal and the two dot products of the plane test (find_nearest_smem)
 #define DFACE_TRI    8             // EMITTING faces only: plane trimmed to one triangle (a tessellated emitter), aux[0..5] = its corners (u, v)
 
 // Shell record: the first-level cull of ray.py:345-374 (shell BoundBox enlarged by distTol).  The box is fp32,

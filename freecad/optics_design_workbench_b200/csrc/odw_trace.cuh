@@ -98,6 +98,28 @@ __device__ __forceinline__ void accept_hit(double t, int idx, int group, int med
   if (group != medium && t < h.tB) { h.tB = t; h.fB = idx; }
 }
 
+// trimmed part of the plane fast paths: the crossing at parameter t against the rectangle / disc dilated by the tolerance
+__device__ __forceinline__ void plane_accept(const DFace& f, int idx, double t, const double* s, const double* dn, int medium, double tol, NearestHit& h) {
+  if (t > tol && t < h.lim) {
+    const double Px = fma(t, dn[0], s[0]), Py = fma(t, dn[1], s[1]), Pz = fma(t, dn[2], s[2]);
+    const double u = dot3(Px, Py, Pz, f.x) - f.c1, v = dot3(Px, Py, Pz, f.y) - f.c2;
+    if (f.flags & DFACE_DISC) {
+      // one full circle as the only trim loop (every lens flat): distance of P to the disc < tol  <=>  rho < r + tol
+      const double du = u - f.umin, dv = v - f.vmin, rr = f.umax + tol;
+      if (du*du + dv*dv < rr*rr) accept_hit(t, idx, f.group, medium, tol, h);
+    } else if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, tol, h);
+  }
+}
+
+// two planes with the same normal (opposite faces of a box, DFACE_PAIR): one reciprocal and one pair of dot products serve
+// both; each t is bit-identical to what test_face computes for the face alone
+__device__ __forceinline__ void test_plane_pair(const DFace& fa, const DFace& fb, int idx, const double* s, const double* dn, int medium, double tol, NearestHit& h) {
+  const double r = fast_rcp(dot3(dn, fa.z)), sz = dot3(s, fa.z);
+  const double ta = (fa.c0 - sz)*r, tb = (fb.c0 - sz)*r;
+  plane_accept(fa, idx, ta, s, dn, medium, tol, h);
+  plane_accept(fb, idx + 1, tb, s, dn, medium, tol, h);
+}
+
 // One face against the line start + t*dn (ray.py:407-432).  tmax = maxRayLength + distTol.
 // Fast paths (inline, no division / inverse trigonometry): rectangle on a plane, whole sphere or spherical cap/zone
 // with full azimuth, cylinder band with full azimuth.  Everything else goes through test_face_general.
@@ -118,15 +140,7 @@ __device__ __forceinline__ void test_face(const DFace& f, int idx, const TracePa
   if (f.kind == ODW_SURF_PLANE) {
     const double den = dot3(dn, f.z);
     const double t = (f.c0 - dot3(s, f.z))*fast_rcp(den);            // den == 0: inf/NaN fails the range test
-    if (t > tol && t < limit) {
-      const double Px = fma(t, dn[0], s[0]), Py = fma(t, dn[1], s[1]), Pz = fma(t, dn[2], s[2]);
-      const double u = dot3(Px, Py, Pz, f.x) - f.c1, v = dot3(Px, Py, Pz, f.y) - f.c2;
-      if (f.flags & DFACE_DISC) {
-        // one full circle as the only trim loop (every lens flat): distance of P to the disc < tol  <=>  rho < r + tol
-        const double du = u - f.umin, dv = v - f.vmin, rr = f.umax + tol;
-        if (du*du + dv*dv < rr*rr) accept_hit(t, idx, f.group, medium, tol, h);
-      } else if (u >= f.umin - tol && u <= f.umax + tol && v >= f.vmin - tol && v <= f.vmax + tol) accept_hit(t, idx, f.group, medium, tol, h);
-    }
+    plane_accept(f, idx, t, s, dn, medium, tol, h);
     return;
   }
   // sphere / cylinder: a t^2 + 2 b t + c = 0 in the coordinates of the axis frame
@@ -168,13 +182,16 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
   const double tmax = max_len + tol;
   NearestHit h; h.tA = 1e300; h.tB = 1e300; h.lim = tmax; h.fA = -1; h.fB = -1;
   const float sx = (float)s[0], sy = (float)s[1], sz = (float)s[2];
-  // MUFU reciprocal: 1 ulp, inside the culling margin; 1/0 = inf is fine.  (The slab distances must stay
-  // (lo - s)*inv: as one FMA, lo*inv - s*inv, an axis-parallel ray gives inf - inf = NaN for ONE side of a slab and
-  // the other side then serves as both entry and exit — measured: every ray of a collimated source was culled.)
+  // MUFU reciprocal: 1 ulp, inside the culling margin.  An axis-parallel direction gets a huge FINITE reciprocal, so that the
+  // slab distances can be one FMA each, plane * inv + (-origin * inv), without inf - inf = NaN (with an infinite reciprocal
+  // ONE side of a slab became NaN and the other served as both entry and exit — measured: every ray of a collimated source
+  // was culled).  The FMA form carries an error of 2^-23 |origin| in position, like the rounding of the origin itself: inside the margin.
   float ix, iy, iz;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ix) : "f"((float)dn[0]));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iy) : "f"((float)dn[1]));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dn[2]));
+  ix = fminf(fmaxf(ix, -1e30f), 1e30f); iy = fminf(fmaxf(iy, -1e30f), 1e30f); iz = fminf(fmaxf(iz, -1e30f), 1e30f);
+  const float cx = -sx*ix, cy = -sy*iy, cz = -sz*iz;
   float limf = (float)tmax*1.000002f;                                  // nothing beyond this can still matter
   const bool seq_off = !(FEAT & FEAT_SEQ) || !p.sequential;
   const bool seq_dead = seq_index >= 128;
@@ -184,16 +201,19 @@ __device__ __forceinline__ int find_nearest_smem(const DShell* sshells, const DF
     const DShell& sh = sshells[si];
     if (si == skip_shell) continue;
     if (!seq_off && (seq_dead || !((sh.seqmask[sw] >> sb) & 1ull))) continue;
-    float ta = (sh.lo[0] - sx)*ix, tb = (sh.hi[0] - sx)*ix;             // NaN (0*inf) is dropped by fminf/fmaxf
+    float ta = fmaf(sh.lo[0], ix, cx), tb = fmaf(sh.hi[0], ix, cx);
     float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
-    ta = (sh.lo[1] - sy)*iy; tb = (sh.hi[1] - sy)*iy;
+    ta = fmaf(sh.lo[1], iy, cy); tb = fmaf(sh.hi[1], iy, cy);
     t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
-    ta = (sh.lo[2] - sz)*iz; tb = (sh.hi[2] - sz)*iz;
+    ta = fmaf(sh.lo[2], iz, cz); tb = fmaf(sh.hi[2], iz, cz);
     t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
     // miss, entirely behind the start, or beyond what can still matter
     if (t0 > t1 || t1 < 0.0f || t0 > limf) continue;
     const int f1 = sh.face_first + sh.face_count;
-    for (int i = sh.face_first; i < f1; ++i) test_face<false, FEAT>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
+    for (int i = sh.face_first; i < f1; ++i) {
+      if (sfaces[i].flags & DFACE_PAIR) { test_plane_pair(sfaces[i], sfaces[i+1], i, s, dn, medium, tol, h); ++i; }
+      else test_face<false, FEAT>(sfaces[i], i, p, s, dn, medium, seq_index, tmax, h);
+    }
     limf = (float)h.lim*1.000002f;
   }
   if (h.fA < 0) return -1;
