@@ -8,7 +8,9 @@ hits come back as arrays, grouped per optical group and appended to the store in
 (optical_group.py:206-209 -> results_store.py:641-648 semantics: only groups with RecordHits).
 
 Same name, same keyword arguments, same side effects on `store` (hits, totalTracedRays).  `draw=True`
-(GUI ray drawing through Part.makeLine, :102-138) has no meaning without FreeCAD and raises.
+(GUI ray drawing, :102-138): the rays are traced on the GPU with every intersection recorded and their polylines go to
+a drawing back end (freecad_elements/ray_drawing.py: the reference's Part.makeLine / RaySegment calls inside FreeCAD, a
+recording back end elsewhere).
 '''
 
 import numpy as np
@@ -66,7 +68,7 @@ class GenericSourceProxy:
 
   # -- the iteration --------------------------------------------------------------------------------
   def runSimulationIteration(self, obj=None, *, mode, draw=False, store=False, returnInitialConditions=False,
-                             useInitialConditions=None, iterations=1, **kwargs):
+                             useInitialConditions=None, iterations=1, drawBackend=None, sourceObject=None, **kwargs):
     '''
     mode 'true'  : `iterations` Monte-Carlo iterations of RaysPerIteration*RaysPerIterationScale rays each in ONE
                    engine call (odw_trace_mc), drawn on the device from the Philox stream (seed, source id) at
@@ -77,9 +79,26 @@ class GenericSourceProxy:
     '''
     ctx = self.context
     obj = obj if obj is not None else self.record
-    if draw:
-      raise NotImplementedError('draw=True builds FreeCAD Part objects; keep the reference path for displayed rays')
     kind = obj.get('proxy', 'PointSourceProxy')
+    if draw:
+      # displayed rays (generic_source.py:102-138): traced as an explicit list with every intersection recorded, then drawn
+      from . import ray_drawing
+      backend = drawBackend if drawBackend is not None else ray_drawing.default_backend()
+      if useInitialConditions is not None:
+        batch = useInitialConditions
+      elif mode in ('fans', 'multicorefans'):
+        batch = self._generateRays(obj, mode='fans', **kwargs)
+      elif mode in ('pseudo', 'singlepseudo'):
+        batch = self._pseudo_rays(obj, int(iterations))
+      elif kind == 'ReplaySourceProxy':
+        raise NotImplementedError('drawing the rays of a replay source')
+      else:
+        first, n = ctx.claim_rays(self.index, point_source.rays_per_iteration(obj, ctx.sim.settings)*int(iterations))
+        smp = ctx.device_source(self.index).sample(ctx.seed, first, n)
+        batch = point_source.RayBatch(smp['origins'], smp['directions'], np.ones(n), float(obj['Wavelength']), {})
+      counts, rays = self._trace_explicit(obj, batch, store, record_rays=bool(store and obj.get('RecordRays', False)), return_rays=True)
+      ray_drawing.draw_rays(sourceObject if sourceObject is not None else obj, rays, obj.get('gpM', np.eye(4)), backend)
+      return counts
     if kind not in ('PointSourceProxy', 'SurfaceSourceProxy', 'ReplaySourceProxy'):
       raise NotImplementedError(f"light source kind {kind} is not handled by the engine yet")
     if kind == 'ReplaySourceProxy':
@@ -179,19 +198,23 @@ class GenericSourceProxy:
         out.append(dict(points=np.array(pts), powers=np.array(powers[:n_seg]), media=media))
     return out
 
-  def _trace_explicit(self, obj, batch, store, record_rays=False):
+  def _trace_explicit(self, obj, batch, store, record_rays=False, return_rays=False):
+    'return_rays: also return the per-ray polylines (for drawing); every intersection is recorded then, stored or not'
     ctx = self.context
-    cfg = ctx.cfg(obj, store_hits=bool(store), record_all_hits=bool(record_rays),
+    want_rays = bool(return_rays or (store and record_rays))
+    cfg = ctx.cfg(obj, store_hits=bool(store or return_rays), record_all_hits=want_rays,
                   hit_capacity=max(1024, len(batch)*int(ctx.sim.settings['MaxIntersections'])),
                   wavelength=batch.wavelength, scatter_seed=ctx.seed,
                   max_ray_length=float(ctx.sim.settings['MaxRayLength'])*float(obj.get('MaxRayLengthScale', 1.0)),
                   max_intersections=int(float(ctx.sim.settings['MaxIntersections'])*float(obj.get('MaxIntersectionsScale', 1.0))))
     with ctx.device_scene.trace_rays(cfg, batch.origins, batch.directions, batch.powers, ignored=obj.get('ignored', ())) as res:
       counts = res.counts
-      hits = res.hits(sort=True) if store else None
-      summary = res.ray_summary() if (store and record_rays) else None
+      hits = res.hits(sort=True) if (store or return_rays) else None
+      summary = res.ray_summary() if want_rays else None
+    rays = self._ray_dicts(obj, batch, hits, summary) if want_rays else None
     if store and record_rays:
-      store.addRays(results_store.named((obj['name'], obj['label'])), self._ray_dicts(obj, batch, hits, summary))
+      store.addRays(results_store.named((obj['name'], obj['label'])), rays)
+    if want_rays and hits is not None:
       keep = ctx.sim.scene.groups['record_hits'][hits['group']] != 0        # onRayHit only stores RecordHits groups
       hits = {k: v[keep] for k, v in hits.items()}
     if store:
@@ -208,7 +231,7 @@ class GenericSourceProxy:
         return md
       self._store_hits(obj, hits, store, metadata_of)
       store.incrementRayCount(len(batch))
-    return counts
+    return (counts, rays) if return_rays else counts
 
   def _trace_monte_carlo_recording_rays(self, obj, iterations, store):
     '''

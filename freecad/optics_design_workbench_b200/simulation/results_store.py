@@ -334,6 +334,16 @@ class SimulationResults:
     atomic_write_bytes(f'{self.progressMonitorPath()}/master-{self._masterProgressDumpIdx:09d}', pickle.dumps(d))
     self._masterProgressDumpIdx += 1
     self._lastMasterProgressDump = time.time()
+    # like the reference (results_store.py:527-539): master files older than 10 s are removed, the newest always stays
+    mine = f'master-{self._masterProgressDumpIdx-1:09d}'
+    for name in os.listdir(self.progressMonitorPath()):
+      if name.startswith('master-') and name != mine and not name.endswith('.tmp'):
+        path = f'{self.progressMonitorPath()}/{name}'
+        try:
+          if time.time()-os.path.getmtime(path) > 10:
+            os.remove(path)
+        except OSError:
+          pass
 
   def performanceDescription(self):
     'results_store.py:541-556: the log line benchmark/run-benchmarks.py scrapes'

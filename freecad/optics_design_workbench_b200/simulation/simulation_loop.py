@@ -194,6 +194,7 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
     store.dumpGlobalInfo(collect_global_info(sim))
   ctx = SimulationContext(sim, engine, seed=seed, rank=rank, world=world)
   sources = [GenericSourceProxy(ctx, i) for i in range(len(sim.source_records))]
+  run_error, clean_exit = None, True
   try:
     if not continuous:
       # one iteration (simulation_loop.py:342-411: single shots and fans are not continuous)
@@ -221,24 +222,32 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
       batch_rays = min(maxBatchRays, max(per_iter, 1 << 16))
       while True:
         k = _iterations_until_end(store_global(store, world), per_iter, batch_rays)
-        ended = False
-        for src in sources:
-          try:
-            src.runSimulationIteration(mode='pseudo' if mode == 'pseudo' else 'true', store=store, iterations=k)
-          except SimulationEnded:
-            ended = True                                          # a replay source ran out of rays (replay_source.py:160-161)
-        store.incrementIterationCount(k)
-        store.writeDiskIfNeeded()
+        ended, failure = False, None
+        try:
+          for src in sources:
+            try:
+              src.runSimulationIteration(mode='pseudo' if mode == 'pseudo' else 'true', store=store, iterations=k)
+            except SimulationEnded:
+              ended = True                                        # a replay source ran out of rays (replay_source.py:160-161)
+          store.incrementIterationCount(k)
+          store.writeDiskIfNeeded()
+        except Exception as exc:                                  # reported to the other ranks below, raised after the loop
+          failure = exc
+        # ONE collective per batch carries the counters and every reason to leave the loop, so that all ranks take the same
+        # branch: a rank whose replay source ran dry, a rank that failed and a flag file seen by one rank only stop everybody
+        stop = query_status(basePath, 'simulation-is-canceled') or query_status(basePath, 'simulation-is-done')
         total = sharding.all_reduce_counters(dict(totalTracedRays=store.totalTracedRays,
-                                                   totalRecordedHits=store.progressDict()['totalRecordedHits']))
+                                                   totalRecordedHits=store.progressDict()['totalRecordedHits'],
+                                                   _stop=int(stop), _ended=int(ended), _failed=int(failure is not None)))
+        stop, ended, failed = bool(total.pop('_stop')), bool(total.pop('_ended')), bool(total.pop('_failed'))
+        if failed:
+          run_error = failure if failure is not None else RuntimeError('another rank failed during the simulation; see its log')
+          break
         total['totalIterations'] = store.totalIterations        # iterations are global (every rank takes part in each)
         total['totalRecordedRays'] = 0
         store._global = total
         if rank == 0:
           store.dumpMasterProgress(total)
-        stop = query_status(basePath, 'simulation-is-canceled') or query_status(basePath, 'simulation-is-done')
-        if world > 1:                                             # all ranks leave the loop in the same batch
-          stop = bool(sharding.all_reduce_counters(dict(stop=int(stop)))['stop'])
         if store.isEndReached(total):
           if rank == 0:
             set_status(basePath, 'simulation-is-done', True)      # results_store.py:507-512 -> setIsFinished(True)
@@ -246,9 +255,13 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
         if ended or stop:
           break
         batch_rays = min(maxBatchRays, batch_rays*4)            # grow while only EndAfterHits is pending
+  except BaseException:
+    clean_exit = False                                            # an exception outside the batch loop: do not wait for ranks that may never arrive
+    raise
   finally:
     store.flush()
-    sharding.barrier()
+    if clean_exit:
+      sharding.barrier()
     if rank == 0:
       set_status(basePath, 'simulation-is-running', False)        # simulation_loop.py:726-775
     if not keepProgressFiles:
@@ -257,6 +270,8 @@ def runSimulation(project, action, *, engine=None, basePath=None, seed=DEFAULT_S
       else:
         store._cleanedUp = True
     ctx.close()
+  if run_error is not None:
+    raise run_error
   return store.runFolderPath()
 
 

@@ -304,3 +304,33 @@ def test_pseudo_mode_thins_towards_its_expected_histogram(tmp_path, engine):
   run = simulation_loop.runSimulation(prepare(os.path.join(SCENES, 'minimal.npz')), 'pseudo', engine=engine,
                                       basePath=str(tmp_path/'p.OpticsDesign'), settings=dict(EndAfterRays=250), maxBatchRays=200)
   assert len(load_hits(run)['points']) == 300
+
+
+def test_draw_hands_the_traced_polylines_to_a_drawing_back_end(tmp_path, engine):
+  '''
+  draw=True (reference generic_source.py:102-138): one Part line per segment, in the light source's local frame, grouped into
+  RaySegment features of the source.  Here the traced polylines go to a drawing back end; the recording one stands in for
+  FreeCAD.  Fans mode (the GUI's default action) and a single Monte-Carlo iteration.
+  '''
+  from freecad.optics_design_workbench_b200.freecad_elements import ray_drawing
+  from freecad.optics_design_workbench_b200.freecad_elements.generic_source import GenericSourceProxy
+  sim = prepare(os.path.join(SCENES, 'lensesAndMirrors.npz'))
+  ctx = simulation_loop.SimulationContext(sim, engine, seed=3)
+  src = GenericSourceProxy(ctx, 0)
+  backend = ray_drawing.RecordingBackend()
+  counts = src.runSimulationIteration(mode='fans', draw=True, drawBackend=backend)
+  assert backend.cleared == 1 and len(backend.rays) == 40 == counts['rays']
+  assert sum(len(r) for r in backend.rays) == counts['segments']
+  full = [r for r in backend.rays if len(r) == 7][0]
+  np.testing.assert_allclose(full[0][0], 0.0, atol=1e-12)                  # starts at the source
+  np.testing.assert_allclose(full[1:, 0], full[:-1, 1])                   # segments chain: end of one = start of the next
+  assert abs(full[-1][1][2]-73.0) < 1e-6                                  # ends on the absorber (the source frame is the world frame here)
+  counts = src.runSimulationIteration(mode='true', draw=True, drawBackend=backend)
+  assert backend.cleared == 2 and len(backend.rays) == 100 == counts['rays']
+  # a source with a placement: lines are drawn in its LOCAL frame (gpMi * p)
+  sim.source_records[0]['gpM'] = np.array([[1, 0, 0, 5.0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)
+  ctx2 = simulation_loop.SimulationContext(sim, engine, seed=3)
+  GenericSourceProxy(ctx2, 0).runSimulationIteration(mode='fans', draw=True, drawBackend=backend)
+  np.testing.assert_allclose(backend.rays[0][0][0], 0.0, atol=1e-12)      # the ray starts at the source's own origin
+  with pytest.raises(RuntimeError, match='FreeCAD is not importable'):
+    src.runSimulationIteration(mode='fans', draw=True)
