@@ -84,6 +84,20 @@ def load_library():
   return L
 
 
+def device_count():
+  'number of CUDA devices the library can open (0 without a driver / device)'
+  L = load_library()
+  n = 0
+  while n < 64:
+    h = C.c_void_p()
+    rc = L.odw_engine_create(n, C.byref(h))
+    if rc != 0:
+      break
+    L.odw_engine_destroy(h)
+    n += 1
+  return n
+
+
 def _check(rc, allow=()):
   if rc != 0 and rc not in allow:
     raise EngineError(rc, load_library().odw_last_error().decode(errors='replace'))

@@ -74,7 +74,8 @@ def test_kernel_instance_selection():
   '''
   Which instance of the trace kernel a launch gets (csrc/odw_kernels.cu pick_feat; FEAT_* bits: 1 gratings / scatter / absorption /
   aspheres, 2 surface source, 4 sequential mode, 8 device binning): the lean one only when nothing is needed, the sequential
-  one for sequential mode alone, the full one otherwise and for explicit ray lists and BVH scenes.  Host logic, no GPU call.
+  one for sequential mode alone, the one without FEAT_EXT for surface sources / device binning in scenes of ideal surfaces,
+  the full one otherwise and for explicit ray lists and BVH scenes.  Host logic, no GPU call.
   '''
   import ctypes as C
   from freecad.optics_design_workbench_b200 import engine
@@ -83,7 +84,9 @@ def test_kernel_instance_selection():
   L.odw_trace_instance.argtypes = [C.c_bool, C.c_bool, C.c_int]
   assert L.odw_trace_instance(True, False, 0) == 0
   assert L.odw_trace_instance(True, False, 4) == 4
-  for need in (1, 2, 8, 5, 6, 12, 15):
+  for need in (2, 8, 6, 12, 14):
+    assert L.odw_trace_instance(True, False, need) == 14, need    # surface source / binning without gratings, scatter, ...: everything but FEAT_EXT
+  for need in (1, 5, 3, 9, 15):
     assert L.odw_trace_instance(True, False, need) == 15, need
   for need in (0, 4, 15):
     assert L.odw_trace_instance(False, False, need) == 15       # explicit ray lists
