@@ -1016,7 +1016,8 @@ static int launch_features(const odw_scene* sc, const TraceParams& p, bool mc) {
 
 static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams& p, bool mc, uint64_t* launches) {
   const int need = launch_features(sc, p, mc);
-  int per_sm = odw_trace_occupancy(mc, sc->use_bvh, need, sc->smem);
+  const bool presample = mc && p.src.kind == ODW_SRC_SURFACE && !sc->use_bvh && getenv("ODW_NO_PRESAMPLE") == nullptr;   // see below
+  int per_sm = odw_trace_occupancy(mc && !presample, sc->use_bvh, need, sc->smem);
   if (per_sm <= 0) { cudaError_t e = cudaGetLastError(); return fail(ODW_ECUDA, std::string("trace kernel cannot be resident: ") + cudaGetErrorString(e)); }
   // persistent grid: a multiple of the SM count, no more blocks than there is work
   const int blocks = eng->sm_count*per_sm;
@@ -1043,6 +1044,14 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     CU(cudaEventRecord(eng->ev_fork, eng->stream));
     for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
   }
+  // Surface sources: the emission code (face pick, area-uniform point, trim test, direction) is as large as the bounce loop, and a
+  // warp of the register-resident kernel runs it whenever one of its rays ends — with rays of two or three segments the
+  // kernel's instruction working set no longer fits the instruction cache (profiles/r02_v3_lines_lambertSource.txt: 58 % of the
+  // stall samples are "no instruction").  The rays of a wave are therefore drawn by the sampling kernel first (all lanes in the
+  // same code) and traced as an explicit list; 48 B per ray through HBM is nothing against that.
+  double* sample_buf[odw_engine::MAX_WAVE_STREAMS] = {};
+  if (presample)
+    for (int i = 0; i < n_streams; ++i) { int rc = eng->alloc((void**)&sample_buf[i], (size_t)std::min<uint64_t>(wave, p.n_rays)*48); if (rc) return rc; }
   uint64_t wave_index = 0;
   for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
@@ -1065,9 +1074,20 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     const uint64_t tpb = (uint64_t)odw_trace_threads();
     uint64_t want_w = (q.n_rays + tpb - 1)/tpb;
     int blocks_w = (int)std::min<uint64_t>((uint64_t)blocks, std::max<uint64_t>(1, want_w));
-    CU(odw_launch_trace(&q, mc, sc->use_bvh, need, blocks_w, sc->smem, eng->wave_stream[wave_index % (uint64_t)n_streams]));
+    cudaStream_t wst = eng->wave_stream[wave_index % (uint64_t)n_streams];
+    if (presample) {
+      double* buf = sample_buf[wave_index % (uint64_t)n_streams];            // waves of one stream run one after the other: the buffer is free again
+      const int sblocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*8, std::max<uint64_t>(1, (q.n_rays + 255)/256));
+      CU(odw_launch_sample(&q.src, q.seed, q.first_ray, q.n_rays, nullptr, nullptr, buf, buf + 3*q.n_rays, sblocks, wst));
+      q.in_origins = buf; q.in_dirs = buf + 3*q.n_rays;
+      CU(odw_launch_trace(&q, false, false, need, blocks_w, sc->smem, wst));
+      if (launches) *launches += 2;
+      continue;
+    }
+    CU(odw_launch_trace(&q, mc, sc->use_bvh, need, blocks_w, sc->smem, wst));
     if (launches) ++*launches;
   }
+  for (int i = 0; i < odw_engine::MAX_WAVE_STREAMS; ++i) eng->release(sample_buf[i]);   // stream order protects them: every later user is queued after the join below
   for (int i = 1; i < n_streams; ++i) { CU(cudaEventRecord(eng->ev_join[i], eng->wave_stream[i])); CU(cudaStreamWaitEvent(eng->stream, eng->ev_join[i], 0)); }
   return ODW_OK;
 }

@@ -202,7 +202,8 @@ def test_gpu_surface_source_trace_equals_oracle(gpu_engine, oracle, sims):
   with gpu_engine.scene(sim.scene).trace_mc(gpu_engine.source(sa), cfg, SEED, 0, n) as res:
     gc, gh = res.counts, res.hits(sort=True)
   o = oracle.trace_mc(sim.scene, sa, cfg, SEED, 0, n, hit_capacity=8*n, threads=0)
-  assert gc == o['counts']
+  drop = lambda c: {k: v for k, v in c.items() if k != 'waves'}      # kernel launches: not a property of the result
+  assert drop(gc) == drop(o['counts'])
   oh = o['hits']
   assert np.array_equal(gh['ray_index'], oh['ray_index']) and np.array_equal(gh['face_id'], oh['face_id'])
   np.testing.assert_allclose(gh['points'], oh['points'], rtol=0, atol=1e-9)
