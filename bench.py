@@ -339,8 +339,8 @@ def plugin_leg(sim, eng, args, rank, world, barrier, steps):
     t0 = time.perf_counter()
     segs, written = 0, 0
     for k in range(steps):
+      n_before = len(store.writtenFiles)               # large batches are written by runSimulationIteration itself (direct writer)
       c = src.runSimulationIteration(mode='true', store=store, iterations=iterations)
-      n_before = len(store.writtenFiles)
       store.flush()
       segs += c['segments']
       for f in store.writtenFiles[n_before:]:
