@@ -2,10 +2,13 @@
 CPU oracle loader — TEST INFRASTRUCTURE ONLY (see oracle/odw_oracle.c).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
-package.  The product package never does.  Pinned against the reference's own code: the bounce loop, the interaction
-formulas and _makeRay (tests/golden/make_traceray_golden.py), the sampler and the fan grid (tests/golden/).
-"parity unpinned" for the geometry answers the reference obtains from FreeCAD / OpenCASCADE (absent here; the
-reference holds no golden ray vectors) — see the header of odw_oracle.c.
+package.  The product package never does.  Pinned against the reference's own Python, executed unmodified under stand-ins
+for FreeCAD's Base types and the OpenCASCADE primitives it calls: the whole per-ray path — traceRay,
+findNearestIntersection, getNormal, the interaction formulas, find.relevantOpticalObjects, _makeRay
+(tests/golden/make_traceray_golden.py) — the sampler and the fan grids (tests/golden/), and the Monte-Carlo chi-square
+gate (tests/golden/make_mc_gate_golden.py).  "parity unpinned" only for OpenCASCADE's primitive answers on real BRep
+shapes (FreeCAD is absent here and on the GPU box; the reference holds no golden ray vectors) — see the header of
+odw_oracle.c.
 '''
 
 import ctypes as C
