@@ -146,6 +146,23 @@ def revolved_parabola_dish(focal, aperture_radius):
   return [_face(surf, [_rect_loop(0, TWO_PI, 0.0, aperture_radius)], shell_key=None)]
 
 
+def revolved_spline_dish(sag, aperture_radius, n_points=41, reversed_=False):
+  '''
+  An aspheric surface the way FreeCAD users model it: a cubic B-spline through n_points points (rho, sag(rho)) of the lens
+  formula in the x-z plane, revolved about the z axis (BRep surface type 7 with a B-spline generatrix), trimmed to the whole
+  curve.  Exercises the revolution -> even-asphere fit of scene.face_record.
+  '''
+  import scipy.interpolate
+  from .brep import Curve3d, BSplineCurve
+  rho = np.linspace(0.0, aperture_radius, n_points)
+  pts = np.column_stack([rho, np.zeros_like(rho), sag(rho)])
+  sp = scipy.interpolate.make_interp_spline(rho, pts, k=3)           # parameter = rho at the data points (not in general in between)
+  knots, mults = np.unique(sp.t, return_counts=True)
+  curve = Curve3d('bspline', spline=BSplineCurve(3, sp.c, None, knots, mults, False))
+  surf = Surface('revolution', p=np.zeros(3), d=_Z.copy(), curve=curve)
+  return [_face(surf, [_rect_loop(0, TWO_PI, float(knots[0]), float(knots[-1]))], reversed_=reversed_, shell_key=None)]
+
+
 # ------------------------------------------------------------------------------------------
 # rigid transforms
 

@@ -208,6 +208,107 @@ def _revolved_conic(surf):
   return Surface('conicoid', p=np.asarray(curve.p, dtype=float), n=Z, dx=X, dy=Y, c=1.0/(2.0*curve.f), k=-1.0)
 
 
+ASPHERE_FIT_TOLERANCE = 1e-7      # mm: largest sag residual for which a revolved free-form meridian is taken as an even asphere
+
+
+def _revolved_asphere(surf, tolerance=None):
+  '''
+  A surface of revolution whose meridian is a free-form curve (B-spline / Bezier — how FreeCAD users model an aspheric lens:
+  a spline through points of the lens formula, revolved about the optical axis) fitted to the even-asphere form
+    z = z0 + c rho^2 / (1 + sqrt(1 - (1+k) c^2 rho^2)) + a4 rho^4 + ... + a12 rho^12        (include/odw.h ODW_SEG_ASPHERE)
+  Returns a 'conicoid' Surface with .poly and .vmap (curve parameter t -> rho, for the trim curves), or None when the
+  meridian is not of that kind or the fit leaves a sag residual above `tolerance` (then the face is meshed as before, with
+  the tessellation's deflection as its error).  The residual is reported in .fit_residual.
+  '''
+  from .brep import Surface
+  import scipy.optimize
+  tolerance = ASPHERE_FIT_TOLERANCE if tolerance is None else tolerance
+  curve, t0, t1 = surf.curve, None, None
+  while curve.kind == 'trimmed':
+    t0 = curve.u1 if t0 is None else t0
+    t1 = curve.u2 if t1 is None else t1
+    curve = curve.basis
+  if curve.kind not in ('bspline', 'bezier'):
+    return None
+  spline = curve.spline
+  if t0 is None:
+    t0, t1 = float(spline.knots[0]), float(spline.knots[-1])
+  axis = np.asarray(surf.d, dtype=float)
+  axis = axis/np.linalg.norm(axis)
+  A = np.asarray(surf.p, dtype=float)
+  t = np.linspace(t0, t1, 801)
+  w = curve.eval(t)-A
+  z = w @ axis
+  radial = w-z[:, None]*axis
+  rho = np.linalg.norm(radial, axis=1)
+  far = int(np.argmax(rho))
+  if rho[far] < 1e-9:
+    return None
+  X = radial[far]/rho[far]
+  if np.abs(radial-rho[:, None]*X).max() > 1e-9*max(1.0, rho[far]):
+    return None                                           # the meridian leaves the half plane through the axis (or crosses the axis)
+  if np.any(np.diff(rho) <= 0) and np.any(np.diff(rho) >= 0):
+    return None                                           # rho must be monotonic along the curve: one sag value per radius
+  order = np.argsort(rho)
+  r, zz = rho[order], z[order]
+
+  def sag(params, r):
+    z0, c, k = params[:3]
+    u = r*r
+    root = np.sqrt(np.maximum(1e-300, 1-(1+k)*c*c*u))
+    a = params[3:]
+    return z0 + c*u/(1+root) + u*u*(a[0] + u*(a[1] + u*(a[2] + u*(a[3] + u*a[4]))))
+
+  # start: vertex height by extrapolation, vertex curvature from the innermost part of the meridian
+  inner = r <= max(r[0] + 0.2*(r[-1]-r[0]), r[min(len(r)-1, 8)])
+  quad = np.polyfit(r[inner]**2, zz[inner], 1)
+  start = np.array([quad[1], 2*quad[0] if quad[0] != 0 else 1e-6, 0.0, 0, 0, 0, 0, 0], dtype=float)
+  scale = np.array([1.0, 1.0, 1.0] + [r[-1]**-(2*j+4) for j in range(5)])       # polynomial terms of order one at the rim
+  best = None
+  for n_poly in (0, 2, 5):                                # plain conic first, then with rho^4, rho^6, then all five terms
+    def residual(q, n_poly=n_poly):
+      params = np.concatenate([q[:3], q[3:3+n_poly]*scale[3:3+n_poly], np.zeros(5-n_poly)])
+      if (1+params[2])*params[1]**2*r[-1]**2 >= 1:
+        return np.full_like(r, 1e3)
+      return sag(params, r)-zz
+    q0 = np.concatenate([start[:3], np.zeros(n_poly)]) if best is None else np.concatenate([best[0][:3], (best[0][3:]/scale[3:])[:n_poly]])
+    sol = scipy.optimize.least_squares(residual, q0, xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=2000)
+    params = np.concatenate([sol.x[:3], sol.x[3:3+n_poly]*scale[3:3+n_poly], np.zeros(5-n_poly)])
+    err = float(np.abs(sag(params, r)-zz).max())
+    if best is None or err < best[1]:
+      best = (params, err)
+    if err <= tolerance:
+      break
+  params, err = best
+  if not (err <= tolerance) or not np.isfinite(params).all() or params[1] == 0:
+    return None
+  z0, c, k = params[:3]
+  Y = np.cross(axis, X)                                   # OCC: rotation by u about the axis takes the meridian plane from X towards Y
+  out = Surface('conicoid', p=A+z0*axis, n=axis, dx=X, dy=Y, c=float(c), k=float(k),
+                poly=[float(a) for a in params[3:]] if np.any(params[3:] != 0) else None)
+  out.fit_residual = err
+  tt, rr = t, rho
+  if rr[0] > rr[-1]:
+    tt, rr = tt[::-1], rr[::-1]
+  out.vmap = lambda v: float(np.linalg.norm((lambda q: q-(q @ axis)*axis)(curve.eval(np.array([v]))[0]-A)))
+  return out
+
+
+def _map_v(segs, vmap):
+  'trim pieces given in (u, t) of a revolved curve -> (u, rho): pointwise on straight pieces (split where both coordinates change)'
+  out = []
+  for kind, a in segs:
+    if kind != SEG_LINE:
+      raise UnsupportedGeometry('curved trim piece on a fitted surface of revolution')
+    u0, v0, u1, v1 = a[:4]
+    n = 1 if (abs(u1-u0) < 1e-12 or abs(v1-v0) < 1e-12) else 32
+    for j in range(n):
+      ua, ub = u0+(u1-u0)*j/n, u0+(u1-u0)*(j+1)/n
+      va, vb = v0+(v1-v0)*j/n, v0+(v1-v0)*(j+1)/n
+      out.append((SEG_LINE, [ua, vmap(va), ub, vmap(vb), 0.0]))
+  return out
+
+
 def face_record(fi, transform, group, shell, face_id, segs_out):
   '''
   Convert a brep.FaceInstance (+ an extra world transform applied on the left) into a FACE_DTYPE
@@ -215,7 +316,7 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
   '''
   surf = fi.surface
   if surf.kind == 'revolution':
-    surf = _revolved_conic(surf) or surf
+    surf = _revolved_conic(surf) or _revolved_asphere(surf) or surf
   if surf.kind not in _KIND_ID:
     raise UnsupportedGeometry(f'surface kind {surf.kind!r} has no closed form')
   R, T = _rigid(transform @ fi.transform)
@@ -247,6 +348,8 @@ def face_record(fi, transform, group, shell, face_id, segs_out):
   for loop in fi.loops:
     for curve, first, last in loop:
       _curve_to_segs(curve, first, last, out=segs)
+  if getattr(surf, 'vmap', None) is not None:
+    segs = _map_v(segs, surf.vmap)                        # the face's v is the parameter of the revolved curve, the conicoid's is rho
   if not segs:
     if surf.kind in ('sphere', 'torus'):
       lo, hi = np.array([0.0, -np.pi/2 if surf.kind == 'sphere' else 0.0]), \

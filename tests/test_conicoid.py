@@ -301,3 +301,64 @@ def test_gpu_conicoid_parity_with_oracle(gpu_engine, oracle):
   assert np.abs(gh['directions']-oh['directions']).max() < 1e-9
   assert np.abs(gh['powers']-oh['powers']).max() < 1e-14
   assert {int(scene.faces[f]['kind']) for f in np.unique(gh['face_id'])} >= {1, 6}
+
+
+# ---- aspheres the way FreeCAD users model them: a spline through points of the lens formula, revolved ----------------
+ASPHERE = dict(c=1/25.0, k=-0.8, poly=[2e-5, -3e-8])
+
+
+def spline_dish(n_points=81, **kw):
+  sag = lambda r: sc_mod.conic_sag(ASPHERE['c'], ASPHERE['k'], r, ASPHERE['poly'])
+  return prim.revolved_spline_dish(sag, 8.0, n_points=n_points, **kw)
+
+
+def test_revolved_spline_meridian_is_fitted_to_the_even_asphere_form(oracle):
+  '''
+  A surface of revolution with a B-spline generatrix (BRep surface type 7) becomes a closed-form conicoid + even-asphere
+  terms when the fit reproduces the meridian within ASPHERE_FIT_TOLERANCE (1e-7 mm); the stated residual is the error
+  bound of the face.  Rays reflected by it land where the exact asphere sends them, within that bound's effect.
+  '''
+  faces = spline_dish()
+  fitted = sc_mod._revolved_asphere(faces[0].surface)
+  assert fitted is not None and fitted.fit_residual < 1e-8              # the cubic spline through 81 points is that close to the formula
+  assert abs(fitted.c-ASPHERE['c']) < 1e-8 and abs(fitted.k-ASPHERE['k']) < 1e-3
+  scene = dish_and_screen(faces, screen_z=12.0, screen_r=50.0)
+  f = scene.faces[0]
+  assert int(f['kind']) == sc_mod.SURF_CONICOID and int(f['trim_kind']) == sc_mod.TRIM_UVBOX
+  assert abs(f['uv_max'][1]-8.0) < 1e-9 and f['uv_min'][1] == 0.0      # the trim is in rho now, not in the curve parameter
+  assert int(scene.segs[int(f['seg_first'])]['kind']) == sc_mod.SEG_ASPHERE
+  exact = dish_and_screen(prim.conic_dish(ASPHERE['c'], ASPHERE['k'], 8.0, poly=ASPHERE['poly']), screen_z=12.0, screen_r=50.0)
+  o, d = grid_rays(8.0)
+  a, b = trace(oracle, scene, o, d), trace(oracle, exact, o, d)
+  assert np.array_equal(a['n_segments'], b['n_segments']) and np.array_equal(a['hits']['group'], b['hits']['group'])
+  assert np.abs(a['hits']['points']-b['hits']['points']).max() < 1e-6   # residual 1e-9 mm in sag -> ~1e-8 in slope -> < 1e-6 mm on the screen
+  assert np.abs(a['hits']['directions']-b['hits']['directions']).max() < 1e-7
+
+
+def test_a_meridian_that_is_no_asphere_is_not_fitted():
+  'a wavy meridian leaves a residual above the tolerance: no closed form, the face goes to the tessellation as before'
+  wavy = prim.revolved_spline_dish(lambda r: 0.02*r*r + 0.01*np.sin(3*r), 8.0, n_points=81)
+  assert sc_mod._revolved_asphere(wavy[0].surface) is None
+  b = SceneBuilder()
+  g = b.add_group('M', 'M', optical_type='Mirror')
+  b.add_shape(g, wavy, np.eye(4))
+  scene = b.build()
+  assert len(scene.faces) > 100 and (scene.faces['kind'] == sc_mod.SURF_PLANE).all()      # meshed: planar triangles
+  coarse = spline_dish(n_points=6)                                       # a spline through 6 points is 1e-4 mm off the formula ...
+  fitted = sc_mod._revolved_asphere(coarse[0].surface)
+  assert fitted is None or fitted.fit_residual <= sc_mod.ASPHERE_FIT_TOLERANCE   # ... and is only accepted if the fit really reproduces IT
+
+
+@pytest.mark.gpu
+def test_gpu_fitted_asphere_parity_with_oracle(gpu_engine, oracle):
+  scene = dish_and_screen(spline_dish(), screen_z=12.0, screen_r=50.0)
+  o, d = grid_rays(8.0, n=25)
+  cfg = _abi.CfgArgs(max_ray_length=1000.0, dist_tol=1e-6, max_intersections=20, record_all_hits=True)
+  want = oracle.trace_rays(scene, cfg, o, d)
+  ds = gpu_engine.scene(scene)
+  with ds.trace_rays(cfg, o, d) as res:
+    got = res.hits(sort=True)
+  ds.close()
+  assert np.array_equal(got['face_id'], want['hits']['face_id']) and np.array_equal(got['ray_index'], want['hits']['ray_index'])
+  assert np.abs(got['points']-want['hits']['points']).max() < 1e-8
+  assert np.abs(got['directions']-want['hits']['directions']).max() < 1e-9
