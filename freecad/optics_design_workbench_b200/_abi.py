@@ -23,7 +23,7 @@ class SceneDesc(C.Structure):
 
 
 class Scatter(C.Structure):
-  _fields_ = [('n_first', C.c_int32), ('n_phi', C.c_int32), ('n_rows', C.c_int32), ('pad', C.c_int32),
+  _fields_ = [('n_first', C.c_int32), ('n_phi', C.c_int32), ('n_rows', C.c_int32), ('n_tables', C.c_int32),
               ('first_lo', C.c_double), ('first_hi', C.c_double), ('phi_lo', C.c_double), ('phi_hi', C.c_double),
               ('phi_cdf', C.c_void_p), ('first_cdf', C.c_void_p)]
 
@@ -86,7 +86,8 @@ class SceneArgs:
     if tables:
       self.scatters = (Scatter*len(tables))()
       for sct, t in zip(self.scatters, tables):
-        sct.n_first, sct.n_phi, sct.n_rows = t.first_cdf.shape[1], t.phi_cdf.shape[0], t.first_cdf.shape[0]
+        sct.n_first, sct.n_phi, sct.n_rows = t.first_cdf.shape[-1], t.phi_cdf.shape[-1], t.first_cdf.shape[-2]
+        sct.n_tables = int(getattr(t, 'n_tables', 1))
         sct.first_lo, sct.first_hi = t.first_domain
         sct.phi_lo, sct.phi_hi = t.phi_domain
         sct.phi_cdf, sct.first_cdf = _ptr(t.phi_cdf), _ptr(t.first_cdf)

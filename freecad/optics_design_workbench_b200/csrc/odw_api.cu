@@ -599,6 +599,14 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     const odw_scatter& t = sd->scatters[i];
     if (t.n_first < 2 || t.n_phi < 2 || !t.phi_cdf || !t.first_cdf || (t.n_rows != 1 && t.n_rows != t.n_phi - 1))
       return fail(ODW_EINVAL, "scatter " + std::to_string(i) + ": malformed tables");
+    if (t.n_tables > 1 && t.n_rows != 1) return fail(ODW_EUNSUPPORTED, "scatter " + std::to_string(i) + ": a per-hit family of tables needs n_rows == 1");
+  }
+  for (int i = 0; i < sd->n_groups && sd->n_scatters > 0 && sd->group_scatter; ++i) {
+    const int m = sd->group_scatter[2*i], mod = sd->group_scatter[2*i+1];
+    if (m >= 0 && m < sd->n_scatters && sd->scatters[m].n_tables > 1 && sd->groups[i].optical_type == ODW_OPT_LENS && (sd->scatters[m].n_tables & 1))
+      return fail(ODW_EINVAL, "group " + std::to_string(i) + ": the per-hit family of a Lens group holds two families (entering, leaving): n_tables must be even");
+    if (mod >= 0 && mod < sd->n_scatters && sd->scatters[mod].n_tables > 1)
+      return fail(ODW_EINVAL, "group " + std::to_string(i) + ": the ray-modification density is never re-compiled per hit (optical_group.py:318): one table");
   }
   odw_scene* sc = new odw_scene();
   sc->eng = eng; sc->n_groups = sd->n_groups; sc->extent = extent;
@@ -615,14 +623,16 @@ extern "C" int odw_scene_create(odw_engine* eng, const odw_scene_desc* sd, odw_s
     std::vector<DScatter> scat((size_t)sd->n_scatters);
     for (int i = 0; i < sd->n_scatters; ++i) {
       const odw_scatter& t = sd->scatters[i]; DScatter& d = scat[(size_t)i];
-      if ((rc = upload(eng, sc->owned, t.phi_cdf, (size_t)t.n_phi, &d.phi_cdf))) { odw_scene_destroy(sc); return rc; }
-      if ((rc = upload(eng, sc->owned, t.first_cdf, (size_t)t.n_rows*t.n_first, &d.first_cdf))) { odw_scene_destroy(sc); return rc; }
-      std::vector<uint32_t> pg = build_guide(t.phi_cdf, t.n_phi), fg;
-      for (int r = 0; r < t.n_rows; ++r) { std::vector<uint32_t> g = build_guide(t.first_cdf + (size_t)r*t.n_first, t.n_first); fg.insert(fg.end(), g.begin(), g.end()); }
+      const size_t nt = (size_t)std::max(1, t.n_tables);                          // members of a per-hit family, one after the other
+      if ((rc = upload(eng, sc->owned, t.phi_cdf, nt*(size_t)t.n_phi, &d.phi_cdf))) { odw_scene_destroy(sc); return rc; }
+      if ((rc = upload(eng, sc->owned, t.first_cdf, nt*(size_t)t.n_rows*t.n_first, &d.first_cdf))) { odw_scene_destroy(sc); return rc; }
+      std::vector<uint32_t> pg, fg;
+      for (size_t m = 0; m < nt; ++m) { std::vector<uint32_t> g = build_guide(t.phi_cdf + m*(size_t)t.n_phi, t.n_phi); pg.insert(pg.end(), g.begin(), g.end()); }
+      for (size_t r = 0; r < nt*(size_t)t.n_rows; ++r) { std::vector<uint32_t> g = build_guide(t.first_cdf + r*(size_t)t.n_first, t.n_first); fg.insert(fg.end(), g.begin(), g.end()); }
       if ((rc = upload(eng, sc->owned, pg.data(), pg.size(), &d.phi_guide))) { odw_scene_destroy(sc); return rc; }
       if ((rc = upload(eng, sc->owned, fg.data(), fg.size(), &d.first_guide))) { odw_scene_destroy(sc); return rc; }
       d.first_lo = t.first_lo; d.first_hi = t.first_hi; d.phi_lo = t.phi_lo; d.phi_hi = t.phi_hi;
-      d.n_first = t.n_first; d.n_phi = t.n_phi; d.n_rows = t.n_rows; d.pad = 0;
+      d.n_first = t.n_first; d.n_phi = t.n_phi; d.n_rows = t.n_rows; d.n_tables = std::max(1, t.n_tables);
     }
     if ((rc = upload(eng, sc->owned, scat.data(), scat.size(), &sc->d.scatters))) { odw_scene_destroy(sc); return rc; }
   }

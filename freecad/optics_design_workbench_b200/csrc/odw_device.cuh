@@ -56,7 +56,7 @@ struct DScatter {
   const uint32_t* phi_guide;
   const uint32_t* first_guide;
   double first_lo, first_hi, phi_lo, phi_hi;
-  int32_t n_first, n_phi, n_rows, pad;
+  int32_t n_first, n_phi, n_rows, n_tables;      // n_tables > 1: family over the incidence angle of the hit (odw.h odw_scatter)
 };
 
 struct DBinning {

@@ -446,15 +446,26 @@ __device__ __forceinline__ void finish_ray(const TraceParams& p, unsigned long l
 
 // applyStochasticRayCorrections (optical_group.py:279-323) of a Mirror / Lens hit: `o` holds the ideal outgoing direction
 // on entry.  Out of line: surfaces are ideal in every benchmark scene, the bounce loop should not carry this code.
+// family: 0 = Mirror hit or entering Lens hit, 1 = leaving Lens hit, -1 = Mirror group (one family); see odw.h odw_scatter.n_tables
 __device__ __noinline__ Vec3 apply_scatter(const DScatter* scatters, int main_i, int mod_i, unsigned long long seed, uint32_t source_id,
-                                           unsigned long long ray, int bounce, double dx, double dy, double dz,
+                                           unsigned long long ray, int bounce, int family, double dx, double dy, double dz,
                                            double nx, double ny, double nz, double ox, double oy, double oz) {
   const double d_in[3] = { dx, dy, dz }, nrm[3] = { nx, ny, nz };
   double o[3] = { ox, oy, oz };
   if (main_i >= 0) {
     double u0, u1, th, ph;
     philox_uniform2(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce, u0, u1);
-    sample_source(scatters[main_i], u0, u1, th, ph);
+    DScatter t = scatters[main_i];
+    if (t.n_tables > 1) {
+      // per-hit density: the member of the family nearest to theta_in = angle(direction, normal) (optical_group.py:288)
+      const int K = family < 0 ? t.n_tables : t.n_tables/2;
+      const double c = fmin(1.0, fmax(-1.0, dot3(d_in, nrm)/sqrt(dot3(d_in, d_in)*dot3(nrm, nrm))));
+      const int k = min(K - 1, max(0, (int)(acos(c)/(ODW_TWO_PI/4)*(double)(K - 1) + 0.5)));
+      const size_t m = (size_t)((family > 0 ? K : 0) + k);
+      t.phi_cdf += m*(size_t)t.n_phi; t.first_cdf += m*(size_t)t.n_rows*(size_t)t.n_first;
+      t.phi_guide += m*(size_t)(ODW_GUIDE + 1); t.first_guide += m*(size_t)t.n_rows*(size_t)(ODW_GUIDE + 1);
+    }
+    sample_source(t, u0, u1, th, ph);
     scatter_direction(nrm, d_in, th, ph, o);
   }
   if (mod_i >= 0) {
@@ -504,7 +515,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
       mirror_dir(dn, nrm, o);                                                    // d - 2(d.n)n is linear in d: the length carries over
       if ((FEAT & FEAT_EXT) && p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {   // ray.py:151-155 (uniform test first: no scene table, no loads)
         const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
-                                     r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
+                                     r.n_isect-1, -1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
         o[0] = q.x; o[1] = q.y; o[2] = q.z; oscale = 1.0;
       }
       r.power *= g.reflectivity; ++r.seq_index;
@@ -523,7 +534,7 @@ __device__ __forceinline__ bool interact(const TraceParams& p, const DFace* face
       oscale = 1.0;                                                              // snellsLaw works on the unit direction
       if ((FEAT & FEAT_EXT) && p.scene.scatters && (g.scat_main >= 0 || g.scat_modify >= 0)) {   // ray.py:197-201
         const Vec3 q = apply_scatter(p.scene.scatters, g.scat_main, g.scat_modify, p.seed, (uint32_t)p.src.source_id, p.first_ray + i,
-                                     r.n_isect-1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
+                                     r.n_isect-1, entering ? 0 : 1, dn[0], dn[1], dn[2], nrm[0], nrm[1], nrm[2], o[0], o[1], o[2]);
         o[0] = q.x; o[1] = q.y; o[2] = q.z;
       }
       if (!entering && !tir && r.medium == fgroup) { r.medium = -1; ++r.seq_index; }

@@ -81,14 +81,29 @@ class SamplerTables:
   '''
   def __init__(self, phi_cdf, first_cdf, first_domain, phi_domain, first_var):
     self.phi_cdf = np.ascontiguousarray(phi_cdf, dtype=np.float64)
-    self.first_cdf = np.ascontiguousarray(np.atleast_2d(first_cdf), dtype=np.float64)
+    first_cdf = np.asarray(first_cdf, dtype=np.float64)
+    self.first_cdf = np.ascontiguousarray(np.atleast_2d(first_cdf) if first_cdf.ndim < 3 else first_cdf)
     self.first_domain = (float(first_domain[0]), float(first_domain[1]))
     self.phi_domain = (float(phi_domain[0]), float(phi_domain[1]))
     self.first_var = first_var
 
   @property
+  def n_tables(self):
+    '''
+    > 1: a FAMILY of tables over the incidence angle of a hit (scatter_tables with a density that depends on theta_in /
+    theta_refl): phi_cdf [n_tables, n_phi], first_cdf [n_tables, n_rows, n_first]; see include/odw.h odw_scatter
+    '''
+    return self.first_cdf.shape[0] if self.first_cdf.ndim == 3 else 1
+
+  @property
   def n_rows(self):
-    return self.first_cdf.shape[0]
+    return self.first_cdf.shape[-2]
+
+  def table(self, k):
+    'member k of a family as a plain SamplerTables'
+    if self.n_tables == 1:
+      return self
+    return SamplerTables(self.phi_cdf[k], self.first_cdf[k], self.first_domain, self.phi_domain, self.first_var)
 
   # numpy restatement of the draw (random_number_generator.py:413-456,492-500); used by tests
   def draw_from_uniforms(self, u_phi, u_first):
@@ -224,7 +239,24 @@ def surface_source_tables(rec):
   return build_tables(expr, var, dom, (0.0, 2*np.pi), float(rec.get('ThetaResolutionNumericMode', '1e5')), 3)
 
 
-def scatter_tables(density, theta_domain, phi_domain, resolution=None):
+SCATTER_PARAM_TABLES = 91        # members of a per-hit family: incidence angles linspace(0, pi/2, 91), one per degree
+
+
+def specular_angle(theta_in, optical_type, entering, refractive_index):
+  '''
+  theta_refl of applyStochasticRayCorrections (optical_group.py:292): angle between the IDEAL outgoing direction and the
+  face normal flipped along the propagation, as a function of the incidence angle.  Mirror: pi - theta_in.  Lens: the
+  refraction angle (vacuum outside; n1 -> n2 = 1 -> n entering, n -> 1 leaving), pi - theta_in beyond the critical angle.
+  '''
+  if optical_type == 'Mirror':
+    return np.pi-theta_in
+  mu = 1.0/refractive_index if entering else refractive_index
+  s = mu*np.sin(theta_in)
+  return float(np.arcsin(s)) if s < 1 else np.pi-theta_in
+
+
+def scatter_tables(density, theta_domain, phi_domain, resolution=None, optical_type='Mirror', refractive_index=1.0,
+                   param_tables=None):
   '''
   Stochastic surface model of an optical group (reference freecad_elements/optical_group.py:212-269): the density string
   in (theta, phi) as it stands (no sin(theta) factor, :219-223) -> SamplerTables, or None when the density is empty or
@@ -233,8 +265,14 @@ def scatter_tables(density, theta_domain, phi_domain, resolution=None):
 
   Handled specially: `DiracDelta(theta)` (optionally times DiracDelta(phi) or a function of phi) pins theta to 0, for
   which both rotations of applyStochasticRayCorrections are the identity (:311-320) -> None.
-  Refused: densities that depend on the incident / specular angles (theta_in, phi_in, theta_refl, phi_refl), which the
-  reference re-compiles per hit (:307) — they cannot be tabulated once — and other DiracDelta terms.
+  Densities that depend on the incident / specular angles (theta_in, phi_in, theta_refl, phi_refl): the reference
+  re-compiles them for every hit with theta_in = angle(direction, normal), theta_refl = angle(ideal outgoing direction,
+  normal), phi_in = phi_refl = 0 (:288-307).  Here they become a FAMILY of tables over theta_in on linspace(0, pi/2,
+  SCATTER_PARAM_TABLES) — theta_refl follows from theta_in (specular_angle; a Lens gets two families, entering and
+  leaving) — and a hit uses the member nearest to its incidence angle: the density is evaluated at most half a degree
+  off the hit's own angle (documented approximation; the reference evaluates it exactly).  Such densities must not depend
+  on phi (one conditional row), or the family would not fit.
+  Refused: DiracDelta terms other than DiracDelta(theta).
   '''
   if density is None or not str(density).strip():
     return None
@@ -242,7 +280,23 @@ def scatter_tables(density, theta_domain, phi_domain, resolution=None):
   names = {str(x) for x in expr.free_symbols}
   per_hit = names & {'theta_in', 'phi_in', 'theta_refl', 'phi_refl'}
   if per_hit:
-    raise NotImplementedError(f'stochastic surface density {density!r} depends on {sorted(per_hit)}: needs per-hit tables')
+    if expr.has(sy.DiracDelta):
+      raise NotImplementedError(f'stochastic surface density {density!r}: DiracDelta terms with per-hit parameters')
+    if 'phi' in names:
+      raise NotImplementedError(f'stochastic surface density {density!r} depends on {sorted(per_hit)} AND on phi: the family of '
+                                f'per-hit tables would need a conditional table per incidence angle')
+    K = int(param_tables or SCATTER_PARAM_TABLES)
+    res = 5+int(1e6**0.5) if resolution is None else resolution
+    families = [(True,)] if optical_type == 'Mirror' else [(True,), (False,)]
+    phis, firsts, one = [], [], None
+    for (entering,) in families:
+      for th_in in np.linspace(0.0, np.pi/2, K):
+        sub = {sy.Symbol('theta_in'): th_in, sy.Symbol('phi_in'): 0.0, sy.Symbol('phi_refl'): 0.0,
+               sy.Symbol('theta_refl'): specular_angle(float(th_in), optical_type, entering, float(refractive_index))}
+        one = build_tables(expr.subs(sub), 'theta', parse_domain(theta_domain, (-np.pi/2, np.pi/2)),
+                           parse_domain(phi_domain, (0, 2*np.pi)), res, 3)
+        phis.append(one.phi_cdf); firsts.append(one.first_cdf)
+    return SamplerTables(np.stack(phis), np.stack(firsts), one.first_domain, one.phi_domain, 'theta')
   if expr.has(sy.DiracDelta):
     theta = sy.Symbol('theta')
     pinned = [d for d in expr.atoms(sy.DiracDelta) if d.args[0] == theta]

@@ -514,7 +514,9 @@ class SceneBuilder:
     if int(g['optical_type']) in (OPT_MIRROR, OPT_LENS):       # applyStochasticRayCorrections is only called for these
       for k, (dens, td, pd) in enumerate(((scatter_density, power_theta_domain, power_phi_domain),
                                           (modify_density, modify_theta_domain, modify_phi_domain))):
-        t = scatter_tables(dens, td, pd, scatter_resolution)
+        # only the main density is re-compiled per hit by the reference (optical_group.py:307); the modify density is drawn as it is (:318)
+        t = (scatter_tables(dens, td, pd, scatter_resolution, optical_type=OPTICAL_TYPES[int(g['optical_type'])],
+                            refractive_index=float(g['refractive_index'])) if k == 0 else scatter_tables(dens, td, pd, scatter_resolution))
         if t is not None:
           self.scatters.append(t)
           idx[k] = len(self.scatters)-1

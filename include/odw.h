@@ -152,13 +152,18 @@ typedef struct odw_group {
 /* Tabulated (theta, phi) density of an optical group's stochastic surface model (optical_group.py:212-323:
  * ReflectedProbabilityDensity of a mirror, RefractedProbabilityDensity of a lens, RayModificationProbabilityDensity of
  * either).  Same table layout and draw as a point source sampler (phi from the marginal, theta from the row of the
- * nearest phi mid-point); NO sin(theta) factor is added (optical_group.py:219-223).  Only densities that do not depend
- * on theta_in / phi_in / theta_refl / phi_refl can be tabulated once; the host refuses the others. */
+ * nearest phi mid-point); NO sin(theta) factor is added (optical_group.py:219-223).
+ * n_tables > 1 (main density of a group only): the density depends on the incidence of the hit (theta_in, theta_refl of
+ * optical_group.py:288-307, which the reference substitutes for every hit) and is given as a FAMILY of tables over
+ * theta_in = angle(incoming direction, normal along the propagation) on linspace(0, pi/2, K): K = n_tables for a Mirror
+ * group, n_tables / 2 for a Lens group (first K tables: entering hits, then K for leaving hits; theta_refl follows from
+ * theta_in by the law of reflection / refraction).  A hit draws from the member nearest to its theta_in.  n_rows must be 1. */
 typedef struct odw_scatter {
-  int32_t n_first, n_phi, n_rows, pad;
+  int32_t n_first, n_phi, n_rows;
+  int32_t n_tables;              /* 0 or 1: one table */
   double first_lo, first_hi, phi_lo, phi_hi;
-  const double* phi_cdf;         /* [n_phi] */
-  const double* first_cdf;       /* [n_rows][n_first] */
+  const double* phi_cdf;         /* [n_tables][n_phi] */
+  const double* first_cdf;       /* [n_tables][n_rows][n_first] */
 } odw_scatter;
 
 typedef struct odw_scene_desc {

@@ -151,14 +151,30 @@ static void scatter_direction(const double* n, const double* d_in, double theta,
 }
 
 /* applyStochasticRayCorrections (optical_group.py:279-323) for a Mirror / Lens hit; dir_in unit, out = ideal direction on entry */
+/* member of a per-hit family (odw.h odw_scatter.n_tables > 1) for a hit: the table nearest to theta_in = angle(direction,
+ * normal), optical_group.py:288; Lens groups carry two families (entering, leaving) */
+static int scatter_member(const odw_scatter* t, const double* dir_in, const double* nrm, int lens, int entering) {
+  if (t->n_tables <= 1) return 0;
+  int K = lens ? t->n_tables/2 : t->n_tables;
+  double c = dot3(dir_in, nrm)/(len3(dir_in)*len3(nrm));
+  if (c > 1) c = 1; if (c < -1) c = -1;
+  double th = acos(c);
+  int k = (int)(th/(TWO_PI/4)*(double)(K - 1) + 0.5);
+  if (k < 0) k = 0; if (k > K - 1) k = K - 1;
+  return (lens && !entering ? K : 0) + k;
+}
+
 static void apply_scatter(const odw_scene_desc* sc, int group, uint64_t seed, uint32_t source_id, uint64_t ray, int bounce,
-                          const double* dir_in, const double* nrm, double* out) {
+                          const double* dir_in, const double* nrm, int entering, double* out) {
   if (!sc->n_scatters || !sc->group_scatter) return;
   int main_i = sc->group_scatter[2*group], mod_i = sc->group_scatter[2*group+1];
   if (main_i >= 0) {
     double u[2], th, ph;
     oracle_philox(seed, source_id, ray, 0x10000u + 4u*(uint32_t)bounce, u);
-    scatter_sample(&sc->scatters[main_i], u[0], u[1], &th, &ph);
+    odw_scatter t = sc->scatters[main_i];
+    int m = scatter_member(&t, dir_in, nrm, sc->groups[group].optical_type == ODW_OPT_LENS, entering);
+    t.phi_cdf += (size_t)m*(size_t)t.n_phi; t.first_cdf += (size_t)m*(size_t)t.n_rows*(size_t)t.n_first;
+    scatter_sample(&t, u[0], u[1], &th, &ph);
     scatter_direction(nrm, dir_in, th, ph, out);
   }
   if (mod_i >= 0) {
@@ -1004,7 +1020,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
     switch (g->optical_type) {
       case ODW_OPT_MIRROR: {                                                /* :146-161 */
         double o[3]; mirror(dir, nrm, o);
-        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, o);   /* :151-155 */
+        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, entering, o);   /* :151-155 */
         memcpy(dir, o, sizeof o);
         power *= g->reflectivity;
         seq_index++;
@@ -1032,7 +1048,7 @@ static void trace_one(const odw_scene_desc* sc, const odw_trace_cfg* cfg, const 
           }
         }
         int tir = snell(dnrm, n1, n2, nrm, o);
-        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, o);   /* :197-201 */
+        apply_scatter(sc, f->group, seed, source_id, ray_index, n_isect-1, dnrm, nrm, entering, o);   /* :197-201 */
         memcpy(dir, o, sizeof o);
         if (!entering && !tir && medium == f->group) { medium = -1; seq_index++; }
         break;

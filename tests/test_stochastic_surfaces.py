@@ -38,9 +38,14 @@ def test_density_classification():
   t = scatter_tables('cos(theta)**2 * abs(sin(theta))', '-pi, -pi/2', '-pi,pi')
   assert t.n_rows == 1 and t.first_cdf.shape[1] == 1005 and t.first_domain == (-np.pi, -np.pi/2)
   with pytest.raises(NotImplementedError):
-    scatter_tables('exp(-(theta-theta_refl)**2)', '-pi/2, pi/2', '0, 2*pi')
-  with pytest.raises(NotImplementedError):
     scatter_tables('DiracDelta(theta-0.1)', '-pi/2, pi/2', '0, 2*pi')
+  # densities with per-hit parameters become a family over the incidence angle (one family for a mirror, two for a lens) ...
+  f = scatter_tables('exp(-(theta-theta_refl)**2/0.02)', 'pi/2, pi', '0, 2*pi', resolution=201, param_tables=11)
+  assert f.n_tables == 11 and f.first_cdf.shape == (11, 1, 201) and f.phi_cdf.shape == (11, 3)
+  g = scatter_tables('exp(-(theta-theta_refl)**2/0.02)', '0, pi/2', '0, 2*pi', resolution=201, optical_type='Lens', refractive_index=1.5, param_tables=11)
+  assert g.n_tables == 22
+  with pytest.raises(NotImplementedError):            # ... unless they also depend on phi
+    scatter_tables('exp(-(theta-theta_refl)**2)*(1+cos(phi))', '-pi/2, pi/2', '0, 2*pi')
 
 
 def test_ideal_surfaces_are_unchanged_by_no_op_densities(oracle):
@@ -100,7 +105,85 @@ def test_reference_mirror_diffuse_scene_imports_and_runs(oracle, sims):
   assert r['counts']['hits'] > 0 and r['counts']['depth_terminated'] == 0
 
 
+# ---- densities the reference re-compiles for every hit (optical_group.py:288-307) -------------------------------------
+LOBE = 'exp(-(theta-theta_refl)**2/0.02)'            # a Gaussian lobe around the specular direction, whatever the incidence
+
+
+def lobe_mirror_scene():
+  b = SceneBuilder()
+  m = b.add_group('Mirror', 'Mirror', optical_type='Mirror', record_hits=True, scatter_density=LOBE,
+                  power_theta_domain='pi/2, pi', power_phi_domain='0, 2*pi', scatter_resolution=801)
+  b.add_shape(m, prim.box(400, 400, 1), prim.translation(-200, -200, 10))
+  a = b.add_group('Abs', 'Abs', optical_type='Absorber', record_hits=True)
+  b.add_shape(a, prim.sphere(90.0), np.eye(4))
+  return b.build()
+
+
+def outgoing_theta(hits):
+  'angle between the direction AFTER the mirror (incoming direction of the second hit) and the normal along the propagation (+z)'
+  d = hits['directions'][hits['bounce'] == 1]
+  return np.arccos(np.clip(d[:, 2]/np.linalg.norm(d, axis=1), -1, 1))
+
+
+@pytest.mark.parametrize('tilt', [0.05, 0.35, 0.9, 1.2])     # (at exactly normal incidence the rotation axis n x d vanishes and nothing is rotated, as in the reference)
+def test_per_hit_density_follows_the_incidence_angle(tilt, oracle):
+  '''
+  the lobe sits at theta_refl = pi - theta_in for every incidence: the outgoing angle (measured from the normal that
+  points into the mirror) is distributed like the density evaluated at the hit's own theta_in — here the analytic
+  truncated Gaussian around pi - tilt on [pi/2, pi] — up to the half-degree grid of the family
+  '''
+  n = 40000
+  scene = lobe_mirror_scene()
+  assert scene.scatters[0].n_tables == 91
+  o_, d_ = rays(n, tilt=tilt)
+  r = oracle.trace_rays(scene, _abi.CfgArgs(max_ray_length=500, record_all_hits=True, scatter_seed=5), o_, d_, threads=0)
+  th = outgoing_theta(r['hits'])
+  assert len(th) == n
+  grid = np.linspace(np.pi/2, np.pi, 20001)
+  k = int(round(tilt/(np.pi/2)*90))                              # the family member the hit uses
+  centre = np.pi - k*(np.pi/2)/90
+  pdf = np.exp(-(grid-centre)**2/0.02)
+  cdf = np.concatenate([[0], np.cumsum((pdf[1:]+pdf[:-1])/2)]); cdf /= cdf[-1]
+  assert stats.kstest(th, lambda x: np.interp(x, grid, cdf)).pvalue > 0.01
+  assert abs(centre-(np.pi-tilt)) <= 0.5*np.pi/180+1e-12        # never more than half a degree off the hit's own angle
+
+
+@pytest.mark.reference
+def test_per_hit_density_against_the_reference_sampler(oracle):
+  'the reference compiles the density with the hit\'s parameters and draws (optical_group.py:307-308): same distribution of theta'
+  import reference_shim
+  ref = reference_shim.load()
+  tilt, n = 0.35, 40000
+  vrv = ref.distributions.VectorRandomVariable(probabilityDensity='('+LOBE+')', variableOrder=('theta', 'phi'),
+                                               variableDomains=dict(theta=(np.pi/2, np.pi), phi=(0, 2*np.pi)))
+  vrv.compile(theta_in=tilt, phi_in=0, theta_refl=np.pi-tilt, phi_refl=0)
+  np.random.seed(7)
+  want, _ = vrv.draw(N=n)
+  o_, d_ = rays(n, tilt=tilt)
+  r = oracle.trace_rays(lobe_mirror_scene(), _abi.CfgArgs(max_ray_length=500, record_all_hits=True, scatter_seed=6), o_, d_, threads=0)
+  got = outgoing_theta(r['hits'])
+  # two-sample test; the family member for 0.35 rad is 0.349 rad (0.05 degrees off)
+  assert stats.ks_2samp(got, np.asarray(want, dtype=float)).pvalue > 0.01
+
+
 # ------------------------------------------------------------------------------------------ GPU
+
+@pytest.mark.gpu
+def test_gpu_per_hit_density_equals_oracle(gpu_engine, oracle):
+  n = 30000
+  scene = lobe_mirror_scene()
+  rng = np.random.default_rng(3)
+  o_ = np.zeros((n, 3))
+  d_ = np.column_stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.5, 1.5, n), np.ones(n)])         # incidence angles from 0 to 65 degrees
+  cfg = _abi.CfgArgs(max_ray_length=500, record_all_hits=True, scatter_seed=11, hit_capacity=4*n)
+  want = oracle.trace_rays(scene, cfg, o_, d_, hit_capacity=4*n, threads=0)
+  ds = gpu_engine.scene(scene)
+  with ds.trace_rays(cfg, o_, d_) as res:
+    gh = res.hits(sort=True)
+  ds.close()
+  np.testing.assert_array_equal(gh['face_id'], want['hits']['face_id'])
+  np.testing.assert_allclose(gh['points'], want['hits']['points'], rtol=0, atol=1e-7)
+  np.testing.assert_allclose(gh['directions'], want['hits']['directions'], rtol=0, atol=1e-9)
 
 @pytest.mark.gpu
 def test_gpu_diffuse_mirror_equals_oracle(gpu_engine, oracle, sims):
