@@ -332,7 +332,7 @@ def plugin_leg(sim, eng, args, rank, world, barrier, steps):
     src = GenericSourceProxy(ctx, 0)
     per_iter = point_source.rays_per_iteration(sim.source_records[0], sim.settings)
     iterations = max(1, int(args.rays)//per_iter)
-    src.runSimulationIteration(mode='true', store=store, iterations=max(1, iterations//8)); store.flush()     # warm-up: pinned buffers, page cache
+    src.runSimulationIteration(mode='true', store=store, iterations=iterations); store.flush()     # warm-up at full size: the page-locked delivery buffers are allocated once, here
     for f in store.writtenFiles:
       os.remove(f)
     barrier()

@@ -156,7 +156,10 @@ class GenericSourceProxy:
     keys = self.context.sim.settings.get('store_hit_keys', [])
     if not len(group):
       return
-    present = np.flatnonzero(np.bincount(group, minlength=len(scene.group_names)))
+    if getattr(group, 'strides', (1,))[0] == 0:                   # one recording group, broadcast instead of a column: nothing to count
+      present = np.array([int(group[0])])
+    else:
+      present = np.flatnonzero(np.bincount(group, minlength=len(scene.group_names)))
     for gi in present:
       if len(present) == 1:
         sel = slice(None)
