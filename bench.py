@@ -490,7 +490,8 @@ def main():
       eng.free_pinned(view)
   # ---- e2e_plugin: runSimulationIteration + flush (hit files of the reference's result tree)
   plugin = None
-  if not args.no_e2e and not args.no_plugin and not binned and sim.source_records[0].get('proxy') == 'PointSourceProxy':
+  # (N = 1 only, like cpu_baseline: eight ranks writing 6 GB of hit files each into the same RAM disk measure the box, not the path)
+  if not args.no_e2e and not args.no_plugin and not binned and world == 1 and sim.source_records[0].get('proxy') == 'PointSourceProxy':
     plugin = plugin_leg(sim, eng, args, rank, world, barrier, max(1, min(args.steps, 2)))
 
   # ---- reduce over ranks: max time, summed work

@@ -437,9 +437,11 @@ __global__ void __launch_bounds__(ODW_WF4_THREADS, 1) wf_traverse4(const __grid_
     }
     __syncthreads();
   }
-  const DSphere* spheres = stage_prims ? s_spheres : p.scene.spheres;      // generic pointers: shared or global
-  const int2* sphere_info = stage_prims ? s_info : p.scene.sphere_info;
-  const int32_t* prims = stage_prims ? s_prims : p.scene.bvh4_prims;
+  // ALLSTAGED instances are launched only when the compact primitives are staged too: their pointers are known to be shared
+  // memory at compile time (LDS), the others are generic (shared or global)
+  const DSphere* spheres = (ALLSTAGED || stage_prims) ? s_spheres : p.scene.spheres;
+  const int2* sphere_info = (ALLSTAGED || stage_prims) ? s_info : p.scene.sphere_info;
+  const int32_t* prims = (ALLSTAGED || stage_prims) ? s_prims : p.scene.bvh4_prims;
   const bool filter = p.sequential || (p.ignore_mask[0] | p.ignore_mask[1] | p.ignore_mask[2] | p.ignore_mask[3]) != 0ull;
   const unsigned int lane = threadIdx.x & 31u;
   bool have = false, exhausted = false;
@@ -665,7 +667,7 @@ extern "C" cudaError_t odw_wf_traverse4(const TraceParams* p, void* pool, size_t
   wf4_layout(p->scene, &n_staged, &stage_prims, &smem);
 #define ODW_LAUNCH4(F, R, A) { cudaFuncSetAttribute(wf_traverse4<F, R, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     wf_traverse4<F, R, A><<<grid, ODW_WF4_THREADS, smem, st>>>(*p, pl, static_cast<double2*>(hits), n, fetch_counter, order, po, n_staged, stage_prims); }
-  const bool all = n_staged == p->scene.n_bvh4_nodes;
+  const bool all = n_staged == p->scene.n_bvh4_nodes && stage_prims;
   if (need & FEAT_EXT) { if (regen) ODW_LAUNCH4(FEAT_ALL, true, false) else ODW_LAUNCH4(FEAT_ALL, false, false) }
   else if (all) { if (regen) ODW_LAUNCH4(0, true, true) else ODW_LAUNCH4(0, false, true) }
   else { if (regen) ODW_LAUNCH4(0, true, false) else ODW_LAUNCH4(0, false, false) }
