@@ -1061,7 +1061,10 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   // same code) and traced as an explicit list; 48 B per ray through HBM is nothing against that.
   double* sample_buf[odw_engine::MAX_WAVE_STREAMS] = {};
   if (presample)
-    for (int i = 0; i < n_streams; ++i) { int rc = eng->alloc((void**)&sample_buf[i], (size_t)std::min<uint64_t>(wave, p.n_rays)*48); if (rc) return rc; }
+    for (int i = 0; i < n_streams; ++i) {
+      const int rc = eng->alloc((void**)&sample_buf[i], (size_t)std::min<uint64_t>(wave, p.n_rays)*48);
+      if (rc) { for (int k = 0; k < i; ++k) eng->release(sample_buf[k]); return rc; }
+    }
   uint64_t wave_index = 0;
   for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
