@@ -1156,7 +1156,7 @@ extern "C" int odw_trace_mc_host(odw_scene* sc, odw_source* src, const odw_trace
   if (cfg->n_binnings > 0) return fail(ODW_EUNSUPPORTED, "odw_trace_mc_host: use odw_trace_mc for device binning");
   odw_engine* eng = sc->eng;
   CU(cudaSetDevice(eng->device));
-  uint64_t chunk = 1ull << 23;
+  uint64_t chunk = sc->use_bvh ? (1ull << 25) : (1ull << 23);   // BVH scenes: a chunk is one wave of the wavefront path, which wants to be large
   if (const char* w = getenv("ODW_HOST_CHUNK")) { long long v = atoll(w); if (v > 0) chunk = (uint64_t)v; }
   chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(n_rays, 1));
   // cfg->hit_capacity = rows the caller expects for the WHOLE range (0: two per ray); the per-chunk device lists get the
