@@ -388,7 +388,7 @@ struct BvhBuilder {
 };
 }  // namespace
 
-static std::vector<uint32_t> build_guide(const double* cdf, int n);
+static std::vector<uint32_t> build_guide(const double* cdf, int n, int G = ODW_GUIDE);
 
 // ---- convex shells ---------------------------------------------------------------------------------------------
 // A shell bounds a convex solid iff every tangent plane of its surface is a supporting plane.  Checked on samples:
@@ -698,10 +698,10 @@ extern "C" void odw_scene_destroy(odw_scene* sc) {
   delete sc;
 }
 
-static std::vector<uint32_t> build_guide(const double* cdf, int n) {
-  std::vector<uint32_t> g(ODW_GUIDE + 1);
-  for (int k = 0; k <= ODW_GUIDE; ++k) {
-    double x = (double)k/(double)ODW_GUIDE;
+static std::vector<uint32_t> build_guide(const double* cdf, int n, int G) {
+  std::vector<uint32_t> g((size_t)G + 1);
+  for (int k = 0; k <= G; ++k) {
+    double x = (double)k/(double)G;
     const double* it = std::upper_bound(cdf, cdf + n, x);     // first element > x
     long j = (it - cdf) - 1;
     g[(size_t)k] = (uint32_t)std::max<long>(0, j);
@@ -768,7 +768,7 @@ static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw
     if ((rc = upload(eng, s->owned, eg.data(), eg.size(), &s->d.emit_guide))) { odw_source_destroy(s); return rc; }
   }
   if ((rc = upload(eng, s->owned, sd->first_cdf, (size_t)sd->n_first, &s->d.first_cdf))) { odw_source_destroy(s); return rc; }
-  std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first);
+  std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first, ODW_EMIT_GUIDE);
   if ((rc = upload(eng, s->owned, fg.data(), fg.size(), &s->d.first_guide))) { odw_source_destroy(s); return rc; }
   s->d.first_lo = sd->first_lo; s->d.first_hi = sd->first_hi; s->d.phi_lo = 0; s->d.phi_hi = ODW_TWO_PI;
   s->d.wavelength = sd->wavelength;

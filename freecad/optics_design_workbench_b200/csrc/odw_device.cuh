@@ -218,11 +218,12 @@ __device__ __forceinline__ double linspace_at(double lo, double hi, int n, int i
   return (i >= n-1) ? hi : lo + (double)i*((hi-lo)/(double)(n-1));
 }
 
-// numpy.interp(x, cdf, linspace(lo,hi,n)); guide[k] = last index with cdf[j] <= k/GUIDE
+// numpy.interp(x, cdf, linspace(lo,hi,n)); guide[k] = last index with cdf[j] <= k/G (G+1 entries; the theta table of a surface
+// source, up to 1e6 entries, has G = ODW_EMIT_GUIDE)
 __device__ __forceinline__ double interp_cdf(double x, const double* __restrict__ cdf, const uint32_t* __restrict__ guide,
-                                             int n, double lo, double hi) {
-  int k = (int)(x*(double)ODW_GUIDE);
-  if (k > ODW_GUIDE-1) k = ODW_GUIDE-1;
+                                             int n, double lo, double hi, const int G = ODW_GUIDE) {
+  int k = (int)(x*(double)G);
+  if (k > G-1) k = G-1;
   int a = (int)guide[k], b = (int)guide[k+1] + 1;     // cdf[a] <= x ; answer <= guide[k+1]
   if (b > n) b = n;
   while (b - a > 1) {
@@ -620,14 +621,15 @@ __device__ __forceinline__ void outward_normal_general(const DFace& f, const dou
 // ---- surface source (reference freecad_elements/surface_source.py:85-111,390-410,522-555) ----------------
 // point and first derivatives of the parametrisation (OCC's, see odw_face in include/odw.h)
 __device__ __forceinline__ void surface_eval(const DFace& f, double u, double v, double* P, double* du, double* dv) {
+  if (f.kind == ODW_SURF_PLANE) {
+    for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + u*f.x[i] + v*f.y[i]; du[i] = f.x[i]; dv[i] = f.y[i]; }
+    return;
+  }
   double su, cu; sincos(u, &su, &cu);
   double rad[3], tang[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { rad[i] = cu*f.x[i] + su*f.y[i]; tang[i] = -su*f.x[i] + cu*f.y[i]; }
   switch (f.kind) {
-    case ODW_SURF_PLANE:
-      for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + u*f.x[i] + v*f.y[i]; du[i] = f.x[i]; dv[i] = f.y[i]; }
-      break;
     case ODW_SURF_CYLINDER:
       for (int i = 0; i < 3; ++i) { P[i] = f.o[i] + f.p0*rad[i] + v*f.z[i]; du[i] = f.p0*tang[i]; dv[i] = f.z[i]; }
       break;

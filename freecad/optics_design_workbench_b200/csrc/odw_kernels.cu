@@ -127,15 +127,53 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
   }
 }
 
-// draws only (odw_sample_mc): same Philox counters and tables as the MC trace kernel
-__global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long long seed, unsigned long long first_ray,
+// draws only (odw_sample_mc): same Philox counters and tables as the MC trace kernel.
+// Surface sources: the three ways a point is drawn (triangle without rejection, analytic surface with natural bounds,
+// trimmed face with the loop test) differ by an order of magnitude in work, and a warp that holds all three runs them one
+// after the other.  Each block therefore picks the faces of its 256 rays first, orders the rays by face class in shared
+// memory and only then draws: warps are uniform except at the class boundaries.  The results are stored by ray index, so
+// the order inside the block does not show.
+#define ODW_SAMPLE_CLASSES 8
+__device__ __forceinline__ int emit_class(const DFace& f, int k) {
+  return (f.flags & DFACE_TRI) ? 0 : 1 + (k % (ODW_SAMPLE_CLASSES - 1));
+}
+
+#ifndef ODW_SAMPLE_MINB
+#define ODW_SAMPLE_MINB 4     // latency bound (table look-ups, fp64 trigonometry): 64 registers and 32 warps per SM measured 20 % faster than 128 and 16
+#endif
+__global__ void __launch_bounds__(256, ODW_SAMPLE_MINB) sample_kernel(DSource src, unsigned long long seed, unsigned long long first_ray,
                                                      unsigned long long n, double* first_out, double* phi_out,
                                                      double* origins, double* dirs) {
+  __shared__ int s_count[ODW_SAMPLE_CLASSES], s_base[ODW_SAMPLE_CLASSES];
+  __shared__ int s_lane[256], s_face[256];
   const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {
+  const bool surface = src.kind == ODW_SRC_SURFACE;
+  for (unsigned long long base = (unsigned long long)blockIdx.x*blockDim.x; base < n; base += stride) {
+    unsigned long long i = base + threadIdx.x;
+    int face = -1;
+    if (surface) {
+      if (threadIdx.x < ODW_SAMPLE_CLASSES) s_count[threadIdx.x] = 0;
+      __syncthreads();
+      int cls = 0, rank = 0;
+      if (i < n) {
+        double a0, a1;
+        philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, a0, a1);
+        face = pick_emit_face(src, a0);
+        cls = emit_class(src.emit_faces[face], face);
+        rank = atomicAdd(&s_count[cls], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { int acc = 0; for (int c = 0; c < ODW_SAMPLE_CLASSES; ++c) { s_base[c] = acc; acc += s_count[c]; } }
+      __syncthreads();
+      if (i < n) { s_lane[s_base[cls] + rank] = (int)threadIdx.x; s_face[s_base[cls] + rank] = face; }
+      __syncthreads();
+      const unsigned long long left = n - base;
+      if (threadIdx.x < left) { i = base + (unsigned long long)s_lane[threadIdx.x]; face = s_face[threadIdx.x]; }
+    }
+    if (i >= n) continue;
     double u0, u1, first, phi, o[3], d[3];
-    if (src.kind == ODW_SRC_SURFACE) {
-      const RayInit r = init_ray_surface(src, seed, first_ray + i, &first, &phi);
+    if (surface) {
+      const RayInit r = init_ray_surface(src, seed, first_ray + i, &first, &phi, face);
       for (int k = 0; k < 3; ++k) { o[k] = r.o[k]; d[k] = r.d[k]; }
     } else {
       philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, u0, u1);
@@ -156,7 +194,8 @@ __global__ void __launch_bounds__(256) sample_kernel(DSource src, unsigned long 
 // feature sets, everything else only with all features.  pick_feat() maps the features a launch needs to the leanest
 // instance that covers them.
 static int pick_feat(bool mc, bool bvh, int need) {
-  if (!mc || bvh) return FEAT_ALL;
+  if (bvh) return FEAT_ALL;
+  if (!mc) return (need & FEAT_EXT) ? FEAT_ALL : FEAT_ALL & ~FEAT_EXT;   // explicit rays: fans, replays, pre-sampled surface sources
   if (need == 0) return 0;
   if ((need & ~FEAT_SEQ) == 0) return FEAT_SEQ;
   if (!(need & FEAT_EXT)) return FEAT_ALL & ~FEAT_EXT;      // surface sources / device binning in scenes of ideal surfaces (BASELINE configs[4])
@@ -188,6 +227,7 @@ extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh,
   }
   if (mc) return launch_instance<true, true, FEAT_ALL>(p, blocks, smem, st);
   if (bvh) return launch_instance<false, true, FEAT_ALL>(p, blocks, smem, st);
+  if (feat == (FEAT_ALL & ~FEAT_EXT)) return launch_instance<false, false, FEAT_ALL & ~FEAT_EXT>(p, blocks, smem, st);
   return launch_instance<false, false, FEAT_ALL>(p, blocks, smem, st);
 }
 
@@ -210,6 +250,7 @@ extern "C" int odw_trace_occupancy(bool mc, bool bvh, int need, size_t smem) {
   }
   if (mc) return occupancy_instance<true, true, FEAT_ALL>(smem);
   if (bvh) return occupancy_instance<false, true, FEAT_ALL>(smem);
+  if (feat == (FEAT_ALL & ~FEAT_EXT)) return occupancy_instance<false, false, FEAT_ALL & ~FEAT_EXT>(smem);
   return occupancy_instance<false, false, FEAT_ALL>(smem);
 }
 

@@ -344,16 +344,22 @@ __device__ __noinline__ RayInit init_ray_mc(const TraceParams& p, unsigned long 
 // d = cos(theta) n + sin(theta) (cos(phi) (t x n) + sin(phi) t).  Philox purposes: 0 -> (face, theta), 1 -> (phi, -),
 // 2+k -> (u, v) of try k, 0x100+k -> acceptance uniform of try k.
 #define ODW_SURFACE_MAX_TRIES 64
-__device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long long seed, unsigned long long ray,
-                                                 double* theta_out, double* phi_out) {
-  double a0, a1, b0, b1;
-  philox_uniform2(seed, (uint32_t)s.source_id, ray, 0u, a0, a1);
-  philox_uniform2(seed, (uint32_t)s.source_id, ray, 1u, b0, b1);
-  // first face with a0 < emit_cdf[k]: the guide table brackets it (a tessellated emitter has 1e4..1e5 faces: a plain binary
-  // search is 17 dependent trips to L2)
+// first face with a0 < emit_cdf[k]: the guide table brackets it (a tessellated emitter has 1e4..1e5 faces: a plain binary
+// search is 17 dependent trips to L2)
+__device__ __forceinline__ int pick_emit_face(const DSource& s, double a0) {
   const int cell = min(ODW_EMIT_GUIDE-1, (int)(a0*(double)ODW_EMIT_GUIDE));
   int k = (int)__ldg(s.emit_guide + cell), hi = min(s.n_emit-1, (int)__ldg(s.emit_guide + cell + 1));
   while (k < hi) { const int m = (k + hi) >> 1; if (a0 < __ldg(s.emit_cdf + m)) hi = m; else k = m + 1; }
+  return k;
+}
+
+// face >= 0: the emitting face of this ray as pick_emit_face found it earlier (sample_kernel regroups rays by face class)
+__device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long long seed, unsigned long long ray,
+                                                 double* theta_out, double* phi_out, int face = -1) {
+  double a0, a1, b0, b1;
+  philox_uniform2(seed, (uint32_t)s.source_id, ray, 0u, a0, a1);
+  philox_uniform2(seed, (uint32_t)s.source_id, ray, 1u, b0, b1);
+  const int k = face >= 0 ? face : pick_emit_face(s, a0);
   const DFace& f = s.emit_faces[k];
   double P[3] = {0, 0, 0}, du[3] = {1, 0, 0}, dv[3] = {0, 1, 0};
   if (f.flags & DFACE_TRI) {
@@ -372,9 +378,10 @@ __device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long
     const bool ok = surface_draw_uv(f, w0, w1, w2, u, v);
     surface_eval(f, u, v, P, du, dv);
     if (!ok) continue;
-    if (on_trimmed_face(f, s.emit_segs, P, s.dist_tol)) break;                  // surface_source.py:399-408
+    // surface_source.py:399-408; a point drawn inside the parameter window of a face without trim loops is on the face
+    if (f.trim != ODW_TRIM_LOOPS || on_trimmed_face(f, s.emit_segs, P, s.dist_tol)) break;
   }
-  const double theta = interp_cdf(a1, s.first_cdf, s.first_guide, s.n_first, s.first_lo, s.first_hi);
+  const double theta = interp_cdf(a1, s.first_cdf, s.first_guide, s.n_first, s.first_lo, s.first_hi, ODW_EMIT_GUIDE);
   const double phi = b0*ODW_TWO_PI;                                              // surface_source.py:544
   double n[3];
   outward_normal(f, P, n);

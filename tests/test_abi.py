@@ -75,7 +75,7 @@ def test_kernel_instance_selection():
   Which instance of the trace kernel a launch gets (csrc/odw_kernels.cu pick_feat; FEAT_* bits: 1 gratings / scatter / absorption /
   aspheres, 2 surface source, 4 sequential mode, 8 device binning): the lean one only when nothing is needed, the sequential
   one for sequential mode alone, the one without FEAT_EXT for surface sources / device binning in scenes of ideal surfaces,
-  the full one otherwise and for explicit ray lists and BVH scenes.  Host logic, no GPU call.
+  the full one otherwise and for BVH scenes; explicit ray lists get the one without FEAT_EXT when they can.  Host logic, no GPU call.
   '''
   import ctypes as C
   from freecad.optics_design_workbench_b200 import engine
@@ -89,5 +89,6 @@ def test_kernel_instance_selection():
   for need in (1, 5, 3, 9, 15):
     assert L.odw_trace_instance(True, False, need) == 15, need
   for need in (0, 4, 15):
-    assert L.odw_trace_instance(False, False, need) == 15       # explicit ray lists
+    assert L.odw_trace_instance(False, False, need) == (15 if need & 1 else 14)    # explicit ray lists (fans, replays, pre-sampled surface sources)
     assert L.odw_trace_instance(True, True, need) == 15         # BVH scenes
+    assert L.odw_trace_instance(False, True, need) == 15
