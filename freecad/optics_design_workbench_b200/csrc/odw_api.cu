@@ -15,7 +15,9 @@
 extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh, int need, int blocks, size_t smem, cudaStream_t st);
 extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
                                          unsigned long long n, double* first_out, double* phi_out, double* origins,
-                                         double* dirs, int blocks, cudaStream_t st);
+                                         double* dirs, unsigned int* keys, float bound, int blocks, cudaStream_t st);
+extern "C" cudaError_t odw_sort_pairs(void* temp, size_t* temp_bytes, const unsigned int* keys_in, unsigned int* keys_out,
+                                      const unsigned int* vals_in, unsigned int* vals_out, unsigned int n, int begin_bit, int end_bit, cudaStream_t st);
 extern "C" int odw_trace_occupancy(bool mc, bool bvh, int need, size_t smem);
 extern "C" int odw_trace_threads(void);
 // wavefront kernels (odw_wavefront.cu)
@@ -1050,21 +1052,48 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
   // ordered after the memset (and, through the join of the previous request, after every kernel that used the counters).
   if (!(sc->use_bvh && sc->wavefront) && p.n_rays > 0)
     CU(cudaMemsetAsync(eng->wave_counters, 0, ((p.n_rays + wave - 1)/wave)*sizeof(unsigned long long), eng->stream));
-  if (n_streams > 1) {
-    CU(cudaEventRecord(eng->ev_fork, eng->stream));
-    for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
-  }
   // Surface sources: the emission code (face pick, area-uniform point, trim test, direction) is as large as the bounce loop, and a
   // warp of the register-resident kernel runs it whenever one of its rays ends — with rays of two or three segments the
   // kernel's instruction working set no longer fits the instruction cache (profiles/r02_v3_lines_lambertSource.txt: 58 % of the
   // stall samples are "no instruction").  The rays of a wave are therefore drawn by the sampling kernel first (all lanes in the
   // same code) and traced as an explicit list; 48 B per ray through HBM is nothing against that.
+  // The pre-sampled rays of a wave are traced in coherence order (ray_sort_key: origin cell, direction cell): a surface emits
+  // into a hemisphere from every point, so rays with neighbouring numbers have nothing in common and the lanes of a warp
+  // cull different shells and accept different faces (lambert-source: 10 of 32 lanes in the face tests).
+  // ODW_PRESAMPLE_SORT="begin,end": key bits sorted on, "0" = trace in ray order.
+  int sort_b = ODW_PRESAMPLE_SORT_BEGIN, sort_e = ODW_PRESAMPLE_SORT_END;
+  if (const char* w = getenv("ODW_PRESAMPLE_SORT")) { sort_b = sort_e = 0; sscanf(w, "%d,%d", &sort_b, &sort_e); }
+  const bool sort_rays = presample && sort_e > sort_b;
+  const uint64_t wave_cap = std::min<uint64_t>(wave, p.n_rays);
   double* sample_buf[odw_engine::MAX_WAVE_STREAMS] = {};
-  if (presample)
-    for (int i = 0; i < n_streams; ++i) {
-      const int rc = eng->alloc((void**)&sample_buf[i], (size_t)std::min<uint64_t>(wave, p.n_rays)*48);
-      if (rc) { for (int k = 0; k < i; ++k) eng->release(sample_buf[k]); return rc; }
+  unsigned int* sort_buf[odw_engine::MAX_WAVE_STREAMS] = {};     // keys, sorted keys, order: wave_cap entries each
+  void* sort_temp[odw_engine::MAX_WAVE_STREAMS] = {};
+  unsigned int* iota = nullptr;
+  size_t temp_bytes = 0;
+  auto release_buffers = [&]() {
+    for (int k = 0; k < odw_engine::MAX_WAVE_STREAMS; ++k) { eng->release(sample_buf[k]); eng->release(sort_buf[k]); eng->release(sort_temp[k]); }
+    eng->release(iota);
+  };
+  if (presample) {
+    if (sort_rays) {
+      cudaError_t es = odw_sort_pairs(nullptr, &temp_bytes, nullptr, nullptr, nullptr, nullptr, (unsigned int)wave_cap, sort_b, sort_e, eng->stream);
+      if (es != cudaSuccess) return fail(ODW_ECUDA, std::string("pre-sample sort: ") + cudaGetErrorString(es));
+      int rc = eng->alloc((void**)&iota, (size_t)wave_cap*4);
+      if (rc) return rc;
+      if ((es = odw_wf_iota(iota, (unsigned int)wave_cap, eng->stream)) != cudaSuccess) { release_buffers(); return fail(ODW_ECUDA, std::string("pre-sample sort: ") + cudaGetErrorString(es)); }
     }
+    for (int i = 0; i < n_streams; ++i) {
+      int rc = eng->alloc((void**)&sample_buf[i], (size_t)wave_cap*48);
+      if (!rc && sort_rays) rc = eng->alloc((void**)&sort_buf[i], (size_t)wave_cap*12);
+      if (!rc && sort_rays) rc = eng->alloc(&sort_temp[i], std::max<size_t>(temp_bytes, 16));
+      if (rc) { release_buffers(); return rc; }
+    }
+  }
+  // fork: after the memset of the claim counters and the iota fill, both on the engine stream
+  if (n_streams > 1) {
+    { cudaError_t e = cudaEventRecord(eng->ev_fork, eng->stream); if (e != cudaSuccess) { release_buffers(); return fail(ODW_ECUDA, cudaGetErrorString(e)); } }
+    for (int i = 1; i < n_streams; ++i) CU(cudaStreamWaitEvent(eng->wave_stream[i], eng->ev_fork, 0));
+  }
   uint64_t wave_index = 0;
   for (uint64_t off = 0; off < p.n_rays; off += wave, ++wave_index) {
     TraceParams q = p;
@@ -1091,8 +1120,15 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     if (presample) {
       double* buf = sample_buf[wave_index % (uint64_t)n_streams];            // waves of one stream run one after the other: the buffer is free again
       const int sblocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*8, std::max<uint64_t>(1, (q.n_rays + 255)/256));
-      CU(odw_launch_sample(&q.src, q.seed, q.first_ray, q.n_rays, nullptr, nullptr, buf, buf + 3*q.n_rays, sblocks, wst));
+      unsigned int* sb = sort_buf[wave_index % (uint64_t)n_streams];
+      CU(odw_launch_sample(&q.src, q.seed, q.first_ray, q.n_rays, nullptr, nullptr, buf, buf + 3*q.n_rays, sort_rays ? sb : nullptr,
+                           (float)std::max(1e-3, std::max(sc->extent, (double)q.origin_bound)), sblocks, wst));
       q.in_origins = buf; q.in_dirs = buf + 3*q.n_rays;
+      if (sort_rays) {
+        size_t tb = temp_bytes;
+        CU(odw_sort_pairs(sort_temp[wave_index % (uint64_t)n_streams], &tb, sb, sb + wave_cap, iota, sb + 2*wave_cap, (unsigned int)q.n_rays, sort_b, sort_e, wst));
+        q.in_order = sb + 2*wave_cap;
+      }
       CU(odw_launch_trace(&q, false, false, need, blocks_w, sc->smem, wst));
       if (launches) *launches += 2;
       continue;
@@ -1100,7 +1136,7 @@ static int launch_waves(odw_engine* eng, const odw_scene* sc, const TraceParams&
     CU(odw_launch_trace(&q, mc, sc->use_bvh, need, blocks_w, sc->smem, wst));
     if (launches) ++*launches;
   }
-  for (int i = 0; i < odw_engine::MAX_WAVE_STREAMS; ++i) eng->release(sample_buf[i]);   // stream order protects them: every later user is queued after the join below
+  release_buffers();   // stream order protects them: every later user is queued after the join below
   for (int i = 1; i < n_streams; ++i) { CU(cudaEventRecord(eng->ev_join[i], eng->wave_stream[i])); CU(cudaStreamWaitEvent(eng->stream, eng->ev_join[i], 0)); }
   return ODW_OK;
 }
@@ -1251,7 +1287,7 @@ extern "C" int odw_sample_mc(odw_source* src, uint64_t seed, uint64_t first_ray,
   if (origins && (rc = eng->alloc((void**)&dorg, n*24))) return rc;
   if (directions && (rc = eng->alloc((void**)&dd, n*24))) return rc;
   int blocks = (int)std::min<uint64_t>((uint64_t)eng->sm_count*8, std::max<uint64_t>(1, (n + 255)/256));
-  if (n) CU(odw_launch_sample(&src->d, seed, first_ray, n, df, dp, dorg, dd, blocks, eng->stream));
+  if (n) CU(odw_launch_sample(&src->d, seed, first_ray, n, df, dp, dorg, dd, nullptr, 1.0f, blocks, eng->stream));
   if (first_var) CU(cudaMemcpyAsync(first_var, df, n*8, cudaMemcpyDeviceToHost, eng->stream));
   if (phi) CU(cudaMemcpyAsync(phi, dp, n*8, cudaMemcpyDeviceToHost, eng->stream));
   if (origins) CU(cudaMemcpyAsync(origins, dorg, n*24, cudaMemcpyDeviceToHost, eng->stream));

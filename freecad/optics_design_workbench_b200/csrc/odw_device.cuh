@@ -130,6 +130,8 @@ struct DSource {
   double dist_tol;
 };
 #define ODW_EMIT_GUIDE 65536
+#define ODW_PRESAMPLE_SORT_BEGIN 12     // pre-sampled surface-source waves are traced in the order of these bits of ray_sort_key
+#define ODW_PRESAMPLE_SORT_END 32
 #define ODW_GUIDE 4096
 #define ODW_BVH_STACK 64           // entries of a traversal stack (the builders bound the tree depth accordingly)
 
@@ -152,6 +154,7 @@ struct TraceParams {
   const DBinning* binnings; double* bins; int32_t n_binnings;
   // explicit ray input (nullptr for MC)
   const double* in_origins; const double* in_dirs; const double* in_powers;
+  const unsigned int* in_order;      // explicit lists: the k-th claimed ray is row in_order[k] (coherence order of a pre-sampled wave), nullptr = row k
   // per-ray summary (explicit lists)
   int32_t* out_nseg; double* out_final_point; double* out_final_power; int32_t* out_final_medium;
   unsigned long long ignore_mask[4];
@@ -169,6 +172,34 @@ namespace {              // internal linkage: two translation units (odw_kernels
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
 __device__ __forceinline__ double dot3(double ax, double ay, double az, const double* b) { return ax*b[0]+ay*b[1]+az*b[2]; }
 __device__ __forceinline__ double dot3(double ax, double ay, double az, double bx, double by, double bz) { return ax*bx+ay*by+az*bz; }
+
+// Coherence key: rays that start in the same region and point the same way walk the same BVH nodes, so a warp of
+// neighbours in key order stays converged.  12 bits origin cell (16^3 grid, Morton order) above 20 bits direction (octahedral map,
+// 1024 x 1024, Morton order: a narrow beam from one point still spreads over thousands of direction cells).  Measured on hugeArray with the rays of the FIRST bounce sorted by direction on the host:
+// 1.98e9 -> 3.11e9 segments/s (tools/gpu_coherence_probe.py).
+#define ODW_SORT_KEY_BITS 32
+__device__ __forceinline__ unsigned int spread2(unsigned int x) {     // 10 bits -> every second bit
+  x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+__device__ __forceinline__ unsigned int spread3(unsigned int x) {     // 4 bits -> every third bit
+  x = (x | (x << 4)) & 0x0c3u; x = (x | (x << 2)) & 0x249u;
+  return x;
+}
+__device__ __forceinline__ unsigned int ray_sort_key(const double* point, const double* dn, float bound) {
+  const float sc = 8.0f/bound;
+  const int cx = min(15, max(0, (int)(((float)point[0] + bound)*sc)));
+  const int cy = min(15, max(0, (int)(((float)point[1] + bound)*sc)));
+  const int cz = min(15, max(0, (int)(((float)point[2] + bound)*sc)));
+  const float dx = (float)dn[0], dy = (float)dn[1], dz = (float)dn[2];
+  const float l1 = 1.0f/(fabsf(dx) + fabsf(dy) + fabsf(dz) + 1e-30f);
+  float px = dx*l1, py = dy*l1;
+  if (dz < 0) { const float qx = (1.0f - fabsf(py))*(px >= 0 ? 1.0f : -1.0f), qy = (1.0f - fabsf(px))*(py >= 0 ? 1.0f : -1.0f); px = qx; py = qy; }
+  const unsigned int ux = (unsigned int)min(1023, max(0, (int)((px + 1.0f)*512.0f)));
+  const unsigned int uy = (unsigned int)min(1023, max(0, (int)((py + 1.0f)*512.0f)));
+  const unsigned int cell = spread3((unsigned int)cx) | (spread3((unsigned int)cy) << 1) | (spread3((unsigned int)cz) << 2);
+  return (cell << 20) | spread2(ux) | (spread2(uy) << 1);
+}
 
 // Reciprocal / square root without the IEEE slow paths: MUFU seed (2^-23) + two Newton steps (~1 ulp).
 // The correctly rounded '/' and sqrt() cost ~3x the instructions and, inlined at every face test, pushed the

@@ -88,7 +88,11 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
       }
       if (pool_left) {
         const unsigned int k = __popc(need & ((1u << lane) - 1u));
-        if (!alive && k < pool_left) { i = pool_next + k; fetch_ray<MC, FEAT>(p, i, r); alive = true; }
+        if (!alive && k < pool_left) {
+          i = pool_next + k;
+          if (!MC && p.in_order) i = __ldg(p.in_order + i);
+          fetch_ray<MC, FEAT>(p, i, r); alive = true;
+        }
         const unsigned int taken = min((unsigned int)__popc(need), pool_left);
         pool_next += taken; pool_left -= taken;
       }
@@ -130,10 +134,16 @@ __global__ void __launch_bounds__(ODW_THREADS, ODW_MIN_BLOCKS) trace_kernel(cons
 // draws only (odw_sample_mc): same Philox counters and tables as the MC trace kernel.
 // Surface sources: the three ways a point is drawn (triangle without rejection, analytic surface with natural bounds,
 // trimmed face with the loop test) differ by an order of magnitude in work, and a warp that holds all three runs them one
-// after the other.  Each block therefore picks the faces of its 256 rays first, orders the rays by face class in shared
-// memory and only then draws: warps are uniform except at the class boundaries.  The results are stored by ray index, so
-// the order inside the block does not show.
+// after the other.  Each WARP therefore takes ODW_SAMPLE_SPAN consecutive rays, picks their faces first, orders the rays by
+// face class in its slice of shared memory and only then draws, 32 at a time: the lanes are in the same code except at the
+// class boundaries.  The results are stored by ray index, so the order does not show.  (Regrouping per block of 256 rays
+// instead needs four block barriers per round, and the warps with cheap classes wait at them for the warps with expensive
+// ones: 45 % of the stall samples, profiles/r02_v6_sample_*.)
 #define ODW_SAMPLE_CLASSES 8
+#ifndef ODW_SAMPLE_SPAN
+#define ODW_SAMPLE_SPAN 256     // measured on lambert-source, 2e7 rays binned in 2^21-ray waves: 64 / 128 / 256 / 512 / 1024 rays per warp 7.38 / 6.74 / 6.20 / 8.14 / 7.21 ms (512: fewer spans than resident warps; 1024: shared memory halves the occupancy)
+#endif
+static_assert(ODW_SAMPLE_CLASSES == 8 && ODW_SAMPLE_SPAN <= 8192, "class | rank << 3 must fit 16 bits");
 __device__ __forceinline__ int emit_class(const DFace& f, int k) {
   return (f.flags & DFACE_TRI) ? 0 : 1 + (k % (ODW_SAMPLE_CLASSES - 1));
 }
@@ -141,49 +151,65 @@ __device__ __forceinline__ int emit_class(const DFace& f, int k) {
 #ifndef ODW_SAMPLE_MINB
 #define ODW_SAMPLE_MINB 4     // latency bound (table look-ups, fp64 trigonometry): 64 registers and 32 warps per SM measured 20 % faster than 128 and 16
 #endif
+__device__ __forceinline__ void sample_store(unsigned long long i, double first, double phi, const double* o, const double* d,
+                                             double* first_out, double* phi_out, double* origins, double* dirs, unsigned int* keys, float bound) {
+  if (first_out) first_out[i] = first;
+  if (phi_out) phi_out[i] = phi;
+  if (origins) { origins[3*i] = o[0]; origins[3*i+1] = o[1]; origins[3*i+2] = o[2]; }
+  if (dirs) { dirs[3*i] = d[0]; dirs[3*i+1] = d[1]; dirs[3*i+2] = d[2]; }
+  if (keys) keys[i] = ray_sort_key(o, d, bound);
+}
+
 __global__ void __launch_bounds__(256, ODW_SAMPLE_MINB) sample_kernel(DSource src, unsigned long long seed, unsigned long long first_ray,
                                                      unsigned long long n, double* first_out, double* phi_out,
-                                                     double* origins, double* dirs) {
-  __shared__ int s_count[ODW_SAMPLE_CLASSES], s_base[ODW_SAMPLE_CLASSES];
-  __shared__ int s_lane[256], s_face[256];
-  const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
-  const bool surface = src.kind == ODW_SRC_SURFACE;
-  for (unsigned long long base = (unsigned long long)blockIdx.x*blockDim.x; base < n; base += stride) {
-    unsigned long long i = base + threadIdx.x;
-    int face = -1;
-    if (surface) {
-      if (threadIdx.x < ODW_SAMPLE_CLASSES) s_count[threadIdx.x] = 0;
-      __syncthreads();
-      int cls = 0, rank = 0;
-      if (i < n) {
-        double a0, a1;
-        philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, a0, a1);
-        face = pick_emit_face(src, a0);
-        cls = emit_class(src.emit_faces[face], face);
-        rank = atomicAdd(&s_count[cls], 1);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) { int acc = 0; for (int c = 0; c < ODW_SAMPLE_CLASSES; ++c) { s_base[c] = acc; acc += s_count[c]; } }
-      __syncthreads();
-      if (i < n) { s_lane[s_base[cls] + rank] = (int)threadIdx.x; s_face[s_base[cls] + rank] = face; }
-      __syncthreads();
-      const unsigned long long left = n - base;
-      if (threadIdx.x < left) { i = base + (unsigned long long)s_lane[threadIdx.x]; face = s_face[threadIdx.x]; }
-    }
-    if (i >= n) continue;
-    double u0, u1, first, phi, o[3], d[3];
-    if (surface) {
-      const RayInit r = init_ray_surface(src, seed, first_ray + i, &first, &phi, face);
-      for (int k = 0; k < 3; ++k) { o[k] = r.o[k]; d[k] = r.d[k]; }
-    } else {
+                                                     double* origins, double* dirs, unsigned int* keys, float bound) {
+  if (src.kind != ODW_SRC_SURFACE) {
+    const unsigned long long stride = (unsigned long long)gridDim.x*blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += stride) {
+      double u0, u1, first, phi, o[3], d[3];
       philox_uniform2(seed, (uint32_t)src.source_id, first_ray + i, 0u, u0, u1);
       sample_source(src, u0, u1, first, phi);
       make_ray(src, first, phi, o, d);
+      sample_store(i, first, phi, o, d, first_out, phi_out, origins, dirs, keys, bound);
     }
-    if (first_out) first_out[i] = first;
-    if (phi_out) phi_out[i] = phi;
-    if (origins) { origins[3*i] = o[0]; origins[3*i+1] = o[1]; origins[3*i+2] = o[2]; }
-    if (dirs) { dirs[3*i] = d[0]; dirs[3*i+1] = d[1]; dirs[3*i+2] = d[2]; }
+    return;
+  }
+  // per warp: faces in ray order, faces in class order (4 B each), class | rank << 3 in ray order, ray of the span in class order (2 B each)
+  extern __shared__ __align__(16) unsigned char s_sample[];
+  __shared__ int s_count[8][ODW_SAMPLE_CLASSES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int* s_face_in = reinterpret_cast<unsigned int*>(s_sample) + (size_t)warp*2*ODW_SAMPLE_SPAN;
+  unsigned int* s_face = s_face_in + ODW_SAMPLE_SPAN;
+  unsigned short* s_key = reinterpret_cast<unsigned short*>(s_sample + (size_t)8*8*ODW_SAMPLE_SPAN) + (size_t)warp*2*ODW_SAMPLE_SPAN;
+  unsigned short* s_ray = s_key + ODW_SAMPLE_SPAN;
+  const unsigned long long stride = (unsigned long long)gridDim.x*(blockDim.x >> 5)*ODW_SAMPLE_SPAN;
+  for (unsigned long long base = ((unsigned long long)blockIdx.x*(blockDim.x >> 5) + warp)*ODW_SAMPLE_SPAN; base < n; base += stride) {
+    const int span = (int)min((unsigned long long)ODW_SAMPLE_SPAN, n - base);
+    if (lane < ODW_SAMPLE_CLASSES) s_count[warp][lane] = 0;
+    __syncwarp();
+    for (int t = lane; t < span; t += 32) {
+      double a0, a1;
+      philox_uniform2(seed, (uint32_t)src.source_id, first_ray + base + t, 0u, a0, a1);
+      const int face = pick_emit_face(src, a0);
+      const int cls = emit_class(src.emit_faces[face], face);
+      const int rank = atomicAdd(&s_count[warp][cls], 1);
+      s_face_in[t] = (unsigned int)face; s_key[t] = (unsigned short)(cls | (rank << 3));
+    }
+    __syncwarp();
+    if (lane == 0) { int acc = 0; for (int c = 0; c < ODW_SAMPLE_CLASSES; ++c) { const int m = s_count[warp][c]; s_count[warp][c] = acc; acc += m; } }
+    __syncwarp();
+    for (int t = lane; t < span; t += 32) {
+      const int key = s_key[t], slot = s_count[warp][key & 7] + (key >> 3);
+      s_face[slot] = s_face_in[t]; s_ray[slot] = (unsigned short)t;
+    }
+    __syncwarp();
+    for (int t = lane; t < span; t += 32) {
+      const unsigned long long i = base + s_ray[t];
+      double first, phi;
+      const RayInit r = init_ray_surface(src, seed, first_ray + i, &first, &phi, (int)s_face[t]);
+      sample_store(i, first, phi, r.o, r.d, first_out, phi_out, origins, dirs, keys, bound);
+    }
+    __syncwarp();
   }
 }
 
@@ -233,8 +259,10 @@ extern "C" cudaError_t odw_launch_trace(const TraceParams* p, bool mc, bool bvh,
 
 extern "C" cudaError_t odw_launch_sample(const DSource* src, unsigned long long seed, unsigned long long first_ray,
                                          unsigned long long n, double* first_out, double* phi_out, double* origins,
-                                         double* dirs, int blocks, cudaStream_t st) {
-  sample_kernel<<<blocks, 256, 0, st>>>(*src, seed, first_ray, n, first_out, phi_out, origins, dirs);
+                                         double* dirs, unsigned int* keys, float bound, int blocks, cudaStream_t st) {
+  const size_t smem = src->kind == ODW_SRC_SURFACE ? (size_t)8*12*ODW_SAMPLE_SPAN : 0;      // 8 warps x (2 x 4 B + 2 x 2 B) per ray of a span
+  if (smem > 40*1024) cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_kernel<<<blocks, 256, smem, st>>>(*src, seed, first_ray, n, first_out, phi_out, origins, dirs, keys, bound);
   return cudaGetLastError();
 }
 

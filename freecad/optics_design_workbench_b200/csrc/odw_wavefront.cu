@@ -30,34 +30,7 @@ struct WfPool {
   float bound;       // origins are binned on a 16^3 grid over [-bound, bound]^3
 };
 
-// Coherence key: rays that start in the same region and point the same way walk the same BVH nodes, so a warp of
-// neighbours in key order stays converged.  12 bits origin cell (16^3 grid, Morton order) above 20 bits direction (octahedral map,
-// 1024 x 1024, Morton order: a narrow beam from one point still spreads over thousands of direction cells).  Measured on hugeArray with the rays of the FIRST bounce sorted by direction on the host:
-// 1.98e9 -> 3.11e9 segments/s (tools/gpu_coherence_probe.py).
-#define ODW_SORT_KEY_BITS 32
-__device__ __forceinline__ unsigned int spread2(unsigned int x) {     // 10 bits -> every second bit
-  x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
-  return x;
-}
-__device__ __forceinline__ unsigned int spread3(unsigned int x) {     // 4 bits -> every third bit
-  x = (x | (x << 4)) & 0x0c3u; x = (x | (x << 2)) & 0x249u;
-  return x;
-}
-__device__ __forceinline__ unsigned int ray_sort_key(const double* point, const double* dn, float bound) {
-  const float sc = 8.0f/bound;
-  const int cx = min(15, max(0, (int)(((float)point[0] + bound)*sc)));
-  const int cy = min(15, max(0, (int)(((float)point[1] + bound)*sc)));
-  const int cz = min(15, max(0, (int)(((float)point[2] + bound)*sc)));
-  const float dx = (float)dn[0], dy = (float)dn[1], dz = (float)dn[2];
-  const float l1 = 1.0f/(fabsf(dx) + fabsf(dy) + fabsf(dz) + 1e-30f);
-  float px = dx*l1, py = dy*l1;
-  if (dz < 0) { const float qx = (1.0f - fabsf(py))*(px >= 0 ? 1.0f : -1.0f), qy = (1.0f - fabsf(px))*(py >= 0 ? 1.0f : -1.0f); px = qx; py = qy; }
-  const unsigned int ux = (unsigned int)min(1023, max(0, (int)((px + 1.0f)*512.0f)));
-  const unsigned int uy = (unsigned int)min(1023, max(0, (int)((py + 1.0f)*512.0f)));
-  const unsigned int cell = spread3((unsigned int)cx) | (spread3((unsigned int)cy) << 1) | (spread3((unsigned int)cz) << 2);
-  return (cell << 20) | spread2(ux) | (spread2(uy) << 1);
-}
-
+// (coherence key: ray_sort_key, odw_device.cuh)
 struct WfRay {
   double point[3], dn[3], power, dscale;
   unsigned long long i;
@@ -711,6 +684,12 @@ extern "C" cudaError_t odw_wf_sort(void* temp, size_t* temp_bytes, void* pool, s
                                    unsigned int* order, unsigned int n, cudaStream_t st) {
   const WfPool pl = make_pool(pool, cap);
   return cub::DeviceRadixSort::SortPairs(temp, *temp_bytes, (const unsigned int*)pl.key, keys_out, iota, order, (int)n, 0, ODW_SORT_KEY_BITS, st);
+}
+
+// (key, value) pairs by bits [begin_bit, end_bit) of the key; temp == nullptr: size query
+extern "C" cudaError_t odw_sort_pairs(void* temp, size_t* temp_bytes, const unsigned int* keys_in, unsigned int* keys_out,
+                                      const unsigned int* vals_in, unsigned int* vals_out, unsigned int n, int begin_bit, int end_bit, cudaStream_t st) {
+  return cub::DeviceRadixSort::SortPairs(temp, *temp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, begin_bit, end_bit, st);
 }
 
 extern "C" int odw_wf_traverse_occupancy(int n_nodes) {

@@ -51,12 +51,18 @@ def main():
       s = sum(int(r[hdr.index(name)]) for r in b)
       if s/tots > 0.01:
         print(f'  {name:28s} {s/tots*100:5.1f}%')
-  byline, bys = collections.Counter(), collections.Counter()
+  only = os.environ.get('ODW_OPCODES')      # e.g. ODW_OPCODES=LDL,STL: attribute only these opcodes to source lines
+  if only:
+    keep = set(only.split(','))
+    pairs = [(sc, r) for sc, r in zip(seq, b) if (re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)', r[1]) or [None]*3)[2] in keep]
+    seq, b = [x[0] for x in pairs], [x[1] for x in pairs]
+  iT = hdr.index('Thread Instructions Executed')
+  byline, bys, byt = collections.Counter(), collections.Counter(), collections.Counter()
   for (ins, c), r in zip(seq, b):
-    byline[c] += int(r[iE]); bys[c] += int(r[iS])
+    byline[c] += int(r[iE]); bys[c] += int(r[iS]); byt[c] += int(r[iT])
   src = {}
   # per function: a line belongs to the last `__device__` / `__global__` definition that starts at or before it
-  byfun, byfuns = collections.Counter(), collections.Counter()
+  byfun, byfuns, byfunt = collections.Counter(), collections.Counter(), collections.Counter()
   starts = {}
   for k, c in byline.items():
     f, l = k if k else ('?', 0)
@@ -71,10 +77,10 @@ def main():
     for l0, n in starts[f]:
       if l0 <= l:
         name = n
-    byfun[(f, name)] += c; byfuns[(f, name)] += bys[k]
+    byfun[(f, name)] += c; byfuns[(f, name)] += bys[k]; byfunt[(f, name)] += byt[k]
   print('by function (inlined code is attributed to the function it was written in):')
   for (f, name), c in byfun.most_common(25):
-    print(f'  {f[:16]:16s} {name[:28]:28s} {c/tot*100:5.2f}% instr {byfuns[(f, name)]/tots*100:5.2f}% samples')
+    print(f'  {f[:16]:16s} {name[:28]:28s} {c/tot*100:5.2f}% instr {byfuns[(f, name)]/tots*100:5.2f}% samples {byfunt[(f, name)]/max(c, 1):5.1f} lanes')
   for k, c in byline.most_common(top):
     f, l = k if k else ('?', 0)
     if f not in src:
@@ -83,7 +89,7 @@ def main():
       except OSError:
         src[f] = []
     t = src[f][l-1].strip()[:100] if 0 < l <= len(src[f]) else ''
-    print(f'{f[:15]:15s} {l:4d} {c/tot*100:5.2f}% instr {bys[k]/tots*100:5.2f}% samples | {t}')
+    print(f'{f[:15]:15s} {l:4d} {c/tot*100:5.2f}% instr {bys[k]/tots*100:5.2f}% samples {byt[k]/max(c, 1):5.1f} lanes | {t}')
 
 if __name__ == '__main__':
   main()
