@@ -770,7 +770,10 @@ static int surface_source_create(odw_engine* eng, const odw_source_desc* sd, odw
     if ((rc = upload(eng, s->owned, eg.data(), eg.size(), &s->d.emit_guide))) { odw_source_destroy(s); return rc; }
   }
   if ((rc = upload(eng, s->owned, sd->first_cdf, (size_t)sd->n_first, &s->d.first_cdf))) { odw_source_destroy(s); return rc; }
-  std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first, ODW_EMIT_GUIDE);
+  int theta_cells = ODW_GUIDE;
+  while (theta_cells < sd->n_first && theta_cells < (1 << 20)) theta_cells <<= 1;
+  s->d.n_first_guide = theta_cells;
+  std::vector<uint32_t> fg = build_guide(sd->first_cdf, sd->n_first, theta_cells);
   if ((rc = upload(eng, s->owned, fg.data(), fg.size(), &s->d.first_guide))) { odw_source_destroy(s); return rc; }
   s->d.first_lo = sd->first_lo; s->d.first_hi = sd->first_hi; s->d.phi_lo = 0; s->d.phi_hi = ODW_TWO_PI;
   s->d.wavelength = sd->wavelength;

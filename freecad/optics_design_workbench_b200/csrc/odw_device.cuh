@@ -128,9 +128,10 @@ struct DSource {
   const double* emit_cdf;
   const uint32_t* emit_guide;      // [ODW_EMIT_GUIDE+1]: emit_guide[k] = first face whose cumulative weight exceeds k/ODW_EMIT_GUIDE
   double dist_tol;
+  int32_t n_first_guide, pad_;     // cells of first_guide of a surface source (a power of two near n_first: a 1e6-entry theta table is searched in <= 2 probes)
 };
 #define ODW_EMIT_GUIDE 65536
-#define ODW_PRESAMPLE_SORT_BEGIN 12     // pre-sampled surface-source waves are traced in the order of these bits of ray_sort_key
+#define ODW_PRESAMPLE_SORT_BEGIN 8      // pre-sampled surface-source waves are traced in the order of these bits of ray_sort_key (24 bits = 3 radix passes)
 #define ODW_PRESAMPLE_SORT_END 32
 #define ODW_GUIDE 4096
 #define ODW_BVH_STACK 64           // entries of a traversal stack (the builders bound the tree depth accordingly)
@@ -250,7 +251,7 @@ __device__ __forceinline__ double linspace_at(double lo, double hi, int n, int i
 }
 
 // numpy.interp(x, cdf, linspace(lo,hi,n)); guide[k] = last index with cdf[j] <= k/G (G+1 entries; the theta table of a surface
-// source, up to 1e6 entries, has G = ODW_EMIT_GUIDE)
+// source, up to 1e6 entries, has G = DSource::n_first_guide)
 __device__ __forceinline__ double interp_cdf(double x, const double* __restrict__ cdf, const uint32_t* __restrict__ guide,
                                              int n, double lo, double hi, const int G = ODW_GUIDE) {
   int k = (int)(x*(double)G);

@@ -381,7 +381,7 @@ __device__ __noinline__ RayInit init_ray_surface(const DSource& s, unsigned long
     // surface_source.py:399-408; a point drawn inside the parameter window of a face without trim loops is on the face
     if (f.trim != ODW_TRIM_LOOPS || on_trimmed_face(f, s.emit_segs, P, s.dist_tol)) break;
   }
-  const double theta = interp_cdf(a1, s.first_cdf, s.first_guide, s.n_first, s.first_lo, s.first_hi, ODW_EMIT_GUIDE);
+  const double theta = interp_cdf(a1, s.first_cdf, s.first_guide, s.n_first, s.first_lo, s.first_hi, s.n_first_guide);
   const double phi = b0*ODW_TWO_PI;                                              // surface_source.py:544
   double n[3];
   outward_normal(f, P, n);
