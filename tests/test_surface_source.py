@@ -252,3 +252,33 @@ def test_gpu_tessellated_emitter_equals_oracle(gpu_engine, oracle, sims):
   from test_gpu_parity import compare_hits
   bad = compare_hits(gh, want['hits'], n, max_bad_fraction=1e-3)
   assert abs(gc['segments']-want['counts']['segments']) <= 4*max(bad, 1)
+
+
+@pytest.mark.gpu
+def test_gpu_presampled_wave_order_does_not_show(gpu_engine, sims, monkeypatch):
+  '''
+  The rays of a surface-source wave are drawn by sample_kernel and traced in coherence order (radix sort of ray_sort_key,
+  csrc/odw_api.cu launch_waves).  Order of tracing and number of waves must not change one bit of the result (same counters, same hit rows once sorted by
+  (ray, bounce)); the in-kernel draw (ODW_NO_PRESAMPLE) gives the same rows to the last bit but one.
+  '''
+  sim = sims('lambertSource')
+  sa = sim.source_args(0)
+  n = 300000
+  cfg = sim.cfg(record_all_hits=True, hit_capacity=8*n)
+  def run():
+    with gpu_engine.scene(sim.scene).trace_mc(gpu_engine.source(sa), cfg, SEED, 12345, n) as res:
+      c = {k: v for k, v in res.counts.items() if k not in ('waves', 'sm_clock_khz')}
+      return c, res.hits(sort=True)
+  base_c, base_h = run()
+  for env in ({'ODW_PRESAMPLE_SORT': '0'}, {'ODW_PRESAMPLE_SORT': '0,32'}, {'ODW_RAYS_PER_LAUNCH': '65536'}, {'ODW_NO_PRESAMPLE': '1'}):
+    with monkeypatch.context() as m:
+      for k, v in env.items():
+        m.setenv(k, v)
+      c, h = run()
+    assert c == base_c, env
+    for k in base_h:
+      if 'ODW_NO_PRESAMPLE' in env and h[k].dtype.kind == 'f':
+        # the list kernel normalises the stored unit direction once more: a last-bit difference, nothing else
+        np.testing.assert_allclose(h[k], base_h[k], rtol=0, atol=1e-12, err_msg=k)
+      else:
+        assert np.array_equal(h[k], base_h[k]), (env, k)
