@@ -168,7 +168,8 @@ class SimulationResults:
   # batches of at least this many bytes that the caller only LENDS (views of page-locked engine buffers that the next
   # engine call overwrites) are written to their hit files at once instead of being copied into the buffer first
   DIRECT_WRITE_BYTES = 32 << 20
-  ROWS_PER_FILE = 1 << 23            # a lent batch is cut into files of at most this many hits, written by parallel threads
+  ROWS_PER_FILE = 1 << 22            # a lent batch is cut into files of at most this many hits, written by parallel threads
+  WRITER_THREADS = 32                # at most; one thread writes ~2 GB/s into a RAM disk (page allocation + copy), so the rate scales with the cores
 
   def addRayHits(self, source, obj, points, directions, powers, isEntering, metadata=None, borrowed=False):
     '''
@@ -208,7 +209,13 @@ class SimulationResults:
     directions = np.asarray(directions, dtype=np.float64).reshape(n, 3)
     powers = np.asarray(powers, dtype=np.float64).reshape(n)
     isEntering = np.asarray(isEntering).reshape(n)
-    slices = [(a, min(n, a+self.ROWS_PER_FILE)) for a in range(0, n, self.ROWS_PER_FILE)]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    workers = max(1, min(self.WRITER_THREADS, cores))
+    n_files = max(1, -(-n//self.ROWS_PER_FILE))
+    if n_files > workers:
+      n_files = -(-n_files//workers)*workers          # whole rounds of the thread pool, files of equal size
+    rows = max(1, -(-n//n_files))
+    slices = [(a, min(n, a+rows)) for a in range(0, n, rows)]
     names = []
     for _ in slices:
       self._fingerprint(fresh=True)
@@ -227,7 +234,7 @@ class SimulationResults:
     if len(slices) == 1:
       done = [write((slices[0], names[0]))]
     else:
-      with ThreadPoolExecutor(max_workers=min(8, len(slices), os.cpu_count() or 1)) as pool:
+      with ThreadPoolExecutor(max_workers=min(workers, len(slices))) as pool:
         done = list(pool.map(write, zip(slices, names)))
     self.writtenFiles.extend(done)
     self.totalRecordedHits += n

@@ -146,6 +146,44 @@ def test_writer_pads_missing_metadata_with_nan(tmp_path):
   assert st.totalRecordedHits == 3
 
 
+def test_lent_batches_are_written_in_parallel_slices_with_the_same_content(tmp_path, monkeypatch):
+  '''
+  addRayHits(..., borrowed=True) (large batches straight from the page-locked delivery buffers): the batch is cut into equally
+  sized files written by a thread pool.  Whatever the slicing, the files hold the rows of the batch once, in order, with the
+  reference's keys and dtypes (results_store.py:369-460), next to files of the buffered path.
+  '''
+  rng = np.random.default_rng(5)
+  n = 10007
+  pts, dirs, pw = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.random(n)
+  ent = (rng.random(n) > 0.5).astype(np.uint8)
+  md = dict(initTheta=rng.random(n))
+  src, obj = ('S', 'S label'), ('G', 'G label')
+  for rows, threads in ((1 << 22, 32), (1000, 3), (999, 32), (n, 1)):
+    monkeypatch.setattr(results_store.SimulationResults, 'ROWS_PER_FILE', rows)
+    monkeypatch.setattr(results_store.SimulationResults, 'WRITER_THREADS', threads)
+    monkeypatch.setattr(results_store.SimulationResults, 'DIRECT_WRITE_BYTES', 1000)     # small batches are copied into the buffer instead
+    st = results_store.SimulationResults('true', str(tmp_path/f'w{rows}-{threads}.OpticsDesign'))
+    st.addRayHits(src, obj, pts, dirs, pw, ent, md, borrowed=True)
+    st.addRayHits(src, obj, pts[:3], dirs[:3], pw[:3], ent[:3], dict(initTheta=md['initTheta'][:3]))     # buffered path
+    st.flush()
+    assert st.totalRecordedHits == n + 3
+    files = sorted(f for f in st.writtenFiles if f.endswith('-hits.pkl'))
+    assert len(set(files)) == len(files)
+    if rows < n:
+      assert len(files) >= n//rows
+      sizes = [len(pickle.load(open(f, 'rb'))['powers']) for f in files]
+      assert max(sizes) <= rows
+    got = load_hits(os.path.dirname(os.path.dirname(os.path.dirname(files[0]))))
+    assert got['source'] == 'S' and got['obj'] == 'G'
+    assert got['isEntering'].dtype == np.int64 and got['points'].dtype == np.float64
+    order = np.lexsort((got['powers'], got['initTheta']))
+    want = dict(points=np.concatenate([pts, pts[:3]]), directions=np.concatenate([dirs, dirs[:3]]), powers=np.concatenate([pw, pw[:3]]),
+                isEntering=np.concatenate([ent, ent[:3]]).astype(np.int64), initTheta=np.concatenate([md['initTheta'], md['initTheta'][:3]]))
+    worder = np.lexsort((want['powers'], want['initTheta']))
+    for k, v in want.items():
+      assert np.array_equal(got[k][order], v[worder]), (rows, threads, k)
+
+
 def test_unknown_action_and_missing_end_criterion(tmp_path, engine):
   sim = prepare(os.path.join(SCENES, 'minimal.npz'))
   with pytest.raises(ValueError):
